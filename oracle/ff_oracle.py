@@ -1,0 +1,483 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the Fireflies hot path.
+
+This module is the *oracle*: an independent CPU (torch fp32 / numpy) restatement
+of the reference algorithms on the north-star path, written from the formulas in
+SURVEY.md section 8(a).  It is NOT part of the product: ``fireflies_b200`` never
+imports it; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs do, as the checker or as the timed
+CPU baseline.
+
+Parity status: the reference ships no tests, golden vectors or fixtures
+(SURVEY.md section 4), so parity is *unpinned by the reference itself*.  We pin
+the oracle against the reference's own code executed in the build container:
+``oracle/make_golden.py`` imports ``/root/reference`` (``oracle/ref_loader.py``)
+and writes ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks every
+function here against those fixtures (and against the live reference when it is
+mounted).  Third-party arithmetic that is absent from ``/root/reference``
+(kornia 0.7.1 ``gaussian_blur2d``) is restated from its published algorithm and
+stays "parity unpinned" -- see ``gaussian_blur2d`` below.
+
+All citations are ``path:line`` relative to ``/root/reference``.
+"""
+from __future__ import annotations
+
+import math
+import random as _pyrandom
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+F32 = torch.float32
+
+
+# ----------------------------------------------------------------------------
+# a1/a2: dense splat and its reductions  (fireflies/graphics/rasterization.py:7-37,156-161)
+# ----------------------------------------------------------------------------
+def _as_ts(texture_size) -> Tuple[int, int]:
+    ts = [int(v) for v in (texture_size.tolist() if torch.is_tensor(texture_size) else texture_size)]
+    return ts[0], ts[1]
+
+
+def _sigma_f32(sigma) -> torch.Tensor:
+    if torch.is_tensor(sigma):
+        return sigma.detach().to(F32).reshape(-1)[0]
+    return torch.tensor(float(sigma), dtype=F32)
+
+
+def splat_dense(points: torch.Tensor, sigma, texture_size) -> torch.Tensor:
+    """``out[n,r,c] = exp(-(((c - p[n,0]*ts0)^2 + (r - p[n,1]*ts1)^2)/sigma)^2)``, shape ``[N, ts1, ts0]``.
+
+    Follows rasterize_points (graphics/rasterization.py:18-35): pixel centres are the
+    integer indices, ``points[:,0]`` pairs with the last (column) axis.
+    """
+    ts0, ts1 = _as_ts(texture_size)
+    scale = torch.tensor([ts0, ts1], dtype=F32)
+    P = points.to(F32) * scale                                     # :18
+    cols = torch.arange(ts0, dtype=F32).view(1, 1, ts0)            # :21-25 (second meshgrid output)
+    rows = torch.arange(ts1, dtype=F32).view(1, ts1, 1)
+    dc = cols - P[:, 0].view(-1, 1, 1)                              # :29
+    dr = rows - P[:, 1].view(-1, 1, 1)                              # :30
+    d2 = dc * dc + dr * dr                                          # :32-34
+    u = d2 / _sigma_f32(sigma)
+    return torch.exp(-(u * u))                                      # :35
+
+
+def softor(tex: torch.Tensor, dim: int = 0) -> torch.Tensor:
+    """``1 - prod(1 - g)``  (graphics/rasterization.py:156-157)."""
+    return 1 - torch.prod(1 - tex, dim=dim)
+
+
+def reduce_sum(tex: torch.Tensor, dim: int = 0) -> torch.Tensor:
+    """``sum(g)``  (graphics/rasterization.py:160-161)."""
+    return torch.sum(tex, dim=dim)
+
+
+# ----------------------------------------------------------------------------
+# a3-a5: footprint-limited ("baked") splat-reduce
+# (fireflies/graphics/rasterization.py:164-237, 240-318, 321-392, 395-472)
+# ----------------------------------------------------------------------------
+def footprint_size(sigma, num_std: int) -> Tuple[int, int]:
+    """(footprint, half) -- graphics/rasterization.py:180-182 (odd(floor(sqrt(sigma))*num_std))."""
+    root = float(torch.sqrt(_sigma_f32(sigma)).item())
+    fp = math.floor(root) * int(num_std)
+    if fp % 2 == 0:
+        fp += 1
+    return fp, int((fp - 1) / 2)
+
+
+def baked_windows(points: torch.Tensor, sigma, texture_size, num_std: int) -> torch.Tensor:
+    """Integer clip rectangles of every point's footprint: int32 ``[N, 2, 3]`` = per axis
+    ``(wo, rs, re)`` -- the texture origin, footprint start and footprint end that the
+    reference slices with (graphics/rasterization.py:199-230 / 275-304).  Axis 0 pairs with
+    ``points[:,0]`` / ``texture_size[0]``.  These are the "index outputs" of the splat path
+    and are compared bit-exactly.
+    """
+    ts0, ts1 = _as_ts(texture_size)
+    fp, half = footprint_size(sigma, num_std)
+    P = points.detach().to(F32) * torch.tensor([ts0, ts1], dtype=F32)
+    fo = torch.floor(P - half)                                      # :186 / :258
+    out = torch.zeros(P.shape[0], 2, 3, dtype=torch.int32)
+    for ax, ts in ((0, ts0), (1, ts1)):
+        wo = fo[:, ax].to(torch.int32)
+        rs = torch.where(wo < 0, wo.abs(), torch.zeros_like(wo))    # :214-220
+        wo = torch.clamp(wo, min=0)
+        re = torch.where(wo + fp >= ts, ts - wo, torch.full_like(wo, fp))  # :222-226
+        out[:, ax, 0], out[:, ax, 1], out[:, ax, 2] = wo, rs, re
+    return out
+
+
+def _footprint_values(points: torch.Tensor, sigma, texture_size, num_std: int):
+    """Per-point footprint values ``[N, fp, fp]`` (axis 1 <-> points[:,0]) and the
+    texture index of every footprint cell plus a validity mask reproducing the
+    reference's slice clipping."""
+    ts0, ts1 = _as_ts(texture_size)
+    fp, half = footprint_size(sigma, num_std)
+    P = points.to(F32) * torch.tensor([ts0, ts1], dtype=F32)       # :174
+    mid = P - torch.floor(P) + half                                 # :184 / :256
+    k = torch.arange(fp, dtype=F32)
+    d0 = k.view(1, fp, 1) - mid[:, 0].view(-1, 1, 1)                # :194 / :269
+    d1 = k.view(1, 1, fp) - mid[:, 1].view(-1, 1, 1)                # :195 / :270
+    d2 = d0 * d0 + d1 * d1
+    u = d2 / _sigma_f32(sigma)
+    vals = torch.exp(-(u * u))                                      # :197 / :273
+    win = baked_windows(points, sigma, texture_size, num_std).to(torch.int64)
+    ki = torch.arange(fp, dtype=torch.int64)
+    idx, ok = [], []
+    for ax in (0, 1):
+        wo, rs, re = win[:, ax, 0:1], win[:, ax, 1:2], win[:, ax, 2:3]
+        n = torch.clamp(re - rs, min=0)                             # slice length (empty if re<rs)
+        inside = (ki.view(1, -1) >= rs) & (ki.view(1, -1) < rs + n)
+        idx.append(wo + (ki.view(1, -1) - rs))
+        ok.append(inside)
+    tex_idx = idx[0].unsqueeze(2) * ts1 + idx[1].unsqueeze(1)       # tex is [ts0, ts1]
+    mask = ok[0].unsqueeze(2) & ok[1].unsqueeze(1)
+    mask = mask & (idx[0].unsqueeze(2) < ts0) & (idx[1].unsqueeze(1) < ts1)
+    return vals, tex_idx, mask, (ts0, ts1)
+
+
+def baked_sum(points, sigma, texture_size, num_std: int = 4, transposed: bool = False) -> torch.Tensor:
+    """Footprint-limited ``sum``.  ``transposed=False`` gives baked_sum's orientation
+    ``[ts1, ts0]`` (= ``splat_dense(...).sum(0)``, graphics/rasterization.py:237);
+    ``transposed=True`` gives baked_sum_2's ``[ts0, ts1]`` (:318)."""
+    vals, tex_idx, mask, (ts0, ts1) = _footprint_values(points, sigma, texture_size, num_std)
+    tex = torch.zeros(ts0 * ts1, dtype=F32)
+    tex = tex.index_put((tex_idx[mask],), vals[mask], accumulate=True)
+    tex = tex.view(ts0, ts1)
+    return tex if transposed else tex.T
+
+
+def baked_softor(points, sigma, texture_size, num_std: int = 5) -> torch.Tensor:
+    """Footprint-limited soft-OR, orientation ``[ts1, ts0]`` for both reference variants
+    (graphics/rasterization.py:392, 472)."""
+    vals, tex_idx, mask, (ts0, ts1) = _footprint_values(points, sigma, texture_size, num_std)
+    tex = torch.ones(ts0 * ts1, dtype=F32)
+    tex = tex.scatter_reduce(0, tex_idx[mask], 1 - vals[mask], reduce="prod", include_self=True)
+    return (1 - tex.view(ts0, ts1)).T
+
+
+def baked_sum_sequential(points, sigma, texture_size, num_std: int = 4) -> torch.Tensor:
+    """Point-by-point variant (accumulation in index order like the reference's loop,
+    graphics/rasterization.py:176-235); used on small cases to validate the scatter form."""
+    vals, tex_idx, mask, (ts0, ts1) = _footprint_values(points, sigma, texture_size, num_std)
+    tex = torch.zeros(ts0 * ts1, dtype=F32)
+    for i in range(vals.shape[0]):
+        tex = tex.index_put((tex_idx[i][mask[i]],), vals[i][mask[i]], accumulate=True)
+    return tex.view(ts0, ts1).T
+
+
+def baked_softor_sequential(points, sigma, texture_size, num_std: int = 5) -> torch.Tensor:
+    vals, tex_idx, mask, (ts0, ts1) = _footprint_values(points, sigma, texture_size, num_std)
+    tex = torch.ones(ts0 * ts1, dtype=F32)
+    for i in range(vals.shape[0]):
+        upd = torch.ones_like(tex).index_put((tex_idx[i][mask[i]],), 1 - vals[i][mask[i]])
+        tex = tex * upd
+    return (1 - tex.view(ts0, ts1)).T
+
+
+def l1_loss(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """``torch.nn.L1Loss()(a, b)`` as used by test_point_reg (graphics/rasterization.py:591-599)."""
+    return (a - b).abs().mean()
+
+
+def splat_grad_analytic(points, sigma, texture_size, g_sum, g_softor,
+                        num_std_sum: Optional[int] = None, num_std_softor: Optional[int] = None):
+    """Closed-form ``d/d points`` of ``<g_sum, S> + <g_softor, O>`` in float64:
+    ``dg/dp0 = 4 g u (c-P0) ts0 / sigma`` and ``dO/dg_n = prod_{m!=n}(1-g_m)``.
+    Independent of torch autograd; windows ``None`` = dense.  ``g_sum``/``g_softor`` are in the
+    dense ``[ts1, ts0]`` orientation."""
+    ts0, ts1 = _as_ts(texture_size)
+    sig = float(_sigma_f32(sigma))
+    P = (points.detach().to(F32) * torch.tensor([ts0, ts1], dtype=F32)).double()
+    c = torch.arange(ts0, dtype=torch.float64).view(1, 1, ts0)
+    r = torch.arange(ts1, dtype=torch.float64).view(1, ts1, 1)
+    dc = c - P[:, 0].view(-1, 1, 1)
+    dr = r - P[:, 1].view(-1, 1, 1)
+    u = (dc * dc + dr * dr) / sig
+    g = torch.exp(-u * u)
+
+    def window_mask(num_std):
+        if num_std is None:
+            return torch.ones_like(g, dtype=torch.bool)
+        win = baked_windows(points, sigma, texture_size, num_std).to(torch.int64)
+        ci = torch.arange(ts0).view(1, 1, ts0)
+        ri = torch.arange(ts1).view(1, ts1, 1)
+        lo0, n0 = win[:, 0, 0].view(-1, 1, 1), torch.clamp(win[:, 0, 2] - win[:, 0, 1], min=0).view(-1, 1, 1)
+        lo1, n1 = win[:, 1, 0].view(-1, 1, 1), torch.clamp(win[:, 1, 2] - win[:, 1, 1], min=0).view(-1, 1, 1)
+        return (ci >= lo0) & (ci < lo0 + n0) & (ri >= lo1) & (ri < lo1 + n1)
+
+    ms, mo = window_mask(num_std_sum), window_mask(num_std_softor)
+    om = torch.where(mo, 1 - g, torch.ones_like(g))
+    excl = torch.empty_like(g)
+    for n in range(g.shape[0]):
+        others = torch.cat([om[:n], om[n + 1:]], dim=0)
+        excl[n] = others.prod(dim=0) if others.shape[0] else torch.ones_like(g[0])
+    coef = torch.zeros_like(g)
+    if g_sum is not None:
+        coef = coef + ms * g_sum.double().unsqueeze(0)
+    if g_softor is not None:
+        coef = coef + mo * g_softor.double().unsqueeze(0) * excl
+    q = coef * 4.0 * g * u / sig
+    d0 = (q * dc).sum(dim=(1, 2)) * ts0
+    d1 = (q * dr).sum(dim=(1, 2)) * ts1
+    return torch.stack([d0, d1], dim=1)
+
+
+# ----------------------------------------------------------------------------
+# a14-a17: math primitives, compose, vertex transform
+# (fireflies/utils/math.py:24-60,170-175,199-235; entity/base.py:194-244; entity/mesh.py:131-165)
+# ----------------------------------------------------------------------------
+def _trig32(alpha) -> Tuple[float, float]:
+    # utils/math.py:24-60: python math.cos/sin on the fp32 angle (fp64 trig), rounded to fp32
+    a = float(alpha)
+    return math.cos(a), math.sin(a)
+
+
+def yaw(alpha) -> torch.Tensor:      # utils/math.py:24-34  (rotation about Z)
+    c, s = _trig32(alpha)
+    return torch.tensor([[c, -s, 0], [s, c, 0], [0, 0, 1]], dtype=F32)
+
+
+def pitch(alpha) -> torch.Tensor:    # utils/math.py:37-47  (rotation about Y)
+    c, s = _trig32(alpha)
+    return torch.tensor([[c, 0, s], [0, 1, 0], [-s, 0, c]], dtype=F32)
+
+
+def roll(alpha) -> torch.Tensor:     # utils/math.py:50-60  (rotation about X)
+    c, s = _trig32(alpha)
+    return torch.tensor([[1, 0, 0], [0, c, -s], [0, s, c]], dtype=F32)
+
+
+def to_mat4(m3: torch.Tensor) -> torch.Tensor:     # utils/math.py:203-209
+    out = torch.zeros(4, 4, dtype=F32)
+    out[:3, :3] = m3
+    out[3, 3] = 1.0
+    return out
+
+
+def rotation_from_sample(r: Sequence[float]) -> torch.Tensor:
+    """entity/base.py:194-207: ``Pitch(r[2]) @ Yaw(r[1]) @ Roll(r[0])`` (so ``rotate_z`` spins about Y)."""
+    return to_mat4(pitch(r[2]) @ yaw(r[1]) @ roll(r[0]))
+
+
+def translation_from_sample(t: Sequence[float]) -> torch.Tensor:   # entity/base.py:209-218
+    m = torch.eye(4, dtype=F32)
+    m[0, 3], m[1, 3], m[2, 3] = float(t[0]), float(t[1]), float(t[2])
+    return m
+
+
+def scale_from_sample(s: Sequence[float]) -> torch.Tensor:         # entity/mesh.py:131-139
+    m = torch.eye(4, dtype=F32)
+    m[0, 0], m[1, 1], m[2, 2] = float(s[0]), float(s[1]), float(s[2])
+    return m
+
+
+def centroid_mat(c: Sequence[float]) -> torch.Tensor:              # entity/base.py:43,51-54
+    m = torch.zeros(4, 4, dtype=F32)
+    m[0, 3], m[1, 3], m[2, 3] = float(c[0]), float(c[1]), float(c[2])
+    return m
+
+
+def compose_world(t, r, s, centroid, world, has_scale: bool) -> torch.Tensor:
+    """``(T + C) @ R [@ S] @ W``  (entity/mesh.py:145-150 with scale, entity/base.py:224-228 without)."""
+    m = (translation_from_sample(t) + centroid_mat(centroid)) @ rotation_from_sample(r)
+    if has_scale:
+        m = m @ scale_from_sample(s)
+    return m @ world.to(F32)
+
+
+def chain_world(locals_: List[torch.Tensor], parent: Sequence[int]) -> List[torch.Tensor]:
+    """``world = parent.world() @ local`` recursively (entity/base.py:239-244); parent[i] = -1 for roots."""
+    out: List[Optional[torch.Tensor]] = [None] * len(locals_)
+
+    def rec(i):
+        if out[i] is None:
+            out[i] = locals_[i].clone() if parent[i] < 0 else rec(parent[i]) @ locals_[i]
+        return out[i]
+
+    return [rec(i) for i in range(len(locals_))]
+
+
+def transform_points(points: torch.Tensor, T: torch.Tensor) -> torch.Tensor:
+    """utils/math.py:220-228: homogeneous ``T @ [x,y,z,1]`` then divide by w."""
+    ph = torch.cat([points.to(F32), torch.ones(points.shape[0], 1, dtype=F32)], dim=1)
+    q = torch.matmul(T.to(F32).unsqueeze(0), ph.unsqueeze(-1)).squeeze(-1)
+    return q[:, :3] / q[:, 3:4]
+
+
+def transform_directions(dirs: torch.Tensor, T: torch.Tensor) -> torch.Tensor:
+    """utils/math.py:231-235: ``T @ [x,y,z,0]``, no divide."""
+    dh = torch.cat([dirs.to(F32), torch.zeros(dirs.shape[0], 1, dtype=F32)], dim=1)
+    q = torch.matmul(T.to(F32).unsqueeze(0), dh.unsqueeze(-1)).squeeze(-1)
+    return q[:, :3]
+
+
+def uniform_between(a: torch.Tensor, b: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+    """utils/math.py:170-175 with the ``torch.rand`` variates ``u`` injected: ``u*(b-a)+a``."""
+    assert a.shape == b.shape
+    return u.to(F32) * (b.to(F32) - a.to(F32)) + a.to(F32)
+
+
+# ----------------------------------------------------------------------------
+# a11-a13: sampler state machines, reproducing the aliasing quirks
+# (fireflies/sampling/base.py:54-74, uniform_scalar_to_vec3.py:18-38, animation.py:27-45)
+# ----------------------------------------------------------------------------
+class EvalStepper:
+    """Bit-reproduction of ``Sampler.sample_eval`` (sampling/base.py:64-74) *including* its
+    aliasing: the returned value is the post-increment ``_current_step``; on wrap
+    ``_current_step`` aliases ``_min_range`` so later increments drift the range itself and
+    wrapping is decided against the (un-drifted) ``_max_range``.  ``start`` is the value
+    ``_current_step`` was cloned from at construction (sampling/base.py:26-30)."""
+
+    def __init__(self, min_range, max_range, start, step: float = 0.01):
+        self.min = torch.as_tensor(min_range, dtype=F32).clone().reshape(-1)
+        self.max = torch.as_tensor(max_range, dtype=F32).clone().reshape(-1)
+        self.cur = torch.as_tensor(start, dtype=F32).clone().reshape(-1)
+        self.step = step
+        self.aliased = False
+
+    def sample(self) -> torch.Tensor:
+        if bool((self.min == self.max).all()):                      # :65-66
+            return self.min.clone()
+        self.cur += self.step                                       # :68-69 (alias -> post-increment)
+        if self.aliased:
+            self.min = self.cur                                     # same storage in the reference
+        ret = self.cur
+        if bool((self.cur > self.max).any()):                       # :71-72
+            self.cur = self.min
+            self.aliased = True
+            # reference returns the tensor object that held the overflowing value
+        return ret.clone()
+
+
+class AnimationStepper:
+    """sampling/animation.py:27-37: eval walks ``min..max`` inclusive; train = ``random.randint``."""
+
+    def __init__(self, min_train, max_train, min_eval, max_eval, step: int = 1):
+        self.min_train, self.max_train = int(min_train), int(max_train)
+        self.min_eval, self.max_eval = int(min_eval), int(max_eval)
+        self.step = int(step)
+        self.cur = int(min_eval)
+
+    def sample_eval(self) -> int:
+        s = self.cur
+        self.cur += self.step
+        if self.cur > self.max_eval:
+            self.cur = self.min_eval
+        return s
+
+    def sample_train(self, rng: _pyrandom.Random = _pyrandom) -> int:
+        return rng.randint(self.min_train, self.max_train - 1)
+
+
+# ----------------------------------------------------------------------------
+# a8/a9: laser <-> NDC glue  (fireflies/projection/laser.py:19-37,199-206,262-296; utils/io.py:14-68)
+# ----------------------------------------------------------------------------
+def build_projection_matrix(fov_deg: float, near: float, far: float) -> torch.Tensor:
+    """utils/io.py:14-68 (pytorch3d-style K mapping to NDC [-1,1]); Mitsuba-free stand-in."""
+    K = torch.zeros(4, 4, dtype=F32)
+    t = torch.tan(torch.tensor((math.pi / 180) * fov_deg) / 2.0)
+    max_y = t * near
+    min_y = -max_y
+    max_x = max_y * 1.0
+    min_x = -max_x
+    K[0, 0] = 2.0 * near / (max_x - min_x)
+    K[1, 1] = 2.0 * near / (max_y - min_y)
+    K[0, 2] = (max_x + min_x) / (max_x - min_x)
+    K[1, 2] = (max_y + min_y) / (max_y - min_y)
+    K[3, 2] = -1.0
+    K[2, 2] = -1.0 * far / (far - near)
+    K[2, 3] = -(far * near) / (far - near)
+    return K
+
+
+def uniform_rays(angle: float, nx: int, ny: int) -> torch.Tensor:
+    """projection/laser.py:19-37 -- row index is ``x*nx + y`` (only a bijection for nx == ny)."""
+    rays = torch.zeros(nx * ny, 3, dtype=F32)
+    for x in range(nx):
+        for y in range(ny):
+            rays[x * nx + y] = torch.tensor(
+                [math.tan((x - (nx - 1) / 2) * angle), math.tan((y - (ny - 1) / 2) * angle), -1.0])
+    return rays / torch.linalg.norm(rays, dim=-1, keepdim=True)
+
+
+_FLIP_Y = torch.diag(torch.tensor([1.0, -1.0, 1.0, 1.0]))
+
+
+def rays_to_ndc(rays: torch.Tensor, K: torch.Tensor) -> torch.Tensor:
+    """projection/laser.py:262-275."""
+    return transform_points(rays, K.to(F32) @ _FLIP_Y)
+
+
+def ndc_to_world(points: torch.Tensor, K: torch.Tensor) -> torch.Tensor:
+    """projection/laser.py:277-290."""
+    return transform_points(points, (K.to(F32) @ _FLIP_Y).inverse())
+
+
+def clamp_to_fov(rays: torch.Tensor, K: torch.Tensor, clamp_val: float = 0.95) -> torch.Tensor:
+    """projection/laser.py:199-206 (returns the new, renormalised rays)."""
+    ndc = rays_to_ndc(rays, K)
+    ndc[:, 0:2] = torch.clamp(ndc[:, 0:2], 1 - clamp_val, clamp_val)
+    w = ndc_to_world(ndc, K)
+    return w / torch.linalg.norm(w, dim=-1, keepdim=True)
+
+
+# ----------------------------------------------------------------------------
+# a19-a21: post-processing  (fireflies/postprocessing/*.py; kornia 0.7.1 restated)
+# ----------------------------------------------------------------------------
+def gaussian_kernel1d(ksize: int, sigma: float) -> torch.Tensor:
+    """kornia 0.7.1 ``get_gaussian_kernel1d``: ``x = i - k//2`` (+0.5 for even k),
+    ``exp(-x^2 / (2 sigma^2))`` normalised to sum 1.  Third-party, absent here: parity unpinned."""
+    x = torch.arange(ksize, dtype=F32) - ksize // 2
+    if ksize % 2 == 0:
+        x = x + 0.5
+    g = torch.exp(-x.pow(2.0) / (2 * float(sigma) ** 2))
+    return g / g.sum()
+
+
+def gaussian_blur2d(img: torch.Tensor, kernel_size: Tuple[int, int], sigma: Tuple[float, float]) -> torch.Tensor:
+    """kornia 0.7.1 ``filters.gaussian_blur2d(x, (ky,kx), (sy,sx))`` with its defaults
+    ``border_type='reflect'``, ``separable=True`` -- restated as reflect padding followed by a
+    horizontal then a vertical 1-D correlation (postprocessing/gauss_blur.py:18-28 call site).
+    ``img`` is ``[..., H, W]``."""
+    ky, kx = int(kernel_size[0]), int(kernel_size[1])
+    sy, sx = float(sigma[0]), float(sigma[1])
+    lead = img.shape[:-2]
+    x = img.to(F32).reshape(-1, 1, img.shape[-2], img.shape[-1])
+    wx = gaussian_kernel1d(kx, sx).view(1, 1, 1, kx)
+    wy = gaussian_kernel1d(ky, sy).view(1, 1, ky, 1)
+    x = torch.nn.functional.pad(x, (kx // 2, (kx - 1) // 2, 0, 0), mode="reflect")
+    x = torch.nn.functional.conv2d(x, wx)
+    x = torch.nn.functional.pad(x, (0, 0, ky // 2, (ky - 1) // 2), mode="reflect")
+    x = torch.nn.functional.conv2d(x, wy)
+    return x.reshape(*lead, x.shape[-2], x.shape[-1])
+
+
+def white_noise(img: np.ndarray, noise: np.ndarray) -> np.ndarray:
+    """postprocessing/white_noise.py:16-20 with the normal variates injected (already scaled
+    by ``mean``/``std``): fp64 draw added into the fp32 image, then clip to [0,1]."""
+    out = img.astype(np.float32, copy=True)
+    out += noise
+    return np.clip(out, 0, 1)
+
+
+def post_process(img: np.ndarray, blur: Optional[dict], noise: Optional[dict], gates: Sequence[bool],
+                 noise_values: Optional[np.ndarray] = None) -> np.ndarray:
+    """PostProcessor.post_process (postprocessing/postprocessor.py:14-19) for the chain
+    ``[GaussianBlur, WhiteNoise]`` with the Bernoulli gates (postprocessing/base.py:10-14) injected."""
+    out = img.copy()
+    gi = 0
+    if blur is not None:
+        if gates[gi]:
+            out = gaussian_blur2d(torch.tensor(out), blur["kernel_size"], blur["sigma"]).numpy()
+        gi += 1
+    if noise is not None:
+        if gates[gi]:
+            out = white_noise(out, noise_values)
+        gi += 1
+    return out
+
+
+def bernoulli_gates(probabilities: Sequence[float], rng: _pyrandom.Random) -> List[bool]:
+    """postprocessing/base.py:10-11: one ``random.uniform(0,1) < p`` per function, in chain order."""
+    return [rng.uniform(0, 1) < p for p in probabilities]

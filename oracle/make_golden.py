@@ -1,0 +1,295 @@
+"""TEST INFRASTRUCTURE ONLY -- writes ``tests/golden/*.npz`` by running the REAL reference
+(``/root/reference``, imported through ``oracle/ref_loader.py``) on CPU.
+
+Run in the build container only:  ``python oracle/make_golden.py``.
+The fixtures pin ``oracle/ff_oracle.py`` (and, on the GPU box, the CUDA path) to outputs of
+the reference's own code, because the reference ships no tests or golden vectors of its own.
+"""
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+CPU = torch.device("cpu")
+
+
+def npy(t):
+    return t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+
+
+def splat_case(ff, name, points, sigma, ts, store_full=True, stride=1):
+    """dense + all four baked variants + L1 / weighted-sum gradients from the reference."""
+    R = ff.graphics.rasterization
+    tsz = torch.tensor(ts)
+    sig_t = torch.tensor([float(sigma)])
+    out = {"points": npy(points), "sigma": np.float32(sigma), "texture_size": np.array(ts)}
+    n, h, w = points.shape[0], ts[1], ts[0]
+    if n * h * w <= 30_000_000:
+        p = points.clone().requires_grad_(True)
+        dense = R.rasterize_points(p, float(sigma), tsz, device=CPU)
+        S, O = R.sum(dense), R.softor(dense)
+        loss = torch.nn.L1Loss()(O, S)
+        loss.backward()
+        out.update(dense_sum=npy(S)[::stride, ::stride], dense_softor=npy(O)[::stride, ::stride],
+                   dense_l1=npy(loss), dense_l1_grad=npy(p.grad))
+        if store_full and n <= 4:
+            out["dense"] = npy(dense)
+        g = torch.Generator().manual_seed(7)
+        wS, wO = torch.randn(h, w, generator=g), torch.randn(h, w, generator=g)
+        if stride == 1:
+            out.update(wS=npy(wS), wO=npy(wO))   # else: regenerate in the test with torch.Generator().manual_seed(7)
+        p = points.clone().requires_grad_(True)
+        dense = R.rasterize_points(p, float(sigma), tsz, device=CPU)
+        ((R.sum(dense) * wS).sum() + (R.softor(dense) * wO).sum()).backward()
+        out["dense_weighted_grad"] = npy(p.grad)
+    else:
+        g = torch.Generator().manual_seed(7)
+        wS, wO = torch.randn(h, w, generator=g), torch.randn(h, w, generator=g)
+    # baked variants (sigma must be a tensor for these)
+    b1 = R.baked_sum(points, sig_t, tsz, device=CPU)
+    b2 = R.baked_sum_2(points, sig_t, tsz, device=CPU)
+    o1 = R.baked_softor(points, sig_t, tsz, device=CPU)
+    o2 = R.baked_softor_2(points, sig_t, tsz, device=CPU)
+    out.update(baked_sum=npy(b1)[::stride, ::stride], baked_sum_2=npy(b2)[::stride, ::stride],
+               baked_softor=npy(o1)[::stride, ::stride], baked_softor_2=npy(o2)[::stride, ::stride],
+               baked_sum_total=np.float64(npy(b1).astype(np.float64).sum()),
+               baked_softor_total=np.float64(npy(o1).astype(np.float64).sum()))
+    # the in-tree pattern-optimisation step (rasterization.py:589-600)
+    p = points.clone().requires_grad_(True)
+    summed = R.baked_sum_2(p, sig_t, tsz, device=CPU)
+    softored = R.baked_softor_2(p, sig_t, tsz, device=CPU)
+    loss = torch.nn.L1Loss()(softored, summed) if ts[0] == ts[1] else torch.nn.L1Loss()(softored, summed.T)
+    loss.backward()
+    out.update(baked_l1=npy(loss), baked_l1_grad=npy(p.grad))
+    # weighted: <wS, baked_sum> + <wO, baked_softor_2>, weights in the dense orientation
+    p = points.clone().requires_grad_(True)
+    L = (R.baked_sum_2(p, sig_t, tsz, device=CPU).T * wS).sum() + (R.baked_softor_2(p, sig_t, tsz, device=CPU) * wO).sum()
+    L.backward()
+    out["baked_weighted_grad"] = npy(p.grad)
+    out["stride"] = np.int64(stride)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
+
+
+def transform_cases(ff):
+    Mesh = ff.entity.Mesh
+    US = ff.sampling.UniformSampler
+    out = {}
+    # KAT2: fixed samplers
+    verts = torch.tensor([[1.0, 2.0, 3.0], [-1.0, 0.5, 0.25]])
+    m = Mesh("m", verts, device=CPU)
+    m.set_centroid(torch.tensor([[0.5, -0.5, 2.0]]))
+    m.set_rotation_sampler(US(torch.tensor([0.1, 0.2, 0.3]), torch.tensor([0.1, 0.2, 0.3]), device=CPU))
+    m.set_translation_sampler(US(torch.tensor([1.0, 2.0, 3.0]), torch.tensor([1.0, 2.0, 3.0]), device=CPU))
+    m.set_scale_sampler(US(torch.tensor([2.0, 1.0, 0.5]), torch.tensor([2.0, 1.0, 0.5]), device=CPU))
+    m.set_randomizable(True)
+    m.train()
+    m.randomize()
+    out.update(kat2_verts=npy(verts), kat2_world=npy(m.world()), kat2_out=npy(m.get_randomized_vertices()))
+
+    # seeded random T/R/S with a non-identity world, 8 successive draws; u variates replayed
+    g = torch.Generator().manual_seed(11)
+    verts = torch.rand(257, 3, generator=g) * 2 - 1
+    W0 = torch.eye(4)
+    W0[:3, :3] = torch.tensor([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]]) * 1.5
+    W0[:3, 3] = torch.tensor([0.3, -0.2, 0.1])
+    m = Mesh("r", verts, device=CPU)
+    m.set_world(W0)
+    m.set_centroid(torch.tensor([[0.25, 0.5, -0.75]]))
+    m.rotate(torch.tensor([-0.5, -1.0, -3.0]), torch.tensor([0.5, 1.0, 3.0]))
+    m.translate(torch.tensor([-1.0, -2.0, -3.0]), torch.tensor([1.0, 2.0, 3.0]))
+    m.scale(torch.tensor([0.5, 0.8, 1.0]), torch.tensor([2.0, 1.2, 3.0]))
+    m.train()
+    torch.manual_seed(1234)
+    worlds, outs = [], []
+    for _ in range(8):
+        m.randomize()
+        worlds.append(npy(m.world()))
+        outs.append(npy(m.get_randomized_vertices()))
+    torch.manual_seed(1234)
+    u = torch.stack([torch.rand(3) for _ in range(8 * 3)]).view(8, 3, 3)   # draw order T, R, S (SURVEY KAT5)
+    out.update(rand_verts=npy(verts), rand_world0=npy(W0), rand_centroid=np.array([0.25, 0.5, -0.75], np.float32),
+               rand_min=np.array([[-1, -2, -3], [-0.5, -1, -3], [0.5, 0.8, 1.0]], np.float32),
+               rand_max=np.array([[1, 2, 3], [0.5, 1, 3], [2.0, 1.2, 3.0]], np.float32),
+               rand_u=npy(u), rand_worlds=np.stack(worlds), rand_outs=np.stack(outs))
+
+    # parent -> child chain (examples/03_parent_child.py), rotate_z on the parent, eval mode
+    g = torch.Generator().manual_seed(12)
+    va, vb = torch.rand(33, 3, generator=g), torch.rand(17, 3, generator=g)
+    a, b = Mesh("a", va, device=CPU), Mesh("b", vb, device=CPU)
+    a.set_centroid(torch.tensor([[1.0, 0.0, 0.0]]))
+    b.set_centroid(torch.tensor([[0.0, 2.0, 0.0]]))
+    b.setParent(a)
+    b.set_randomizable(True)
+    a.rotate_z(-np.pi, np.pi)
+    a.eval(); b.eval()
+    cw, cv, rot = [], [], []
+    for _ in range(5):
+        a.randomize(); b.randomize()
+        rot.append(npy(a._sampled_rotation).copy())
+        cw.append(np.stack([npy(a.world()), npy(b.world())]))
+        cv.append(npy(b.get_randomized_vertices()))
+    out.update(chain_va=npy(va), chain_vb=npy(vb), chain_rot=np.stack(rot), chain_worlds=np.stack(cw),
+               chain_child_verts=np.stack(cv))
+
+    # non-mesh Transformable (no scale) + attribute draws (entity/base.py:220-234)
+    t = ff.entity.Transformable("light", device=CPU)
+    t.set_world(W0.clone())
+    t.rotate_x(-0.3, 0.3)
+    t.translate_y(-1.0, 1.0)
+    t.add_float_key("power", 1.0, 3.0)
+    t.add_vec3_key("color", torch.tensor([0.0, 0.1, 0.2]), torch.tensor([1.0, 0.9, 0.8]))
+    t.add_vec3_sampler("intensity", ff.sampling.UniformScalarToVec3Sampler(0.1, 10.0, device=CPU))
+    t.train()
+    torch.manual_seed(99)
+    tw, tf, tv, ti = [], [], [], []
+    for _ in range(4):
+        t.randomize()
+        tw.append(npy(t.world()))
+        tf.append(npy(t.get_randomized_float_attributes()["power"]).copy())
+        tv.append(npy(t.get_randomized_vec3_attributes()["color"]).copy())
+        ti.append(npy(t.get_randomized_vec3_attributes()["intensity"]).copy())
+    torch.manual_seed(99)
+    us = []
+    for _ in range(4):   # draw order: translation(3), rotation(3), power(1), color(3), intensity(1)
+        us.append(np.concatenate([npy(torch.rand(3)), npy(torch.rand(3)), npy(torch.rand(1)), npy(torch.rand(3)), npy(torch.rand(1))]))
+    out.update(tr_world0=npy(W0), tr_worlds=np.stack(tw), tr_power=np.stack(tf), tr_color=np.stack(tv),
+               tr_intensity=np.stack(ti), tr_u=np.stack(us))
+
+    # transform_points / transform_directions with a projective matrix
+    g = torch.Generator().manual_seed(13)
+    pts = torch.rand(101, 3, generator=g) * 4 - 2
+    K = ff.utils.io.build_projection_matrix(60, 0.01, 1000.0, device=CPU) if hasattr(ff.utils, "io") else None
+    if K is None:
+        import fireflies.utils.io as io
+        K = io.build_projection_matrix(60, 0.01, 1000.0, device=CPU)
+    out.update(tp_pts=npy(pts), tp_K=npy(K), tp_out=npy(ff.utils.math.transform_points(pts, K)),
+               td_out=npy(ff.utils.math.transform_directions(pts, W0)))
+    np.savez_compressed(os.path.join(OUT, "transforms.npz"), **out)
+    print("wrote transforms")
+
+
+def sampler_cases(ff):
+    S = ff.sampling
+    out = {}
+    # KAT4: eval stepping with aliasing
+    us = S.UniformSampler(torch.zeros(3), torch.zeros(3), device=CPU)
+    us.get_min()[2], us.get_max()[2] = -np.pi, np.pi     # what rotate_z(-pi, pi) does
+    us.eval()
+    out["eval_vec3"] = np.stack([npy(us.sample()).copy() for _ in range(12)])
+    sc = S.UniformSampler(0.0, 0.05, device=CPU)
+    sc.eval()
+    out["eval_scalar"] = np.stack([npy(sc.sample()).copy() for _ in range(14)])
+    v3 = S.UniformSampler(torch.tensor([0.0, 1.0, -1.0]), torch.tensor([0.035, 1.5, 0.0]), device=CPU)
+    v3.eval()
+    out["eval_vec3_ranged"] = np.stack([npy(v3.sample()).copy() for _ in range(12)])
+    s2v = S.UniformScalarToVec3Sampler(0.1, 10.0, device=CPU)
+    s2v.eval()
+    out["eval_s2v"] = np.stack([npy(s2v.sample()).copy() for _ in range(4)])
+    an = S.AnimationSampler(0, 5, 0, 5, device=CPU)
+    an.eval()
+    out["anim_eval"] = np.array([an.sample() for _ in range(9)], np.int64)
+    an.train()
+    random.seed(1)
+    out["anim_train_seed1"] = np.array([an.sample() for _ in range(5)], np.int64)
+    # train-mode uniform draws with their u variates
+    tr = S.UniformSampler(torch.tensor([-1.0, 0.0, 2.0]), torch.tensor([1.0, 0.5, 2.0]), device=CPU)
+    torch.manual_seed(5)
+    out["train_uniform"] = np.stack([npy(tr.sample()) for _ in range(6)])
+    torch.manual_seed(5)
+    out["train_uniform_u"] = np.stack([npy(torch.rand(3)) for _ in range(6)])
+    np.savez_compressed(os.path.join(OUT, "samplers.npz"), **out)
+    print("wrote samplers")
+
+
+def laser_cases(ff):
+    import fireflies.utils.io as io
+    Laser = ff.projection.Laser
+    out = {}
+    rays = Laser.generate_uniform_rays(0.0275, 18, 18, device=CPU)
+    K = io.build_projection_matrix(60, 0.01, 1000.0, device=CPU)
+    tr = ff.entity.Transformable("projector", device=CPU)
+    laser = Laser(tr, rays, K, 60.0, 0.01, 1000.0, device=CPU)
+    ndc = laser.projectRaysToNDC()
+    back = laser.projectNDCPointsToWorld(ndc.clone())
+    out.update(rays=npy(rays), K=npy(K), ndc=npy(ndc), back=npy(back))
+    # clamp_to_fov expects NDC in [0,1]: use a K that maps there (0.5*x+0.5)
+    A = torch.tensor([[0.5, 0, 0, 0.5], [0, 0.5, 0, 0.5], [0, 0, 1.0, 0], [0, 0, 0, 1.0]])
+    K01 = A @ K
+    wide = Laser.generate_uniform_rays(0.09, 9, 9, device=CPU)
+    laser2 = Laser(tr, wide.clone(), K01, 60.0, 0.01, 1000.0, device=CPU)
+    ndc2 = laser2.projectRaysToNDC()
+    laser2.clamp_to_fov()
+    out.update(K01=npy(K01), wide=npy(wide), wide_ndc=npy(ndc2), wide_clamped=npy(laser2._rays))
+    tex = laser.generateTexture(10.0, torch.tensor([64, 48]))
+    pts01 = (ndc[:, 0:2] * 0.5 + 0.5)
+    out.update(gen_tex_sum=npy(tex.sum(0)), pts01=npy(pts01))
+    np.savez_compressed(os.path.join(OUT, "laser.npz"), **out)
+    print("wrote laser")
+
+
+def post_cases(ff):
+    P = ff.postprocessing
+    out = {}
+    g = np.random.default_rng(3)
+    img = g.random((37, 53), dtype=np.float32)
+    wn = P.WhiteNoise(0.02, 0.05, 1.0)
+    np.random.seed(21)
+    res = wn.post_process(img.copy())
+    np.random.seed(21)
+    noise = np.random.normal(np.ones_like(img) * 0.02, np.ones_like(img) * 0.05)
+    out.update(img=img, wn_out=res, wn_noise=noise)
+    # gates: random.uniform(0,1) < p per function, chain order (postprocessing/base.py:10-14)
+    random.seed(6)
+    calls = []
+
+    class Probe(P.BasePostProcessingFunction):
+        def __init__(self, p, tag):
+            super().__init__(p)
+            self.tag = tag
+
+        def post_process(self, image):
+            calls.append(self.tag)
+            return image
+
+    pp = P.PostProcessor([Probe(0.5, 0), Probe(0.5, 1)])
+    gates = []
+    for _ in range(16):
+        calls.clear()
+        pp.post_process(img)
+        gates.append([0 in calls, 1 in calls])
+    out["gates_seed6"] = np.array(gates)
+    np.savez_compressed(os.path.join(OUT, "postprocess.npz"), **out)
+    print("wrote postprocess")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    ff = ref_loader.load()
+    # KAT1: point 2 exactly on pixel (3,4) -> g == 1
+    splat_case(ff, "splat_kat1", torch.tensor([[0.25, 0.75], [0.5, 0.5]]), 4.0, [8, 6])
+    g = torch.Generator().manual_seed(0)
+    pts = torch.rand(24, 2, generator=g)
+    pts[0] = torch.tensor([0.004, 0.5]); pts[1] = torch.tensor([0.5, 0.996]); pts[2] = torch.tensor([0.999, 0.001])
+    pts[3] = torch.tensor([0.5, 0.5])    # exactly on a pixel centre for even sizes
+    splat_case(ff, "splat_small_rect", pts, 9.0, [48, 40])
+    g = torch.Generator().manual_seed(1)
+    splat_case(ff, "splat_mid", torch.rand(64, 2, generator=g) * 0.96 + 0.02, 30.0, [128, 128])
+    g = torch.Generator().manual_seed(0)
+    splat_case(ff, "splat_c1", torch.rand(100, 2, generator=g) * 0.8 + 0.1, 100.0, [512, 512], stride=8)
+    transform_cases(ff)
+    sampler_cases(ff)
+    laser_cases(ff)
+    post_cases(ff)
+
+
+if __name__ == "__main__":
+    main()
