@@ -1,0 +1,313 @@
+// Image-space post-processing for sm_100a: separable Gaussian blur (reflect border) fused with white
+// noise + clip, per-frame Bernoulli gates.
+//
+// Replaces (reference paths relative to the Fireflies tree):
+//   fireflies/postprocessing/gauss_blur.py:18-28   GaussianBlur.post_process -> kornia.filters.gaussian_blur2d
+//   fireflies/postprocessing/white_noise.py:16-20  WhiteNoise.post_process
+//   fireflies/postprocessing/base.py:10-14, postprocessor.py:14-19  (gates are drawn by the caller)
+//
+// HBM-bound stencil: each CTA produces a 128x32 output tile.  The input tile + halo is fetched by ONE
+// TMA tensor load (cp.async.bulk.tensor.3d) into shared memory -- out-of-image halo cells arrive as zeros
+// and are never read: the reflect border (kornia border_type="reflect", no edge repeat) is an index remap
+// onto in-tile cells.  Horizontal pass smem->smem, vertical pass smem->registers, noise/clip in registers,
+// 128-bit coalesced stores.  Traffic: 4 B read (+ halo re-reads served by L2) + 4 B written per texel.
+#include <cuda.h>
+
+#include "ffb_common.cuh"
+
+namespace ffb {
+namespace post {
+
+constexpr int TW = 128, TH = 32, THREADS = 256, KMAX = 15;
+
+struct PostParams {
+    int B, H, W;
+    int kx, ky, hx, hy;          // taps and left/top halo (k/2)
+    int boxw, boxh;              // TMA box (boxw multiple of 4)
+    float wx[KMAX], wy[KMAX];
+    int noise;
+    float mean, stdv;
+    uint64_t seed, frame0;
+    const float* img;
+    const uint8_t* gates;        // [B,2] or null
+    const double* noise_inj;     // [B,H,W] or null
+    float* out;
+};
+
+__device__ __forceinline__ int reflect(int i, int n) {      // torch 'reflect' padding (pad < n)
+    i = i < 0 ? -i : i;
+    return i >= n ? 2 * (n - 1) - i : i;
+}
+
+// 4 normal variates for 4 consecutive texels of one frame: Philox4x32-10 keyed by the seed, counter =
+// (texel quad index, global frame index); Box-Muller.  Independent of tiling, batching and rank.
+__device__ __forceinline__ void normal4(uint64_t seed, uint64_t frame, uint32_t quad, float (&z)[4]) {
+    uint32_t r[4];
+    Philox::gen(seed, quad, 0x4E015E00u, (uint32_t)frame, (uint32_t)(frame >> 32), r);
+    const float u0 = ((float)(r[0] >> 8) + 1.0f) * (1.0f / 16777216.0f), u1 = Philox::u01(r[1]);
+    const float u2 = ((float)(r[2] >> 8) + 1.0f) * (1.0f / 16777216.0f), u3 = Philox::u01(r[3]);
+    const float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
+    float sa, ca, sb, cb;
+    sincospif(2.0f * u1, &sa, &ca);
+    sincospif(2.0f * u3, &sb, &cb);
+    z[0] = ra * ca; z[1] = ra * sa; z[2] = rb * cb; z[3] = rb * sb;
+}
+
+// noise + clip on up to 4 consecutive texels (x0..x0+3 of row y) -- white_noise.py:17-20
+__device__ __forceinline__ void noise_clip4(const PostParams& q, int b, int y, int x0, float (&v)[4]) {
+    const size_t base = ((size_t)b * q.H + y) * q.W + x0;
+    if (q.noise_inj) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (x0 + k < q.W) v[k] = (float)((double)v[k] + q.noise_inj[base + k]);    // fp32 image += fp64 draw
+    } else {
+        float z[4];
+        normal4(q.seed, q.frame0 + (uint64_t)b, (uint32_t)(((size_t)y * q.W + x0) >> 2), z);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] += fmaf(q.stdv, z[k], q.mean);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = fminf(fmaxf(v[k], 0.f), 1.f);
+}
+
+__device__ __forceinline__ void store4(const PostParams& q, int b, int y, int x0, const float (&v)[4]) {
+    float* o = q.out + ((size_t)b * q.H + y) * q.W + x0;
+    if (x0 + 4 <= q.W && (q.W & 3) == 0) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (x0 + k < q.W) o[k] = v[k];
+    }
+}
+
+// ---- mbarrier / TMA PTX -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+// Blur (+ optional noise/clip) of one 128x32 tile.  USE_TMA = false is the fallback for W % 4 != 0 (TMA
+// needs 16-byte global strides): the same arithmetic, tile filled with plain loads.
+template <bool USE_TMA>
+__global__ void __launch_bounds__(THREADS) blur_kernel(const __grid_constant__ CUtensorMap tmap, const PostParams q) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* in_s = reinterpret_cast<float*>(smem_raw);                  // [boxh][boxw]
+    float* mid_s = in_s + q.boxh * q.boxw;                              // [boxh][TW]
+    __shared__ __align__(8) uint64_t bar;
+    const int tiles_x = (q.W + TW - 1) / TW;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x, b = blockIdx.y;
+    const int x0 = tx * TW, y0 = ty * TH;
+    const int tid = threadIdx.x;
+    const bool do_blur = q.gates ? q.gates[b * 2] != 0 : true;
+    const bool do_noise = q.noise && (q.gates ? q.gates[b * 2 + 1] != 0 : true);
+
+    if (!do_blur) {      // gate off: copy (PostProcessor copies once) [+ noise]
+        for (int i = tid; i < (TW / 4) * TH; i += THREADS) {
+            const int y = y0 + i / (TW / 4), x = x0 + (i % (TW / 4)) * 4;
+            if (y >= q.H || x >= q.W) continue;
+            float v[4];
+            const float* s = q.img + ((size_t)b * q.H + y) * q.W + x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = x + k < q.W ? __ldg(s + k) : 0.f;
+            if (do_noise) noise_clip4(q, b, y, x, v);
+            store4(q, b, y, x, v);
+        }
+        return;
+    }
+
+    // ---- stage input tile + halo ----
+    const int gx0 = x0 - q.hx, gy0 = y0 - q.hy;
+    if (USE_TMA) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar, (uint32_t)(q.boxw * q.boxh * sizeof(float)));
+            tma_load_3d(in_s, &tmap, &bar, gx0, gy0, b);
+        }
+        mbar_wait(&bar, 0);
+    } else {
+        for (int i = tid; i < q.boxw * q.boxh; i += THREADS) {
+            const int ly = i / q.boxw, lx = i - ly * q.boxw;
+            const int gy = gy0 + ly, gx = gx0 + lx;
+            in_s[i] = (gy >= 0 && gy < q.H && gx >= 0 && gx < q.W) ? __ldg(q.img + ((size_t)b * q.H + gy) * q.W + gx) : 0.f;
+        }
+        __syncthreads();
+    }
+
+    // ---- horizontal pass: mid[j][i] = sum_t wx[t] * in[j][reflect(x0 + i + t - hx)] ----
+    const bool edge_x = (x0 == 0) || (x0 + TW + (q.kx - 1 - q.hx) > q.W);
+    const int rows_used = q.boxh;
+    for (int idx = tid; idx < rows_used * TW; idx += THREADS) {
+        const int j = idx / TW, i = idx - j * TW;
+        const int gy = gy0 + j;
+        float acc = 0.f;
+        if (gy >= 0 && gy < q.H && x0 + i < q.W) {
+            const float* row = in_s + j * q.boxw;
+            if (!edge_x) {
+                for (int t = 0; t < q.kx; ++t) acc = fmaf(q.wx[t], row[i + t], acc);
+            } else {
+                for (int t = 0; t < q.kx; ++t) acc = fmaf(q.wx[t], row[reflect(x0 + i + t - q.hx, q.W) - gx0], acc);
+            }
+        }
+        mid_s[j * TW + i] = acc;
+    }
+    __syncthreads();
+
+    // ---- vertical pass + epilogue: each thread 4 consecutive columns of 4 rows ----
+    const int cg = tid & 31, r_base = tid >> 5;
+    const int x = x0 + cg * 4;
+#pragma unroll
+    for (int k = 0; k < TH / 8; ++k) {
+        const int r = r_base + k * 8, y = y0 + r;
+        if (y >= q.H || x >= q.W) continue;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int t = 0; t < q.ky; ++t) {
+            const int j = reflect(y + t - q.hy, q.H) - gy0;
+            const float4 m = *reinterpret_cast<const float4*>(mid_s + j * TW + cg * 4);
+            v[0] = fmaf(q.wy[t], m.x, v[0]); v[1] = fmaf(q.wy[t], m.y, v[1]);
+            v[2] = fmaf(q.wy[t], m.z, v[2]); v[3] = fmaf(q.wy[t], m.w, v[3]);
+        }
+        if (do_noise) noise_clip4(q, b, y, x, v);
+        store4(q, b, y, x, v);
+    }
+}
+
+// no blur stage configured: pure streaming copy / noise / clip
+__global__ void __launch_bounds__(THREADS) pointwise_kernel(const PostParams q) {
+    const size_t quads_per_row = (size_t)(q.W + 3) / 4;
+    const size_t total = quads_per_row * q.H * q.B;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / (quads_per_row * q.H));
+        const size_t rem = i - (size_t)b * quads_per_row * q.H;
+        const int y = (int)(rem / quads_per_row), x = (int)(rem - (size_t)y * quads_per_row) * 4;
+        const bool do_noise = q.noise && (q.gates ? q.gates[b * 2 + 1] != 0 : true);
+        float v[4];
+        const float* s = q.img + ((size_t)b * q.H + y) * q.W + x;
+        if (x + 4 <= q.W && (q.W & 3) == 0) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(s));
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = x + k < q.W ? __ldg(s + k) : 0.f;
+        }
+        if (do_noise) noise_clip4(q, b, y, x, v);
+        store4(q, b, y, x, v);
+    }
+}
+
+// kornia 0.7.1 get_gaussian_kernel1d: x = i - k//2 (+0.5 for even k); exp(-x^2/(2 sigma^2)); normalised.
+// Evaluated in fp32 like torch does (exp, then division by the fp32 sum).
+static void gaussian_taps(int k, float sigma, float* w) {
+    float sum = 0.f;
+    for (int i = 0; i < k; ++i) {
+        float x = (float)(i - k / 2);
+        if (k % 2 == 0) x += 0.5f;
+        w[i] = expf(-(x * x) / (2.0f * sigma * sigma));
+        sum += w[i];
+    }
+    for (int i = 0; i < k; ++i) w[i] /= sum;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+}  // namespace post
+}  // namespace ffb
+
+using namespace ffb;
+using namespace ffb::post;
+
+extern "C" int ffb_postprocess(const ffb_post_desc* d, const float* img, const uint8_t* gates,
+                               const double* noise_injected, float* out, void* stream) {
+    if (!d || !img || !out) return fail_arg(FFB_E_ARG, "postprocess: null pointer");
+    if (d->B <= 0 || d->H <= 0 || d->W <= 0) return fail_arg(FFB_E_ARG, "postprocess: B, H, W must be positive");
+    if (d->B > 65535) return fail_arg(FFB_E_LIMIT, "postprocess: B > 65535");
+    const bool blur = d->blur_ky > 0 && d->blur_kx > 0;
+    PostParams q;
+    memset(&q, 0, sizeof(q));
+    q.B = d->B; q.H = d->H; q.W = d->W;
+    q.noise = d->noise; q.mean = d->noise_mean; q.stdv = d->noise_std; q.seed = d->seed; q.frame0 = d->frame0;
+    q.img = img; q.gates = gates; q.noise_inj = noise_injected; q.out = out;
+    cudaStream_t st = as_stream(stream);
+    if (!blur) {
+        const size_t total = (size_t)((d->W + 3) / 4) * d->H * d->B;
+        size_t blocks = (total + THREADS - 1) / THREADS;
+        if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
+        pointwise_kernel<<<(unsigned)blocks, THREADS, 0, st>>>(q);
+        FFB_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (img == out) return fail_arg(FFB_E_ARG, "postprocess: img and out must not alias when blurring");
+    if (d->blur_kx > KMAX || d->blur_ky > KMAX) return fail_arg(FFB_E_LIMIT, "postprocess: blur kernel size > 15");
+    if (d->blur_kx % 2 == 0 || d->blur_ky % 2 == 0) return fail_arg(FFB_E_ARG, "postprocess: blur kernel sizes must be odd (all reference call sites are)");
+    if (!(d->blur_sx > 0.f) || !(d->blur_sy > 0.f)) return fail_arg(FFB_E_ARG, "postprocess: blur sigma must be > 0");
+    q.kx = d->blur_kx; q.ky = d->blur_ky; q.hx = q.kx / 2; q.hy = q.ky / 2;
+    // torch reflect padding needs pad < dim
+    if (q.hx >= d->W || q.hy >= d->H) return fail_arg(FFB_E_ARG, "postprocess: reflect border needs kernel/2 < image side");
+    gaussian_taps(q.kx, d->blur_sx, q.wx);
+    gaussian_taps(q.ky, d->blur_sy, q.wy);
+    q.boxw = (TW + q.kx - 1 + 3) & ~3;
+    q.boxh = TH + q.ky - 1;
+    const size_t smem = (size_t)q.boxh * (q.boxw + TW) * sizeof(float);
+    const unsigned tiles = (unsigned)(((d->W + TW - 1) / TW) * ((d->H + TH - 1) / TH));
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    bool use_tma = (d->W % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
+    if (use_tma) {
+        EncodeTiledFn enc = get_encode();
+        if (!enc) use_tma = false;
+        else {
+            cuuint64_t gdim[3] = {(cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+            cuuint64_t gstr[2] = {(cuuint64_t)d->W * 4, (cuuint64_t)d->W * d->H * 4};
+            cuuint32_t box[3] = {(cuuint32_t)q.boxw, (cuuint32_t)q.boxh, 1};
+            cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(img), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) use_tma = false;
+        }
+    }
+    if (use_tma) {
+        if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(blur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        blur_kernel<true><<<dim3(tiles, d->B), THREADS, smem, st>>>(tmap, q);
+    } else {
+        if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(blur_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        blur_kernel<false><<<dim3(tiles, d->B), THREADS, smem, st>>>(tmap, q);
+    }
+    FFB_CUDA(cudaGetLastError());
+    return 0;
+}

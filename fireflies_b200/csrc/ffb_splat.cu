@@ -1,0 +1,794 @@
+// Laser splat: fused splat + {sum, soft-OR} reduction, forward and backward, for sm_100a.
+//
+// Replaces (reference paths relative to the Fireflies tree):
+//   fireflies/graphics/rasterization.py:7-37    rasterize_points     (dense [N,H,W])
+//   fireflies/graphics/rasterization.py:156-161 softor / sum
+//   fireflies/graphics/rasterization.py:164-472 baked_sum, baked_sum_2, baked_softor, baked_softor_2
+//   + the torch autograd of those w.r.t. `points`.
+//
+// Design (HBM-bound gather, no tensor cores -- nothing here is a contraction):
+//   * prepare: one CTA per sample bins its N points into 64x32 texture tiles (count / scan / fill in
+//     shared memory, lists sorted so accumulation order is deterministic) and writes one 32-byte record
+//     per point: scaled position + the integer clip windows of both reductions.
+//   * forward: one CTA per (tile, sample).  Each warp owns 8 rows x 32 columns, a lane owns one column
+//     (8 texels in registers).  Candidate records are staged in shared memory; rows outside a point's
+//     window are skipped with warp-uniform branches, so only the column overhang is wasted work.  Every
+//     output texel is written exactly once with 128-byte warp stores: traffic = 4 B/texel/reduction.
+//   * backward: same tiling.  Pass 1 rebuilds the soft-OR product (zero factors tracked like torch.prod's
+//     backward) and caches g in shared memory; pass 2 forms dL/dg per (texel, point), accumulates the two
+//     partial derivatives per lane, reduces them with warp shuffles and issues one shared-memory atomic
+//     per (warp, point), then one global atomic per (tile, point).
+#include "ffb_common.cuh"
+
+namespace ffb {
+namespace splat {
+
+constexpr int TW = 64;        // tile width  (columns, texture_size[0] axis)
+constexpr int TH = 32;        // tile height (rows,    texture_size[1] axis)
+constexpr int WROWS = 8;      // rows per warp
+constexpr int CTA = 256;      // 8 warps: 2 column halves x 4 row groups
+constexpr int CHUNK = 128;    // candidate records staged per pass
+constexpr int KCACHE = 6;     // cached g slots per warp in the backward (8 rows x 32 lanes each; dynamic smem)
+constexpr int PREP_CTA = 1024;
+
+struct __align__(16) PointRec {
+    float p0, p1;             // points * texture_size
+    uint32_t sc, sr;          // sum window:    columns lo | hi << 16, rows lo | hi << 16  (half-open)
+    uint32_t oc, orow;        // soft-OR window
+    uint32_t uc, ur;          // union, used for culling and binning
+};
+static_assert(sizeof(PointRec) == 32, "PointRec must be 32 bytes");
+
+struct Plan {
+    int Bp;                   // number of binned pattern instances (1 when the pattern is shared)
+    int tgx, tgy, T;          // tile grid
+    int cap;                  // list capacity per instance
+    size_t off_recs, off_tileoff, off_list, total;
+    // window parameters
+    int fp_s, half_s, h_s;    // baked: fp/half ; dense: h = cut-off half width
+    int fp_o, half_o, h_o;
+};
+
+static inline int iceil_sqrt(double x) {
+    int r = (int)ceil(sqrt(x));
+    return r < 1 ? 1 : r;
+}
+
+static int make_plan(const ffb_splat_desc* d, Plan* p) {
+    if (!d) return fail_arg(FFB_E_ARG, "splat: null descriptor");
+    if (d->B <= 0 || d->N <= 0 || d->ts0 <= 0 || d->ts1 <= 0) return fail_arg(FFB_E_ARG, "splat: B, N, ts0, ts1 must be positive");
+    if (d->ts0 > 65535 || d->ts1 > 65535) return fail_arg(FFB_E_LIMIT, "splat: texture side > 65535");
+    if (!(d->sigma > 0.f)) return fail_arg(FFB_E_ARG, "splat: sigma must be > 0");
+    if (d->num_std_sum < 0 || d->num_std_softor < 0) return fail_arg(FFB_E_ARG, "splat: num_std must be >= 0");
+    p->Bp = d->pts_batch_stride == 0 ? 1 : d->B;
+    p->tgx = (d->ts0 + TW - 1) / TW;
+    p->tgy = (d->ts1 + TH - 1) / TH;
+    p->T = p->tgx * p->tgy;
+    // footprint = odd(floor(sqrt(sigma)) * num_std)  (rasterization.py:180-182; sqrt in fp32 like sigma.sqrt())
+    const int root = (int)floorf(sqrtf(d->sigma));
+    auto fp_of = [&](int num_std, int* fp, int* half) {
+        int f = root * num_std;
+        if (f % 2 == 0) f += 1;
+        *fp = f;
+        *half = (f - 1) / 2;
+    };
+    fp_of(d->num_std_sum, &p->fp_s, &p->half_s);
+    fp_of(d->num_std_softor, &p->fp_o, &p->half_o);
+    // no-op radii: g < 1.7e-38 once (d^2/sigma)^2 > 87 ; 1-g == 1 exactly once g <= 2^-25 (u^2 >= 17.5)
+    // (2% margin on d^2; exp_neg clamps at w = 87, i.e. g < 1.7e-38 is treated as 0)
+    p->h_s = iceil_sqrt((double)d->sigma * sqrt(87.0) * 1.02);
+    p->h_o = iceil_sqrt((double)d->sigma * sqrt(17.5) * 1.02);
+    int w_s = d->num_std_sum > 0 ? p->fp_s : 2 * p->h_s + 1;
+    int w_o = d->num_std_softor > 0 ? (p->fp_o < 2 * p->h_o + 1 ? p->fp_o : 2 * p->h_o + 1) : 2 * p->h_o + 1;
+    int w = (w_s > w_o ? w_s : w_o) + 1;
+    long tiles_x = (w + 1) / TW + 2, tiles_y = (w + 1) / TH + 2;
+    if (tiles_x > p->tgx) tiles_x = p->tgx;
+    if (tiles_y > p->tgy) tiles_y = p->tgy;
+    long cap = (long)d->N * tiles_x * tiles_y;
+    if (cap > 0x7fffffffL) return fail_arg(FFB_E_LIMIT, "splat: tile list capacity overflows int32");
+    p->cap = (int)cap;
+    size_t o = 0;
+    p->off_recs = o;     o += (size_t)p->Bp * d->N * sizeof(PointRec);
+    o = (o + 255) & ~(size_t)255;
+    p->off_tileoff = o;  o += (size_t)p->Bp * (p->T + 1) * sizeof(int);
+    o = (o + 255) & ~(size_t)255;
+    p->off_list = o;     o += (size_t)p->Bp * p->cap * sizeof(int);
+    p->total = (o + 255) & ~(size_t)255;
+    if ((size_t)p->T * 2 * sizeof(int) > 200 * 1024) return fail_arg(FFB_E_LIMIT, "splat: too many tiles for the binning kernel");
+    return 0;
+}
+
+struct PrepParams {
+    const float* pts;
+    long long stride;
+    int N, ts0, ts1, tgx, tgy, T, cap;
+    int baked_s, fp_s, half_s, h_s;
+    int baked_o, fp_o, half_o, h_o;
+    PointRec* recs;
+    int* tile_off;
+    int* list;
+    int* windows;     // nullable
+};
+
+// One axis of the reference's footprint clipping (rasterization.py:186,214-230): returns [lo,hi) in texture
+// indices and the (wo, rs, re) triple.
+__device__ __forceinline__ void baked_axis(float P, int half, int fp, int ts, int& lo, int& hi, int& wo, int& rs, int& re) {
+    const float fo = floorf(P - (float)half);
+    if (!(fo > -1.0e9f && fo < 1.0e9f)) { lo = hi = 0; wo = 0; rs = 0; re = 0; return; }   // NaN / far away
+    wo = (int)fo;
+    rs = wo < 0 ? -wo : 0;
+    wo = wo < 0 ? 0 : wo;
+    re = (wo + fp >= ts) ? ts - wo : fp;
+    int n = re - rs;
+    n = n < 0 ? 0 : n;
+    lo = wo;
+    hi = wo + n;
+    if (hi > ts) hi = ts;
+    if (lo >= ts) { lo = hi = 0; }
+}
+__device__ __forceinline__ void square_axis(float P, int h, int ts, int& lo, int& hi) {
+    const float fl = floorf(P);
+    if (!(fl > -1.0e9f && fl < 1.0e9f)) { lo = hi = 0; return; }
+    const int c = (int)fl;
+    lo = c - h; hi = c + h + 1;
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > ts ? ts : hi;
+    if (hi <= lo) { lo = hi = 0; }
+}
+__device__ __forceinline__ uint32_t pack_win(int lo, int hi) { return (uint32_t)lo | ((uint32_t)hi << 16); }
+
+__device__ __forceinline__ PointRec make_rec(const PrepParams& q, float x, float y, int* win /* [2][2][3] or null */) {
+    PointRec r;
+    r.p0 = x * (float)q.ts0;      // points.clone() * texture_size  (rasterization.py:18)
+    r.p1 = y * (float)q.ts1;
+    int lo[2][2], hi[2][2];       // [reduction][axis]
+    const float P[2] = {r.p0, r.p1};
+    const int ts[2] = {q.ts0, q.ts1};
+#pragma unroll
+    for (int ax = 0; ax < 2; ++ax) {
+        int wo = 0, rs = 0, re = 0;
+        if (q.baked_s) {
+            baked_axis(P[ax], q.half_s, q.fp_s, ts[ax], lo[0][ax], hi[0][ax], wo, rs, re);
+            if (win) { win[(0 * 2 + ax) * 3 + 0] = wo; win[(0 * 2 + ax) * 3 + 1] = rs; win[(0 * 2 + ax) * 3 + 2] = re; }
+        } else {
+            square_axis(P[ax], q.h_s, ts[ax], lo[0][ax], hi[0][ax]);
+            if (win) { win[(0 * 2 + ax) * 3 + 0] = 0; win[(0 * 2 + ax) * 3 + 1] = 0; win[(0 * 2 + ax) * 3 + 2] = 0; }
+        }
+        int l2, h2;
+        square_axis(P[ax], q.h_o, ts[ax], l2, h2);            // exact no-op bound of the soft-OR
+        if (q.baked_o) {
+            baked_axis(P[ax], q.half_o, q.fp_o, ts[ax], lo[1][ax], hi[1][ax], wo, rs, re);
+            if (win) { win[(1 * 2 + ax) * 3 + 0] = wo; win[(1 * 2 + ax) * 3 + 1] = rs; win[(1 * 2 + ax) * 3 + 2] = re; }
+            lo[1][ax] = max(lo[1][ax], l2);
+            hi[1][ax] = min(hi[1][ax], h2);
+            if (hi[1][ax] <= lo[1][ax]) lo[1][ax] = hi[1][ax] = 0;
+        } else {
+            lo[1][ax] = l2; hi[1][ax] = h2;
+            if (win) { win[(1 * 2 + ax) * 3 + 0] = 0; win[(1 * 2 + ax) * 3 + 1] = 0; win[(1 * 2 + ax) * 3 + 2] = 0; }
+        }
+    }
+    // an empty axis empties the whole window
+#pragma unroll
+    for (int red = 0; red < 2; ++red)
+        if (hi[red][0] <= lo[red][0] || hi[red][1] <= lo[red][1]) lo[red][0] = hi[red][0] = lo[red][1] = hi[red][1] = 0;
+    r.sc = pack_win(lo[0][0], hi[0][0]); r.sr = pack_win(lo[0][1], hi[0][1]);
+    r.oc = pack_win(lo[1][0], hi[1][0]); r.orow = pack_win(lo[1][1], hi[1][1]);
+    int ulo[2], uhi[2];
+#pragma unroll
+    for (int ax = 0; ax < 2; ++ax) {
+        const bool es = hi[0][ax] <= lo[0][ax], eo = hi[1][ax] <= lo[1][ax];
+        if (es && eo) { ulo[ax] = uhi[ax] = 0; }
+        else if (es) { ulo[ax] = lo[1][ax]; uhi[ax] = hi[1][ax]; }
+        else if (eo) { ulo[ax] = lo[0][ax]; uhi[ax] = hi[0][ax]; }
+        else { ulo[ax] = min(lo[0][ax], lo[1][ax]); uhi[ax] = max(hi[0][ax], hi[1][ax]); }
+    }
+    r.uc = pack_win(ulo[0], uhi[0]); r.ur = pack_win(ulo[1], uhi[1]);
+    return r;
+}
+
+__global__ void __launch_bounds__(PREP_CTA) prepare_kernel(PrepParams q) {
+    extern __shared__ int sm[];
+    int* cnt = sm;            // [T] counts, then exclusive offsets
+    int* cur = sm + q.T;      // [T] fill cursors
+    __shared__ int warp_tot[32];
+    const int bin = blockIdx.x, tid = threadIdx.x;
+    const float* pts = q.pts + (long long)bin * q.stride;
+    PointRec* recs = q.recs + (size_t)bin * q.N;
+    int* tile_off = q.tile_off + (size_t)bin * (q.T + 1);
+    int* list = q.list + (size_t)bin * q.cap;
+
+    for (int i = tid; i < q.T; i += PREP_CTA) cnt[i] = 0;
+    __syncthreads();
+    // 1. records + per-tile counts
+    for (int n = tid; n < q.N; n += PREP_CTA) {
+        const float2 xy = reinterpret_cast<const float2*>(pts)[n];
+        int win[12];
+        PointRec r = make_rec(q, xy.x, xy.y, q.windows ? win : nullptr);
+        recs[n] = r;
+        if (q.windows) {
+            int* w = q.windows + ((size_t)bin * q.N + n) * 12;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) w[k] = win[k];
+        }
+        const int c_lo = r.uc & 0xffff, c_hi = r.uc >> 16, r_lo = r.ur & 0xffff, r_hi = r.ur >> 16;
+        if (c_hi > c_lo && r_hi > r_lo) {
+            for (int ty = r_lo / TH; ty <= (r_hi - 1) / TH; ++ty)
+                for (int tx = c_lo / TW; tx <= (c_hi - 1) / TW; ++tx) atomicAdd(&cnt[ty * q.tgx + tx], 1);
+        }
+    }
+    __syncthreads();
+    // 2. exclusive scan over tiles
+    const int per = (q.T + PREP_CTA - 1) / PREP_CTA;
+    const int beg = min(tid * per, q.T), end = min(beg + per, q.T);
+    int local = 0;
+    for (int i = beg; i < end; ++i) local += cnt[i];
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31) >= o) incl += v;
+    }
+    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        int v = warp_tot[tid], s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (tid >= o) s += t;
+        }
+        warp_tot[tid] = s - v;     // exclusive
+    }
+    __syncthreads();
+    int run = warp_tot[tid >> 5] + incl - local;
+    for (int i = beg; i < end; ++i) {
+        const int c = cnt[i];
+        cnt[i] = run; cur[i] = run; tile_off[i] = run;
+        run += c;
+    }
+    if (tid == PREP_CTA - 1) tile_off[q.T] = run;
+    __syncthreads();
+    // 3. fill
+    for (int n = tid; n < q.N; n += PREP_CTA) {
+        const PointRec r = recs[n];
+        const int c_lo = r.uc & 0xffff, c_hi = r.uc >> 16, r_lo = r.ur & 0xffff, r_hi = r.ur >> 16;
+        if (c_hi > c_lo && r_hi > r_lo) {
+            for (int ty = r_lo / TH; ty <= (r_hi - 1) / TH; ++ty)
+                for (int tx = c_lo / TW; tx <= (c_hi - 1) / TW; ++tx) {
+                    const int pos = atomicAdd(&cur[ty * q.tgx + tx], 1);
+                    if (pos < q.cap) list[pos] = n;
+                }
+        }
+    }
+    __syncthreads();
+    // 4. sort every tile's list by point index -> deterministic accumulation order
+    for (int t = tid; t < q.T; t += PREP_CTA) {
+        const int b = cnt[t], e = min(cur[t], q.cap);
+        for (int i = b + 1; i < e; ++i) {
+            const int v = list[i];
+            int j = i - 1;
+            while (j >= b && list[j] > v) { list[j + 1] = list[j]; --j; }
+            list[j + 1] = v;
+        }
+    }
+}
+
+struct RasterParams {
+    const PointRec* recs;
+    const int* tile_off;
+    const int* list;
+    int shared_pattern;       // 1: every sample uses bin 0
+    int N, ts0, ts1, tgx, T, cap;
+    float sigma, rcp_sigma;
+    float* out_sum; float* out_softor;            // forward
+    const float* g_sum; const float* g_softor;    // backward
+    float* d_pts;
+};
+
+__device__ __forceinline__ bool in_win(int v, uint32_t w) { return v >= (int)(w & 0xffff) && v < (int)(w >> 16); }
+
+// g for one texel: identical operation order to the reference (rasterization.py:32-35):
+// (dc*dc + dr*dr) / sigma, squared, negated, exp.
+__device__ __forceinline__ float eval_g(float dx2, float dy, float sigma, float rcp_sigma, float& u) {
+    const float d2 = __fadd_rn(dx2, __fmul_rn(dy, dy));
+    u = div_by(d2, sigma, rcp_sigma);
+    return exp_neg(__fmul_rn(u, u));
+}
+
+template <bool SUM, bool SOFTOR, bool SUM_T>
+__global__ void __launch_bounds__(CTA) splat_fwd_kernel(RasterParams q) {
+    __shared__ PointRec recs_s[CHUNK];
+    const int tile = blockIdx.x % q.T, b = blockIdx.x / q.T;
+    const int bin = q.shared_pattern ? 0 : b;
+    const int tx = tile % q.tgx, ty = tile / q.tgx;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wc0 = tx * TW + (warp & 1) * 32, wr0 = ty * TH + (warp >> 1) * WROWS;
+    const int c = wc0 + lane;
+    const float cf = (float)c, rf0 = (float)wr0;
+    const int* toff = q.tile_off + (size_t)bin * (q.T + 1);
+    const int beg = toff[tile], end = toff[tile + 1];
+    const int* list = q.list + (size_t)bin * q.cap;
+    const PointRec* recs = q.recs + (size_t)bin * q.N;
+
+    float acc_s[WROWS], acc_p[WROWS];
+#pragma unroll
+    for (int i = 0; i < WROWS; ++i) { acc_s[i] = 0.f; acc_p[i] = 1.f; }
+
+    for (int base = beg; base < end; base += CHUNK) {
+        const int n = min(CHUNK, end - base);
+        __syncthreads();
+        if (tid < n) recs_s[tid] = recs[list[base + tid]];
+        __syncthreads();
+        for (int k = 0; k < n; ++k) {
+            const uint4 wa = reinterpret_cast<const uint4*>(&recs_s[k])[0];
+            const uint4 wb = reinterpret_cast<const uint4*>(&recs_s[k])[1];
+            const uint32_t uc = wb.z, ur = wb.w;
+            // warp-uniform cull against this warp's 8x32 block
+            if ((int)(uc >> 16) <= wc0 || (int)(uc & 0xffff) >= wc0 + 32 || (int)(ur >> 16) <= wr0 || (int)(ur & 0xffff) >= wr0 + WROWS) continue;
+            const float p0 = __uint_as_float(wa.x), p1 = __uint_as_float(wa.y);
+            const float dx = cf - p0;
+            const float dx2 = __fmul_rn(dx, dx);
+            const bool cs = SUM && in_win(c, wa.z), co = SOFTOR && in_win(c, wb.x);
+            const int r_lo = ur & 0xffff, r_hi = ur >> 16;
+#pragma unroll
+            for (int i = 0; i < WROWS; ++i) {
+                const int r = wr0 + i;
+                if (r >= r_lo && r < r_hi) {                       // warp-uniform
+                    float u;
+                    const float g = eval_g(dx2, (rf0 + (float)i) - p1, q.sigma, q.rcp_sigma, u);
+                    if (SUM) acc_s[i] += (cs && in_win(r, wa.w)) ? g : 0.f;
+                    if (SOFTOR) acc_p[i] *= (co && in_win(r, wb.y)) ? (1.f - g) : 1.f;
+                }
+            }
+        }
+    }
+    // epilogue: every texel of the tile is written exactly once
+    const size_t frame = (size_t)q.ts0 * q.ts1;
+    if (SOFTOR && c < q.ts0) {
+        float* o = q.out_softor + (size_t)b * frame + c;
+#pragma unroll
+        for (int i = 0; i < WROWS; ++i)
+            if (wr0 + i < q.ts1) o[(size_t)(wr0 + i) * q.ts0] = 1.f - acc_p[i];
+    }
+    if (SUM && c < q.ts0) {
+        if (!SUM_T) {
+            float* o = q.out_sum + (size_t)b * frame + c;
+#pragma unroll
+            for (int i = 0; i < WROWS; ++i)
+                if (wr0 + i < q.ts1) o[(size_t)(wr0 + i) * q.ts0] = acc_s[i];
+        } else {
+            float* o = q.out_sum + (size_t)b * frame + (size_t)c * q.ts1 + wr0;   // [ts0, ts1]: 8 consecutive rows
+            if ((q.ts1 & 3) == 0 && wr0 + WROWS <= q.ts1) {
+                reinterpret_cast<float4*>(o)[0] = make_float4(acc_s[0], acc_s[1], acc_s[2], acc_s[3]);
+                reinterpret_cast<float4*>(o)[1] = make_float4(acc_s[4], acc_s[5], acc_s[6], acc_s[7]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < WROWS; ++i)
+                    if (wr0 + i < q.ts1) o[i] = acc_s[i];
+            }
+        }
+    }
+}
+
+template <bool SUM, bool SOFTOR, bool SUM_T>
+__global__ void __launch_bounds__(CTA) splat_bwd_kernel(RasterParams q) {
+    __shared__ PointRec recs_s[CHUNK];
+    __shared__ float dp_s[CHUNK][2];
+    extern __shared__ float gcache[];      // SOFTOR: [8 warps][KCACHE][8 rows][32 lanes]
+    const int tile = blockIdx.x % q.T, b = blockIdx.x / q.T;
+    const int bin = q.shared_pattern ? 0 : b;
+    const int tx = tile % q.tgx, ty = tile / q.tgx;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wc0 = tx * TW + (warp & 1) * 32, wr0 = ty * TH + (warp >> 1) * WROWS;
+    const int c = wc0 + lane;
+    const float cf = (float)c, rf0 = (float)wr0;
+    const int* toff = q.tile_off + (size_t)bin * (q.T + 1);
+    const int beg = toff[tile], end = toff[tile + 1];
+    if (beg == end) return;
+    const int* list = q.list + (size_t)bin * q.cap;
+    const PointRec* recs = q.recs + (size_t)bin * q.N;
+    const size_t frame = (size_t)q.ts0 * q.ts1;
+    float* gc = gcache + (SOFTOR ? warp * KCACHE * WROWS * 32 + lane : 0);
+
+    // upstream gradients of this lane's 8 texels
+    float gs[WROWS], go[WROWS];
+#pragma unroll
+    for (int i = 0; i < WROWS; ++i) { gs[i] = 0.f; go[i] = 0.f; }
+    if (c < q.ts0) {
+        if (SOFTOR) {
+            const float* p = q.g_softor + (size_t)b * frame + c;
+#pragma unroll
+            for (int i = 0; i < WROWS; ++i)
+                if (wr0 + i < q.ts1) go[i] = __ldg(p + (size_t)(wr0 + i) * q.ts0);
+        }
+        if (SUM) {
+            if (!SUM_T) {
+                const float* p = q.g_sum + (size_t)b * frame + c;
+#pragma unroll
+                for (int i = 0; i < WROWS; ++i)
+                    if (wr0 + i < q.ts1) gs[i] = __ldg(p + (size_t)(wr0 + i) * q.ts0);
+            } else {
+                const float* p = q.g_sum + (size_t)b * frame + (size_t)c * q.ts1 + wr0;
+                if ((q.ts1 & 3) == 0 && wr0 + WROWS <= q.ts1) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+                    const float4 d = __ldg(reinterpret_cast<const float4*>(p) + 1);
+                    gs[0] = a.x; gs[1] = a.y; gs[2] = a.z; gs[3] = a.w; gs[4] = d.x; gs[5] = d.y; gs[6] = d.z; gs[7] = d.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < WROWS; ++i)
+                        if (wr0 + i < q.ts1) gs[i] = __ldg(p + i);
+                }
+            }
+        }
+    }
+
+    // ---- pass 1: product of the non-zero (1-g) factors per texel + zero bookkeeping, g cached ----
+    float prod[WROWS];
+    uint32_t z1 = 0, z2 = 0;      // bit i: >=1 / >=2 exact-zero factors at row i
+#pragma unroll
+    for (int i = 0; i < WROWS; ++i) prod[i] = 1.f;
+    if (SOFTOR) {
+        int kk = 0;               // warp-uniform index of the next relevant candidate
+        for (int base = beg; base < end; base += CHUNK) {
+            const int n = min(CHUNK, end - base);
+            __syncthreads();
+            if (tid < n) recs_s[tid] = recs[list[base + tid]];
+            __syncthreads();
+            for (int k = 0; k < n; ++k) {
+                const uint4 wa = reinterpret_cast<const uint4*>(&recs_s[k])[0];
+                const uint4 wb = reinterpret_cast<const uint4*>(&recs_s[k])[1];
+                const uint32_t uc = wb.z, ur = wb.w;
+                if ((int)(uc >> 16) <= wc0 || (int)(uc & 0xffff) >= wc0 + 32 || (int)(ur >> 16) <= wr0 || (int)(ur & 0xffff) >= wr0 + WROWS) continue;
+                const float p0 = __uint_as_float(wa.x), p1 = __uint_as_float(wa.y);
+                const float dx = cf - p0;
+                const float dx2 = __fmul_rn(dx, dx);
+                const bool co = in_win(c, wb.x);
+                const int r_lo = ur & 0xffff, r_hi = ur >> 16;
+#pragma unroll
+                for (int i = 0; i < WROWS; ++i) {
+                    const int r = wr0 + i;
+                    if (r >= r_lo && r < r_hi) {
+                        float u;
+                        const float g = eval_g(dx2, (rf0 + (float)i) - p1, q.sigma, q.rcp_sigma, u);
+                        if (kk < KCACHE) gc[(kk * WROWS + i) * 32] = g;
+                        if (co && in_win(r, wb.y)) {
+                            const float om = 1.f - g;
+                            if (om == 0.f) { z2 |= z1 & (1u << i); z1 |= 1u << i; }
+                            else prod[i] *= om;
+                        }
+                    }
+                }
+                ++kk;
+            }
+        }
+    }
+
+    // ---- pass 2: dL/dg per (texel, point) -> d/dp, reduced over the tile ----
+    const float k0 = 4.f * (float)q.ts0 * q.rcp_sigma, k1 = 4.f * (float)q.ts1 * q.rcp_sigma;
+    int kk = 0;
+    for (int base = beg; base < end; base += CHUNK) {
+        const int n = min(CHUNK, end - base);
+        if (!SOFTOR || end - beg > CHUNK) {      // single-chunk soft-OR tiles still hold their records
+            __syncthreads();
+            if (tid < n) recs_s[tid] = recs[list[base + tid]];
+        }
+        if (tid < n) { dp_s[tid][0] = 0.f; dp_s[tid][1] = 0.f; }
+        __syncthreads();
+        for (int k = 0; k < n; ++k) {
+            const uint4 wa = reinterpret_cast<const uint4*>(&recs_s[k])[0];
+            const uint4 wb = reinterpret_cast<const uint4*>(&recs_s[k])[1];
+            const uint32_t uc = wb.z, ur = wb.w;
+            if ((int)(uc >> 16) <= wc0 || (int)(uc & 0xffff) >= wc0 + 32 || (int)(ur >> 16) <= wr0 || (int)(ur & 0xffff) >= wr0 + WROWS) continue;
+            const float p0 = __uint_as_float(wa.x), p1 = __uint_as_float(wa.y);
+            const float dx = cf - p0;
+            const float dx2 = __fmul_rn(dx, dx);
+            const bool cs = SUM && in_win(c, wa.z), co = SOFTOR && in_win(c, wb.x);
+            const int r_lo = ur & 0xffff, r_hi = ur >> 16;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < WROWS; ++i) {
+                const int r = wr0 + i;
+                if (r >= r_lo && r < r_hi) {
+                    const float dy = (rf0 + (float)i) - p1;
+                    float u, g;
+                    if (SOFTOR && kk < KCACHE) {
+                        g = gc[(kk * WROWS + i) * 32];
+                        u = __fadd_rn(dx2, __fmul_rn(dy, dy)) * q.rcp_sigma;
+                    } else {
+                        g = eval_g(dx2, dy, q.sigma, q.rcp_sigma, u);
+                    }
+                    float coef = 0.f;
+                    if (SUM && cs && in_win(r, wa.w)) coef = gs[i];
+                    if (SOFTOR && co && in_win(r, wb.y)) {
+                        const float om = 1.f - g;
+                        float excl;                                   // prod_{m != n} (1 - g_m)
+                        if (!(z1 & (1u << i))) excl = __fdividef(prod[i], om);
+                        else excl = (om == 0.f && !(z2 & (1u << i))) ? prod[i] : 0.f;
+                        coef = fmaf(go[i], excl, coef);
+                    }
+                    const float w = coef * g * u;
+                    a0 = fmaf(w, dx, a0);
+                    a1 = fmaf(w, dy, a1);
+                }
+            }
+            a0 = warp_sum(a0);
+            a1 = warp_sum(a1);
+            if (lane == 0) { atomicAdd(&dp_s[k][0], a0); atomicAdd(&dp_s[k][1], a1); }
+            ++kk;
+        }
+        __syncthreads();
+        if (tid < n) {
+            float* o = q.d_pts + ((size_t)b * q.N + list[base + tid]) * 2;
+            const float v0 = dp_s[tid][0] * k0, v1 = dp_s[tid][1] * k1;
+            if (v0 != 0.f) atomicAdd(o, v0);
+            if (v1 != 0.f) atomicAdd(o + 1, v1);
+        }
+    }
+}
+
+template <typename K>
+static int launch_raster(K kernel, const RasterParams& q, int B, cudaStream_t st, size_t smem = 0) {
+    const long long grid = (long long)B * q.T;
+    if (grid > 0x7fffffffLL) return fail_arg(FFB_E_LIMIT, "splat: B * tiles exceeds the grid limit");
+    if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<(unsigned)grid, CTA, smem, st>>>(q);
+    FFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static void fill_raster(const ffb_splat_desc* d, const Plan& p, const void* ws, RasterParams& q) {
+    const char* w = reinterpret_cast<const char*>(ws);
+    q.recs = reinterpret_cast<const PointRec*>(w + p.off_recs);
+    q.tile_off = reinterpret_cast<const int*>(w + p.off_tileoff);
+    q.list = reinterpret_cast<const int*>(w + p.off_list);
+    q.shared_pattern = d->pts_batch_stride == 0;
+    q.N = d->N; q.ts0 = d->ts0; q.ts1 = d->ts1; q.tgx = p.tgx; q.T = p.T; q.cap = p.cap;
+    q.sigma = d->sigma; q.rcp_sigma = 1.0f / d->sigma;
+    q.out_sum = nullptr; q.out_softor = nullptr; q.g_sum = nullptr; q.g_softor = nullptr; q.d_pts = nullptr;
+}
+
+// ---- dense API-compat kernels -----------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dense_fwd_kernel(const float* __restrict__ pts, int N, int ts0, int ts1, float sigma,
+                                                        float rcp_sigma, float* __restrict__ out) {
+    const size_t frame = (size_t)ts0 * ts1;
+    const size_t total = frame * N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / frame);
+        const size_t t = i - (size_t)n * frame;
+        const int r = (int)(t / ts0), c = (int)(t - (size_t)r * ts0);
+        const float dx = (float)c - pts[2 * n] * (float)ts0;
+        const float dy = (float)r - pts[2 * n + 1] * (float)ts1;
+        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        const float u = div_by(d2, sigma, rcp_sigma);
+        const float w = __fmul_rn(u, u);
+        out[i] = w > 87.f ? 0.f : exp_neg(w);
+    }
+}
+
+__global__ void __launch_bounds__(256) dense_bwd_kernel(const float* __restrict__ pts, int N, int ts0, int ts1, float sigma,
+                                                        float rcp_sigma, const float* __restrict__ g_out, float* __restrict__ d_pts) {
+    // grid = (chunks, N): each CTA reduces a slice of one point's frame
+    const int n = blockIdx.y;
+    const size_t frame = (size_t)ts0 * ts1;
+    const float p0 = pts[2 * n] * (float)ts0, p1 = pts[2 * n + 1] * (float)ts1;
+    const float* go = g_out + (size_t)n * frame;
+    float a0 = 0.f, a1 = 0.f;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < frame; t += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(t / ts0), c = (int)(t - (size_t)r * ts0);
+        const float dx = (float)c - p0, dy = (float)r - p1;
+        const float u = (dx * dx + dy * dy) * rcp_sigma;
+        const float w = u * u;
+        if (w <= 87.f) {
+            const float q = go[t] * exp_neg(w) * u;
+            a0 = fmaf(q, dx, a0);
+            a1 = fmaf(q, dy, a1);
+        }
+    }
+    __shared__ float red[2][8];
+    a0 = warp_sum(a0); a1 = warp_sum(a1);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a0; red[1][threadIdx.x >> 5] = a1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int i = 0; i < 8; ++i) { s0 += red[0][i]; s1 += red[1][i]; }
+        atomicAdd(&d_pts[2 * n], s0 * 4.f * (float)ts0 * rcp_sigma);
+        atomicAdd(&d_pts[2 * n + 1], s1 * 4.f * (float)ts1 * rcp_sigma);
+    }
+}
+
+// out[j] = sum_b in[b, j], fixed order
+__global__ void __launch_bounds__(256) reduce_samples_kernel(const float* __restrict__ in, int B, long long row, float* __restrict__ out) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= row) return;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += in[(long long)b * row + j];
+    out[j] = s;
+}
+
+// mean |a - b| per sample and its gradients.  grid = (row blocks, B); each CTA handles 32x32 texels so the
+// transposed operand is read/written through a shared-memory transpose.
+template <bool BT>
+__global__ void __launch_bounds__(256) l1_kernel(const float* __restrict__ a, const float* __restrict__ bsrc, int ts0, int ts1,
+                                                 float inv_numel, float* __restrict__ loss, float* __restrict__ ga, float* __restrict__ gb) {
+    __shared__ float tile[32][33];
+    __shared__ float red[8];
+    const int tiles_x = (ts0 + 31) / 32;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int smp = blockIdx.y;
+    const size_t frame = (size_t)ts0 * ts1;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;      // 32 x 8 threads
+    const float* A = a + (size_t)smp * frame;
+    const float* Bm = bsrc + (size_t)smp * frame;
+    float part = 0.f;
+    if (BT) {   // stage b^T tile: b is [ts0, ts1]; element (r,c) of the natural frame lives at b[c*ts1 + r]
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cc = tx * 32 + ly + j * 8, rr = ty * 32 + lx;
+            tile[ly + j * 8][lx] = (cc < ts0 && rr < ts1) ? Bm[(size_t)cc * ts1 + rr] : 0.f;
+        }
+        __syncthreads();
+    }
+    float sgn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = ty * 32 + ly + j * 8, c = tx * 32 + lx;
+        sgn[j] = 0.f;
+        if (r < ts1 && c < ts0) {
+            const float av = A[(size_t)r * ts0 + c];
+            const float bv = BT ? tile[lx][ly + j * 8] : Bm[(size_t)r * ts0 + c];
+            const float d = av - bv;
+            part += fabsf(d);
+            sgn[j] = d > 0.f ? inv_numel : (d < 0.f ? -inv_numel : 0.f);
+            if (ga) ga[(size_t)smp * frame + (size_t)r * ts0 + c] = sgn[j];
+            if (gb && !BT) gb[(size_t)smp * frame + (size_t)r * ts0 + c] = -sgn[j];
+        }
+    }
+    if (BT && gb) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tile[lx][ly + j * 8] = -sgn[j];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cc = tx * 32 + ly + j * 8, rr = ty * 32 + lx;
+            if (cc < ts0 && rr < ts1) gb[(size_t)smp * frame + (size_t)cc * ts1 + rr] = tile[ly + j * 8][lx];
+        }
+    }
+    part = warp_sum(part);
+    if (lx == 0) red[ly] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        atomicAdd(&loss[smp], s * inv_numel);
+    }
+}
+
+}  // namespace splat
+}  // namespace ffb
+
+using namespace ffb;
+using namespace ffb::splat;
+
+extern "C" size_t ffb_splat_workspace_bytes(const ffb_splat_desc* d) {
+    Plan p;
+    if (make_plan(d, &p)) return 0;
+    return p.total;
+}
+
+extern "C" int ffb_splat_prepare(const ffb_splat_desc* d, const float* pts, void* workspace, size_t workspace_bytes,
+                                 int32_t* windows_out, void* stream) {
+    Plan p;
+    if (int rc = make_plan(d, &p)) return rc;
+    if (!pts || !workspace) return fail_arg(FFB_E_ARG, "splat_prepare: null pointer");
+    if (workspace_bytes < p.total) return fail_arg(FFB_E_WORKSPACE, "splat_prepare: workspace too small");
+    char* w = reinterpret_cast<char*>(workspace);
+    PrepParams q;
+    q.pts = pts; q.stride = d->pts_batch_stride;
+    q.N = d->N; q.ts0 = d->ts0; q.ts1 = d->ts1; q.tgx = p.tgx; q.tgy = p.tgy; q.T = p.T; q.cap = p.cap;
+    q.baked_s = d->num_std_sum > 0; q.fp_s = p.fp_s; q.half_s = p.half_s; q.h_s = p.h_s;
+    q.baked_o = d->num_std_softor > 0; q.fp_o = p.fp_o; q.half_o = p.half_o; q.h_o = p.h_o;
+    q.recs = reinterpret_cast<PointRec*>(w + p.off_recs);
+    q.tile_off = reinterpret_cast<int*>(w + p.off_tileoff);
+    q.list = reinterpret_cast<int*>(w + p.off_list);
+    q.windows = windows_out;
+    const size_t smem = (size_t)p.T * 2 * sizeof(int);
+    static thread_local size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        FFB_CUDA(cudaFuncSetAttribute(prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    prepare_kernel<<<p.Bp, PREP_CTA, smem, as_stream(stream)>>>(q);
+    FFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ffb_splat_fwd(const ffb_splat_desc* d, const float* pts, const void* workspace,
+                             float* out_sum, int sum_transposed, float* out_softor, void* stream) {
+    (void)pts;
+    Plan p;
+    if (int rc = make_plan(d, &p)) return rc;
+    if (!workspace) return fail_arg(FFB_E_ARG, "splat_fwd: null workspace");
+    if (!out_sum && !out_softor) return fail_arg(FFB_E_ARG, "splat_fwd: no output requested");
+    RasterParams q;
+    fill_raster(d, p, workspace, q);
+    q.out_sum = out_sum; q.out_softor = out_softor;
+    cudaStream_t st = as_stream(stream);
+    if (out_sum && out_softor)
+        return sum_transposed ? launch_raster(splat_fwd_kernel<true, true, true>, q, d->B, st)
+                              : launch_raster(splat_fwd_kernel<true, true, false>, q, d->B, st);
+    if (out_sum)
+        return sum_transposed ? launch_raster(splat_fwd_kernel<true, false, true>, q, d->B, st)
+                              : launch_raster(splat_fwd_kernel<true, false, false>, q, d->B, st);
+    return launch_raster(splat_fwd_kernel<false, true, false>, q, d->B, st);
+}
+
+extern "C" int ffb_splat_bwd(const ffb_splat_desc* d, const float* pts, const void* workspace,
+                             const float* g_sum, int sum_transposed, const float* g_softor,
+                             float* d_pts, void* stream) {
+    (void)pts;
+    Plan p;
+    if (int rc = make_plan(d, &p)) return rc;
+    if (!workspace || !d_pts) return fail_arg(FFB_E_ARG, "splat_bwd: null pointer");
+    if (!g_sum && !g_softor) return fail_arg(FFB_E_ARG, "splat_bwd: no upstream gradient");
+    RasterParams q;
+    fill_raster(d, p, workspace, q);
+    q.g_sum = g_sum; q.g_softor = g_softor; q.d_pts = d_pts;
+    cudaStream_t st = as_stream(stream);
+    FFB_CUDA(cudaMemsetAsync(d_pts, 0, (size_t)d->B * d->N * 2 * sizeof(float), st));
+    const size_t gsm = (size_t)(CTA / 32) * KCACHE * WROWS * 32 * sizeof(float);
+    if (g_sum && g_softor)
+        return sum_transposed ? launch_raster(splat_bwd_kernel<true, true, true>, q, d->B, st, gsm)
+                              : launch_raster(splat_bwd_kernel<true, true, false>, q, d->B, st, gsm);
+    if (g_sum)
+        return sum_transposed ? launch_raster(splat_bwd_kernel<true, false, true>, q, d->B, st)
+                              : launch_raster(splat_bwd_kernel<true, false, false>, q, d->B, st);
+    return launch_raster(splat_bwd_kernel<false, true, false>, q, d->B, st, gsm);
+}
+
+extern "C" int ffb_reduce_over_samples(const float* in, int32_t B, int64_t row_elems, float* out, void* stream) {
+    if (!in || !out || B <= 0 || row_elems <= 0) return fail_arg(FFB_E_ARG, "reduce_over_samples: bad argument");
+    const unsigned grid = (unsigned)((row_elems + 255) / 256);
+    reduce_samples_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, B, row_elems, out);
+    FFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ffb_splat_dense_fwd(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sigma, float* out, void* stream) {
+    if (!pts || !out || N <= 0 || ts0 <= 0 || ts1 <= 0 || !(sigma > 0.f)) return fail_arg(FFB_E_ARG, "splat_dense_fwd: bad argument");
+    const size_t total = (size_t)N * ts0 * ts1;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > (size_t)kNumSMs * 32) blocks = (size_t)kNumSMs * 32;
+    dense_fwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(pts, N, ts0, ts1, sigma, 1.0f / sigma, out);
+    FFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ffb_splat_dense_bwd(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sigma,
+                                   const float* g_out, float* d_pts, void* stream) {
+    if (!pts || !g_out || !d_pts || N <= 0 || ts0 <= 0 || ts1 <= 0 || !(sigma > 0.f)) return fail_arg(FFB_E_ARG, "splat_dense_bwd: bad argument");
+    if (N > 65535) return fail_arg(FFB_E_LIMIT, "splat_dense_bwd: N > 65535");
+    cudaStream_t st = as_stream(stream);
+    FFB_CUDA(cudaMemsetAsync(d_pts, 0, (size_t)N * 2 * sizeof(float), st));
+    const size_t frame = (size_t)ts0 * ts1;
+    unsigned chunks = (unsigned)((frame + 256 * 16 - 1) / (256 * 16));
+    if (chunks > 64) chunks = 64;
+    if (chunks < 1) chunks = 1;
+    dense_bwd_kernel<<<dim3(chunks, N), 256, 0, st>>>(pts, N, ts0, ts1, sigma, 1.0f / sigma, g_out, d_pts);
+    FFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ffb_l1_loss_fwd_bwd(const float* a, const float* b, int b_transposed, int32_t B, int32_t ts0, int32_t ts1,
+                                   float* loss_out, float* g_a, float* g_b, void* stream) {
+    if (!a || !b || !loss_out || B <= 0 || ts0 <= 0 || ts1 <= 0) return fail_arg(FFB_E_ARG, "l1_loss: bad argument");
+    if (B > 65535) return fail_arg(FFB_E_LIMIT, "l1_loss: B > 65535");
+    cudaStream_t st = as_stream(stream);
+    FFB_CUDA(cudaMemsetAsync(loss_out, 0, (size_t)B * sizeof(float), st));
+    const unsigned tiles = (unsigned)(((ts0 + 31) / 32) * ((ts1 + 31) / 32));
+    const float inv = 1.0f / ((float)ts0 * (float)ts1);
+    if (b_transposed) l1_kernel<true><<<dim3(tiles, B), 256, 0, st>>>(a, b, ts0, ts1, inv, loss_out, g_a, g_b);
+    else l1_kernel<false><<<dim3(tiles, B), 256, 0, st>>>(a, b, ts0, ts1, inv, loss_out, g_a, g_b);
+    FFB_CUDA(cudaGetLastError());
+    return 0;
+}

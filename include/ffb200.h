@@ -1,0 +1,233 @@
+/*
+ * ffb200.h -- C ABI of libffb200.so, the B200 (sm_100a) hot path of Fireflies.
+ *
+ * The reference (Henningson/Fireflies) is pure Python/PyTorch and exposes no FFI; its
+ * drop-in boundary is the Python API.  This header is the boundary
+ * *behind* that API: every entry point below replaces the body of one or more reference
+ * functions, cited as path:line relative to the reference tree.  The Python package
+ * `fireflies_b200` binds these with ctypes (fireflies_b200/_native.py); INTEGRATION.md shows
+ * the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer on the current CUDA device unless
+ *     the parameter name ends in `_host`; the caller owns every buffer, kernels never allocate;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every call is
+ *     asynchronous with respect to the host;
+ *   - return value: 0 = OK, >0 = cudaError_t from a launch/runtime call, <0 = argument error
+ *     (FFB_E_*); ffb_last_error_string() describes the last failure on the calling thread;
+ *   - no global mutable state; re-entrant across streams;
+ *   - all floating point is IEEE fp32 ("f32"); index outputs are int32.
+ *
+ * Texture orientation: "natural" = [ts1, ts0] row-major, rows pair with points[:,1] and columns
+ * with points[:,0] -- the orientation of rasterize_points(...).sum(0)
+ * (fireflies/graphics/rasterization.py:18-30).  "transposed" = [ts0, ts1], the orientation
+ * baked_sum_2 returns (fireflies/graphics/rasterization.py:318).
+ */
+#ifndef FFB200_H
+#define FFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFB_VERSION 100
+
+#if defined(__GNUC__)
+#define FFB_API __attribute__((visibility("default")))
+#else
+#define FFB_API
+#endif
+
+#define FFB_E_ARG      (-1)   /* invalid argument (null pointer, non-positive size, ...)   */
+#define FFB_E_WORKSPACE (-2)  /* workspace too small                                       */
+#define FFB_E_LIMIT    (-3)   /* size beyond a compiled limit (see message)                */
+
+FFB_API int         ffb_version(void);
+FFB_API const char* ffb_last_error_string(void);
+
+/* ------------------------------------------------------------------------------------------
+ * 1. Laser splat  (fireflies/graphics/rasterization.py)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Reduction windows.  num_std > 0 selects the footprint-limited ("baked") semantics of
+ * baked_sum / baked_sum_2 / baked_softor / baked_softor_2 (rasterization.py:164-472):
+ * footprint = odd(floor(sqrt(sigma)) * num_std), clipped exactly like the reference slices.
+ * num_std == 0 selects the dense semantics of rasterize_points + sum/softor
+ * (rasterization.py:7-37,156-161): every texel, evaluated up to the radius beyond which
+ * exp(-(d^2/sigma)^2) is exactly 0 in fp32 (sum) or 1-g rounds to exactly 1 (softor). */
+typedef struct ffb_splat_desc {
+    int32_t B;              /* scene samples                                                */
+    int32_t N;              /* points per sample                                            */
+    int32_t ts0, ts1;       /* texture_size[0] (columns, pairs with p[:,0]), [1] (rows)     */
+    float   sigma;          /* the reference's `sigma` (divides d^2; NOT squared again)     */
+    int32_t num_std_sum;    /* 4 = baked_sum default; 0 = dense                             */
+    int32_t num_std_softor; /* 5 = baked_softor default; 0 = dense                          */
+    int64_t pts_batch_stride; /* elements between samples in `pts`; 0 = one pattern shared  */
+} ffb_splat_desc;
+
+/* Bytes of scratch the splat calls need for this descriptor (binning tables). */
+FFB_API size_t ffb_splat_workspace_bytes(const ffb_splat_desc* d);
+
+/* Bins the points of every sample into texture tiles and computes each point's integer clip
+ * window.  Must precede ffb_splat_fwd/ffb_splat_bwd on the same workspace (same stream order).
+ *   pts         [B,N,2] f32 in [0,1] (x,y) -- or [N,2] with pts_batch_stride = 0
+ *   windows_out NULL or int32 [Bp,N,2,2,3]: per point, per reduction (0 = sum, 1 = softor), per
+ *               axis, the reference's (wo, rs, re) slice triple (rasterization.py:199-230);
+ *               Bp = B, or 1 when the pattern is shared.  Only defined for baked reductions. */
+FFB_API int ffb_splat_prepare(const ffb_splat_desc* d, const float* pts, void* workspace, size_t workspace_bytes,
+                      int32_t* windows_out, void* stream);
+
+/* Fused splat + reduce, forward.  Replaces rasterize_points+sum/softor and the baked_* family.
+ *   out_sum     NULL or f32 [B,ts1,ts0] (natural) / [B,ts0,ts1] if sum_transposed
+ *   out_softor  NULL or f32 [B,ts1,ts0] */
+FFB_API int ffb_splat_fwd(const ffb_splat_desc* d, const float* pts, const void* workspace,
+                  float* out_sum, int sum_transposed, float* out_softor, void* stream);
+
+/* Backward of ffb_splat_fwd w.r.t. pts (the autograd the reference gets from torch,
+ * SURVEY.md 8(a) a7).  d_pts [B,N,2] f32 is OVERWRITTEN (zeroed, then accumulated).
+ *   g_sum     NULL or upstream gradient of out_sum, same layout as out_sum
+ *   g_softor  NULL or upstream gradient of out_softor */
+FFB_API int ffb_splat_bwd(const ffb_splat_desc* d, const float* pts, const void* workspace,
+                  const float* g_sum, int sum_transposed, const float* g_softor,
+                  float* d_pts, void* stream);
+
+/* sum over the sample axis: out[N*2] = sum_b in[b, N*2]  (fixed order -> deterministic);
+ * used to fold per-sample pattern gradients before the allreduce. */
+FFB_API int ffb_reduce_over_samples(const float* in, int32_t B, int64_t row_elems, float* out, void* stream);
+
+/* API-compatibility dense splat: rasterize_points (rasterization.py:7-37) -> [N,ts1,ts0],
+ * and its backward given the upstream gradient of that tensor. */
+FFB_API int ffb_splat_dense_fwd(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sigma,
+                        float* out, void* stream);
+FFB_API int ffb_splat_dense_bwd(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sigma,
+                        const float* g_out, float* d_pts, void* stream);
+
+/* mean |a-b| and its gradients (torch.nn.L1Loss as used by test_point_reg, rasterization.py:591-599).
+ *   a is natural [B,ts1,ts0]; b is natural or transposed ([B,ts0,ts1]) per b_transposed.
+ *   loss_out f32 [B] (OVERWRITTEN); g_a / g_b (may be NULL) receive d loss_b / d a, d b in the
+ *   layouts of a and b. */
+FFB_API int ffb_l1_loss_fwd_bwd(const float* a, const float* b, int b_transposed, int32_t B, int32_t ts0, int32_t ts1,
+                        float* loss_out, float* g_a, float* g_b, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 3. Sampling  (fireflies/sampling)
+ * ------------------------------------------------------------------------------------------ */
+
+#define FFB_MODE_TRAIN     0  /* counter-based Philox4x32-10 draws                              */
+#define FFB_MODE_EVAL      1  /* deterministic stepping, sampling/base.py:64-74 incl. its aliasing */
+#define FFB_MODE_INJECTED  2  /* variates supplied by the caller (parity tests / torch's RNG stream) */
+
+#define FFB_SAMPLER_UNIFORM        0  /* UniformSampler          sampling/uniform.py:16-19: u*(max-min)+min per component */
+#define FFB_SAMPLER_SCALAR_TO_VEC3 1  /* UniformScalarToVec3Sampler sampling/uniform_scalar_to_vec3.py:18-38: 1 draw, written 3x */
+#define FFB_SAMPLER_GAUSSIAN       2  /* GaussianSampler         sampling/gaussian_distribution.py:19-20: mean + std*z, unclamped */
+
+/* One sampler row.  `dim` is the number of state components (1 or 3).  The eval fields are the
+ * in/out state of Sampler.sample_eval: `cur` = _current_step, `aliased` = _current_step is the
+ * same tensor as _min_range (after the first wrap), in which case stepping also moves vmin. */
+typedef struct ffb_sampler {
+    int32_t kind;           /* FFB_SAMPLER_*                                                 */
+    int32_t dim;            /* 1 or 3                                                        */
+    int32_t aliased;        /* eval state                                                    */
+    float   step;           /* eval_step_size (0.01)                                         */
+    float   vmin[3], vmax[3], cur[3];
+    float   mean[3], std[3];/* FFB_SAMPLER_GAUSSIAN only                                     */
+} ffb_sampler;
+
+/* Draws B successive samples from each of S samplers: out[b,s,0:3] (unused components = 0;
+ * SCALAR_TO_VEC3 rows carry the draw in all three).
+ *   samplers    DEVICE array [S]; in FFB_MODE_EVAL its eval state is advanced B times in place
+ *   seed, sample0  FFB_MODE_TRAIN: Philox key / global index of sample 0 of this call; a draw
+ *               depends only on (seed, sample0+b, s, component) -- never on B, the GPU or rank
+ *   variates    FFB_MODE_INJECTED: f32 [B,S,3] uniform variates in [0,1) (standard normal ones
+ *               for GAUSSIAN rows); else NULL */
+FFB_API int ffb_sample(ffb_sampler* samplers, int32_t S, int32_t B, int32_t mode, uint64_t seed, uint64_t sample0,
+               const float* variates, float* out, void* stream);
+
+/* AnimationSampler frame indices (sampling/animation.py:27-45), int32 out[b,m].
+ * train: min + floor(u*(max-min)) with Philox (python's random.randint stream is not reproducible
+ * on a device; the injected path takes host-drawn indices instead); eval: min..max INCLUSIVE walk
+ * continuing from cur[m] (in/out, device). */
+FFB_API int ffb_sample_anim_index(const int32_t* amin, const int32_t* amax, int32_t* cur, int32_t M, int32_t B, int32_t mode,
+                          uint64_t seed, uint64_t sample0, int32_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 2. Per-entity compose + vertex transforms  (fireflies/entity, fireflies/utils/math.py)
+ * ------------------------------------------------------------------------------------------ */
+
+#define FFB_ENTITY_PLAIN  0   /* (T+C) @ R @ W          entity/base.py:220-234                */
+#define FFB_ENTITY_MESH   1   /* (T+C) @ R @ S @ W      entity/mesh.py:141-150                */
+
+typedef struct ffb_entity {
+    int32_t kind;           /* FFB_ENTITY_*                                                  */
+    int32_t parent;         /* row of the parent entity, -1 = root (entity/base.py:239-244); must be < own row */
+    int32_t randomizable;   /* 0: local = W  (randomize() returns early, entity/base.py:221-222) */
+    int32_t s_translation;  /* sampler rows feeding this entity; -1 = zeros / zeros / ones    */
+    int32_t s_rotation;
+    int32_t s_scale;
+    float   centroid[3];    /* entity/base.py:51-54                                          */
+    float   _pad;
+    float   world[16];      /* row-major _world                                              */
+} ffb_entity;
+
+/* out_world[b,e] = parent chain of ((T+C) @ R [@ S] @ W) built from sampled[b, s_*, :].
+ * Rotation = Pitch(r2) @ Yaw(r1) @ Roll(r0) with fp64 trig rounded to fp32 (utils/math.py:24-60,
+ * entity/base.py:194-207).   entities DEVICE [E]; sampled f32 [B,S,3]; out_world f32 [B,E,16]. */
+FFB_API int ffb_compose_world(const ffb_entity* entities, int32_t E, int32_t B, const float* sampled, int32_t S,
+                      float* out_world, void* stream);
+
+/* Batched transform_points (utils/math.py:220-228) over up to FFB_MAX_MESHES meshes per call, with
+ * optional animation-frame gather (entity/mesh.py:158-165,183-198):
+ *   out[b, voff_m + v] = persp_div(world[b, entity_m] @ [src_m[v], 1])
+ *   src_m = frames_m[anim_idx[b,m]] if frames_m else verts + 3*voff_m.
+ * The mesh table is passed BY VALUE (host struct). */
+#define FFB_MAX_MESHES 32
+typedef struct ffb_mesh_table {
+    int32_t M;
+    int32_t voff[FFB_MAX_MESHES + 1];   /* vertex offsets into verts / out rows              */
+    int32_t entity[FFB_MAX_MESHES];     /* row of `world` per mesh                           */
+    int32_t nframes[FFB_MAX_MESHES];    /* 0 = not animated                                  */
+    const float* frames[FFB_MAX_MESHES];/* DEVICE f32 [nframes, V_m, 3] or NULL              */
+} ffb_mesh_table;
+
+FFB_API int ffb_transform_vertices(const ffb_mesh_table* meshes, const float* verts, int32_t E, int32_t B,
+                           const int32_t* anim_idx, const float* world, float* out, void* stream);
+
+/* transform_points / transform_directions for one matrix (utils/math.py:220-235):
+ * out[v] = persp_div(T @ [x,y,z,1])  or  (T @ [x,y,z,0])[:3].   T f32 [16] row-major, DEVICE. */
+FFB_API int ffb_transform_points(const float* pts, int64_t V, const float* T, int as_directions, float* out, void* stream);
+
+/* Laser glue (projection/laser.py:199-206, 262-290).  M = K @ FLIP_Y and Minv are DEVICE f32 [16].
+ * rays_to_ndc: ndc[n] = persp_div(M @ [ray,1]).
+ * clamp_to_fov: clamp ndc xy to [clamp_lo, clamp_hi] (= [1-c, c], the host rounds 1-c in fp64 like
+ * python does), un-project through Minv, renormalise. */
+FFB_API int ffb_rays_to_ndc(const float* rays, int32_t N, const float* M, float* ndc, void* stream);
+FFB_API int ffb_clamp_to_fov(const float* rays, int32_t N, const float* M, const float* Minv, float clamp_lo, float clamp_hi,
+                     float* rays_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 4. Post-processing  (fireflies/postprocessing)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ffb_post_desc {
+    int32_t B, H, W;        /* frames [B,H,W] f32                                             */
+    int32_t blur_ky, blur_kx; /* 0 = no blur stage; kornia gaussian_blur2d kernel_size (odd, <= 15) */
+    float   blur_sy, blur_sx;
+    int32_t noise;          /* 0 = no noise stage; 1 = WhiteNoise (white_noise.py:16-20)       */
+    float   noise_mean, noise_std;
+    uint64_t seed;          /* Philox key for the native noise stream                         */
+    uint64_t frame0;        /* global index of frame 0 (stream independent of batching/rank)   */
+} ffb_post_desc;
+
+/* out = clip?(noise?(blur?(img))) per frame; gates u8 [B,2] = (blur gate, noise gate) -- the
+ * Bernoulli draws of BasePostProcessingFunction.apply (postprocessing/base.py:10-14) made by the
+ * caller; NULL = all stages on.  noise_injected NULL or f64 [B,H,W] normal variates already
+ * scaled by mean/std, added in fp64 like numpy does (white_noise.py:17; parity tests).  img and out must not alias when a blur stage is present. */
+FFB_API int ffb_postprocess(const ffb_post_desc* d, const float* img, const uint8_t* gates,
+                    const double* noise_injected, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFB200_H */

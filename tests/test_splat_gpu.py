@@ -1,0 +1,205 @@
+"""GPU parity: the CUDA splat (through the C ABI) vs the CPU oracle and the reference-generated fixtures.
+
+Tolerances (north star): forward 1e-5 relative, gradients 1e-4 relative, integer outputs bit-exact.
+Forward comparisons add an absolute floor of 1e-6 (values are O(1); the reference's own dense and baked
+variants differ from each other by 2.4e-7); gradient comparisons add 1e-4 of the largest
+gradient component.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ff_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SPLAT_CASES = ["splat_kat1", "splat_small_rect", "splat_mid", "splat_c1"]
+
+
+@pytest.fixture(scope="module")
+def R():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import fireflies_b200.graphics.rasterization as R
+    return R
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, np.float64)
+    b = b.detach().cpu().double().numpy() if torch.is_tensor(b) else np.asarray(b, np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = np.abs(a - b) - (atol + rtol * np.abs(b))
+    assert err.max() <= 0, f"max violation {err.max():.3e}; max abs diff {np.abs(a - b).max():.3e}"
+
+
+@pytest.mark.parametrize("case", SPLAT_CASES)
+def test_forward_vs_reference_fixtures(R, golden, case):
+    g = golden(case)
+    pts, sigma, ts, st = T(g["points"]).cuda(), float(g["sigma"]), g["texture_size"].tolist(), int(g["stride"])
+    close(R.baked_sum(pts, sigma, ts)[::st, ::st], g["baked_sum"])
+    close(R.baked_sum_2(pts, sigma, ts)[::st, ::st], g["baked_sum_2"])
+    close(R.baked_softor(pts, sigma, ts)[::st, ::st], g["baked_softor"])
+    close(R.baked_softor_2(pts, sigma, ts)[::st, ::st], g["baked_softor_2"])
+    if "dense_sum" in g:
+        close(R.rasterize_points_baked_sum(pts, sigma, ts)[::st, ::st], g["dense_sum"])
+        close(R.rasterize_points_baked_softor(pts, sigma, ts)[::st, ::st], g["dense_softor"])
+    if "dense" in g:
+        close(R.rasterize_points(pts, sigma, T(np.array(ts))), g["dense"], atol=1e-7)
+    # fused: both reductions from one launch equal the separate calls bit for bit
+    s, o = R.splat_reduce(pts, sigma, ts, sum_transposed=True)
+    assert torch.equal(s, R.baked_sum_2(pts, sigma, ts)) and torch.equal(o, R.baked_softor_2(pts, sigma, ts))
+
+
+@pytest.mark.parametrize("case", SPLAT_CASES)
+def test_backward_vs_reference_fixtures(R, golden, case):
+    g = golden(case)
+    pts, sigma, ts = T(g["points"]).cuda(), float(g["sigma"]), g["texture_size"].tolist()
+    h, w = ts[1], ts[0]
+    if "wS" in g:
+        wS, wO = T(g["wS"]), T(g["wO"])
+    else:
+        gen = torch.Generator().manual_seed(7)
+        wS, wO = torch.randn(h, w, generator=gen), torch.randn(h, w, generator=gen)
+    wS, wO = wS.cuda(), wO.cuda()
+    # <wS, baked_sum> + <wO, baked_softor>
+    p = pts.clone().requires_grad_(True)
+    s, o = R.splat_reduce(p, sigma, ts)
+    ((s * wS).sum() + (o * wO).sum()).backward()
+    ref = g["baked_weighted_grad"]
+    close(p.grad, ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+    # same through the transposed-sum layout (baked_sum_2): upstream gradient arrives transposed
+    p = pts.clone().requires_grad_(True)
+    s, o = R.splat_reduce(p, sigma, ts, sum_transposed=True)
+    ((s * wS.T).sum() + (o * wO).sum()).backward()
+    close(p.grad, ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+    # dense semantics
+    if "dense_weighted_grad" in g:
+        p = pts.clone().requires_grad_(True)
+        s, o = R.splat_reduce(p, sigma, ts, num_std_sum=None, num_std_softor=None)
+        ((s * wS).sum() + (o * wO).sum()).backward()
+        ref = g["dense_weighted_grad"]
+        close(p.grad, ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+    # the in-tree pattern-optimisation step: L1(baked_softor_2, baked_sum_2)
+    if ts[0] == ts[1]:
+        p = pts.clone().requires_grad_(True)
+        s, o = R.splat_reduce(p, sigma, ts, sum_transposed=True, batch=1)
+        loss = R.l1_loss(o, s, b_transposed=False)      # the reference compares softor with the *transposed* sum as-is
+        loss.sum().backward()
+        close(loss[0], g["baked_l1"], rtol=1e-5, atol=1e-8)
+        ref = g["baked_l1_grad"]
+        close(p.grad, ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+
+
+def test_dense_autograd_kat1(R, golden):
+    g = golden("splat_kat1")
+    pts, ts = T(g["points"]).cuda().requires_grad_(True), g["texture_size"].tolist()
+    d = R.rasterize_points(pts, 4.0, T(np.array(ts)))
+    loss = torch.nn.L1Loss()(R.softor(d), R.sum(d))
+    loss.backward()
+    close(loss, g["dense_l1"], rtol=1e-5, atol=1e-8)
+    close(pts.grad, g["dense_l1_grad"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,ts,sigma,seed", [
+    (1, [7, 5], 2.0, 0), (33, [100, 37], 12.5, 1), (300, [257, 129], 40.0, 2), (64, [64, 64], 225.0, 3), (500, [512, 512], 100.0, 4),
+])
+def test_randomised_vs_oracle(R, n, ts, sigma, seed):
+    gen = torch.Generator().manual_seed(seed)
+    pts = torch.rand(n, 2, generator=gen)
+    wS, wO = torch.randn(ts[1], ts[0], generator=gen), torch.randn(ts[1], ts[0], generator=gen)
+    p = pts.cuda().requires_grad_(True)
+    s, o = R.splat_reduce(p, sigma, ts)
+    close(s, O.baked_sum(pts, sigma, ts))
+    close(o, O.baked_softor(pts, sigma, ts))
+    ((s * wS.cuda()).sum() + (o * wO.cuda()).sum()).backward()
+    pr = pts.clone().requires_grad_(True)
+    ((O.baked_sum(pr, sigma, ts) * wS).sum() + (O.baked_softor(pr, sigma, ts) * wO).sum()).backward()
+    close(p.grad, pr.grad, rtol=1e-4, atol=1e-4 * pr.grad.abs().max().item())
+    # integer outputs: clip windows bit-exact
+    win = R.splat_windows(pts.cuda(), sigma, ts).cpu()
+    assert torch.equal(win[:, 0], O.baked_windows(pts, sigma, ts, 4))
+    assert torch.equal(win[:, 1], O.baked_windows(pts, sigma, ts, 5))
+    # dense semantics where the dense tensor is affordable
+    if n * ts[0] * ts[1] <= 8_000_000:
+        d = O.splat_dense(pts, sigma, ts)
+        s, o = R.splat_reduce(pts.cuda(), sigma, ts, num_std_sum=None, num_std_softor=None)
+        close(s, O.reduce_sum(d))
+        close(o, O.softor(d))
+
+
+def test_edge_cases(R):
+    ts = [40, 24]
+    # points outside [0,1], on the borders, duplicates on a pixel centre (two exact-zero soft-OR factors), NaN
+    pts = torch.tensor([[0.0, 0.0], [1.0, 1.0], [0.5, 0.5], [0.5, 0.5], [0.5, 0.5], [-0.2, 0.3], [1.4, 0.9], [0.25, 0.75],
+                        [float("nan"), 0.5]])
+    ok = pts[:8]
+    s, o = R.splat_reduce(pts.cuda(), 9.0, ts, num_std_sum=None, num_std_softor=None)
+    d = O.splat_dense(ok, 9.0, ts)
+    close(s, O.reduce_sum(d))
+    close(o, O.softor(d))
+    wS = torch.randn(ts[1], ts[0], generator=torch.Generator().manual_seed(5))
+    wO = torch.randn(ts[1], ts[0], generator=torch.Generator().manual_seed(6))
+    p = ok.cuda().requires_grad_(True)
+    s, o = R.splat_reduce(p, 9.0, ts, num_std_sum=None, num_std_softor=None)
+    ((s * wS.cuda()).sum() + (o * wO.cuda()).sum()).backward()
+    ana = O.splat_grad_analytic(ok, 9.0, ts, wS, wO, None, None)
+    close(p.grad, ana, rtol=1e-4, atol=1e-4 * ana.abs().max().item())
+    assert torch.isfinite(p.grad).all()
+
+
+def test_batched_and_shared_patterns(R):
+    gen = torch.Generator().manual_seed(9)
+    B, n, ts, sigma = 5, 40, [96, 72], 16.0
+    pts = torch.rand(B, n, 2, generator=gen)
+    gS, gO = torch.randn(B, ts[0], ts[1], generator=gen), torch.randn(B, ts[1], ts[0], generator=gen)
+    p = pts.cuda().requires_grad_(True)
+    s, o = R.splat_reduce(p, sigma, ts, sum_transposed=True)
+    assert s.shape == (B, ts[0], ts[1]) and o.shape == (B, ts[1], ts[0])
+    ((s * gS.cuda()).sum() + (o * gO.cuda()).sum()).backward()
+    for b in range(B):
+        close(s[b], O.baked_sum(pts[b], sigma, ts, transposed=True))
+        close(o[b], O.baked_softor(pts[b], sigma, ts))
+        ana = O.splat_grad_analytic(pts[b], sigma, ts, gS[b].T, gO[b], 4, 5)
+        close(p.grad[b], ana, rtol=1e-4, atol=1e-4 * ana.abs().max().item())
+    # one pattern shared by all samples: gradient = sum over samples (linearity)
+    q = pts[0].cuda().requires_grad_(True)
+    s2, o2 = R.splat_reduce(q, sigma, ts, sum_transposed=True, batch=B)
+    assert torch.equal(s2[3], s[0]) and torch.equal(o2[1], o[0])
+    ((s2 * gS.cuda()).sum() + (o2 * gO.cuda()).sum()).backward()
+    ana = O.splat_grad_analytic(pts[0], sigma, ts, gS.sum(0).T, gO.sum(0), 4, 5)
+    close(q.grad, ana, rtol=1e-4, atol=1e-4 * ana.abs().max().item())
+
+
+def test_full_size_properties(R):
+    """BASELINE config 3 shape (4096 points, 2048^2), one sample: size-independent properties."""
+    gen = torch.Generator().manual_seed(0)
+    pts = (torch.rand(4096, 2, generator=gen) * 0.96 + 0.02).cuda()
+    ts = [2048, 2048]
+    s, o = R.splat_reduce(pts, 100.0, ts)
+    # (1) transposed layout is exactly the transpose; (2) swapping x/y transposes the image
+    st, _ = R.splat_reduce(pts, 100.0, ts, sum_transposed=True)
+    assert torch.equal(st, s.T.contiguous())
+    s_sw, o_sw = R.splat_reduce(pts.flip(1).contiguous(), 100.0, ts)
+    close(s_sw, s.T, rtol=1e-6, atol=1e-6)
+    close(o_sw, o.T, rtol=1e-6, atol=1e-6)
+    # (3) linearity of the sum over disjoint point subsets; soft-OR composes as 1-(1-a)(1-b)
+    sa, oa = R.splat_reduce(pts[:2048].contiguous(), 100.0, ts)
+    sb, ob = R.splat_reduce(pts[2048:].contiguous(), 100.0, ts)
+    close(sa + sb, s, rtol=1e-5, atol=1e-6)
+    close(1 - (1 - oa) * (1 - ob), o, rtol=1e-5, atol=1e-6)
+    # (4) bounds and mass: 0 <= softor <= 1, softor <= sum, total mass = N * per-point footprint mass
+    assert o.min() >= 0 and o.max() <= 1 and bool((o <= s + 1e-6).all())
+    one = R.splat_reduce(torch.tensor([[0.5, 0.5]]).cuda(), 100.0, ts)[0].double().sum()
+    close(s.double().sum() / 4096, one, rtol=1e-4, atol=0)
+    # (5) a random 64x64 crop against the oracle evaluated on that crop's candidate points
+    d = O.baked_sum(pts.cpu(), 100.0, ts)
+    close(s[1000:1064, 300:364], d[1000:1064, 300:364])
+    # (6) gradient of the total mass w.r.t. interior points vanishes (translation invariance)
+    p = pts.clone().requires_grad_(True)
+    R.splat_reduce(p, 100.0, ts, reduce=("sum",))[0].sum().backward()
+    inner = ((pts > 0.05) & (pts < 0.95)).all(1)
+    assert p.grad[inner].abs().max() < 2e-2      # vs O(1e3) individual terms: sub-pixel sampling ripple only
