@@ -530,7 +530,8 @@ template <typename K>
 static int launch_raster(K kernel, const RasterParams& q, int B, cudaStream_t st, size_t smem = 0) {
     const long long grid = (long long)B * q.T;
     if (grid > 0x7fffffffLL) return fail_arg(FFB_E_LIMIT, "splat: B * tiles exceeds the grid limit");
-    if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // static + dynamic shared memory may exceed the 48 KB default even when the dynamic part alone does not
+    if (smem > 32 * 1024) FFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kernel<<<(unsigned)grid, CTA, smem, st>>>(q);
     FFB_CUDA(cudaGetLastError());
     return 0;
