@@ -1,0 +1,290 @@
+"""B200-native batched path: randomise B scene samples and run the pattern-optimisation step in a handful
+of launches.  This is what the reference's per-sample loop (``scene.randomize()`` -> render -> ``backward``,
+SURVEY.md section 3 (C)-(E)) becomes when B samples are processed at once.
+
+* :class:`SceneBatch`  -- ``Scene.randomize()`` for B samples: sampling (Philox / eval stepping), 4x4 compose
+  with parent chains, vertex transform with animation gather.  3-4 launches, no host sync.
+* :class:`PatternStep` -- splat fwd (sum + soft-OR) -> loss -> splat bwd -> fold over samples -> allreduce.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .entity import Mesh, Transformable
+from .entity.base import _ENT_INTS, _ENT_WORDS
+from .graphics import rasterization as R
+from .sampling import AnimationSampler, Sampler
+from .sampling.base import _WORDS as _SMP_WORDS
+from .sampling.base import rehome
+
+
+@dataclass
+class BatchResult:
+    world: torch.Tensor                 # [B,E,4,4]
+    sampled: torch.Tensor               # [B,S,3]
+    vertices: Optional[torch.Tensor]    # [B,Vtot,3] (padded slots) or None
+    batch: "SceneBatch"
+
+    def mesh_vertices(self, name: str) -> torch.Tensor:
+        off, n = self.batch._mesh_slices[name]
+        return self.vertices[:, off:off + n]
+
+    def entity_world(self, name: str) -> torch.Tensor:
+        return self.world[:, self.batch._entity_index[name]]
+
+    def attribute(self, entity_name: str, key: str) -> torch.Tensor:
+        row, dim = self.batch._attr_rows[(entity_name, key)]
+        return self.sampled[:, row, :dim]
+
+
+class SceneBatch:
+    def __init__(self, scene, seed: int = 0):
+        self.scene = scene
+        self.seed = int(seed)
+        self.device = torch.device(scene.device())
+        self._next_sample = 0
+        # ---- entities, parents before children ----
+        ents: List[Transformable] = []
+
+        def add_chain(lst):
+            for root in [e for e in lst if e.parent() is None]:
+                node = root
+                while node is not None:
+                    if node not in ents:
+                        ents.append(node)
+                    node = node.child()
+            for e in lst:
+                if e not in ents:
+                    ents.append(e)
+
+        add_chain(scene._meshes)
+        add_chain(scene._lights)
+        for e in (scene._camera, scene._projector):
+            if e is not None:
+                ents.append(e)
+        self.entities = ents
+        self._entity_index = {e.name(): i for i, e in enumerate(ents)}
+        # ---- sampler table ----
+        samplers: List[Sampler] = []
+        self._attr_rows: Dict[Tuple[str, str], Tuple[int, int]] = {}
+        trs_rows = []
+        for e in ents:
+            rows = []
+            for s in (e._translation_sampler, e._rotation_sampler, getattr(e, "_scale_sampler", None)):
+                if s is None:
+                    rows.append(-1)
+                else:
+                    rows.append(len(samplers))
+                    samplers.append(s)
+            trs_rows.append(rows)
+        for e in ents + list(scene._materials):
+            if isinstance(e, Mesh) or not e.randomizable():
+                continue
+            for key, s in list(e._float_attributes.items()) + list(e._vec3_attributes.items()):
+                self._attr_rows[(e.name(), key)] = (len(samplers), 3 if s._KIND == nat.SAMPLER_SCALAR_TO_VEC3 else s._dim)
+                samplers.append(s)
+        for s in samplers:
+            if not isinstance(s, Sampler):
+                raise TypeError("SceneBatch needs fireflies_b200.sampling.Sampler instances")
+        self.samplers = samplers
+        self.S = len(samplers)
+        self.sampler_table = torch.zeros((max(self.S, 1), _SMP_WORDS), dtype=torch.int32, device=self.device)
+        for i, s in enumerate(samplers):
+            rehome(s, self.sampler_table[i])
+        # ---- entity table ----
+        self.E = len(ents)
+        self._trs_rows = trs_rows
+        self.entity_table = torch.zeros((max(self.E, 1), _ENT_WORDS), dtype=torch.int32, device=self.device)
+        self.refresh()
+        # ---- meshes ----
+        self._mesh_slices: Dict[str, Tuple[int, int]] = {}
+        self.meshes = [m for m in scene._meshes if m.randomizable()]
+        self.mesh_tables: List[nat.MeshTable] = []
+        self._frames_keepalive = []
+        if self.meshes:
+            self._build_meshes()
+
+    def refresh(self) -> None:
+        """Re-read world matrices, centroids, flags and parent links from the python objects."""
+        ints = np.full((max(self.E, 1), _ENT_INTS), -1, dtype=np.int32)
+        cents, worlds = [], []
+        for i, e in enumerate(self.entities):
+            parent = self._entity_index[e.parent().name()] if e.parent() is not None else -1
+            ints[i] = (e._KIND, parent, int(e.randomizable()), *self._trs_rows[i])
+            cents.append(e._centroid_mat[0:3, 3].to(self.device).float())
+            worlds.append(e._world.to(self.device).float().reshape(16))
+        self.entity_table[:, :_ENT_INTS] = torch.from_numpy(ints).to(self.device)
+        if self.E:
+            fv = self.entity_table.view(torch.float32)
+            fv[:, 6:9] = torch.stack(cents)
+            fv[:, 10:26] = torch.stack(worlds)
+
+    def _build_meshes(self) -> None:
+        voff, chunks, anim = [0], [], []
+        for m in self.meshes:
+            if m._animated and m._animation_func is not None:
+                raise NotImplementedError("python animation callbacks cannot be batched; use frame data")
+            V = m._vertices.shape[0]
+            slot = (V + 3) // 4 * 4                              # 16-byte aligned slots
+            v = torch.zeros((slot, 3), dtype=torch.float32, device=self.device)
+            v[:V] = m._vertices.float()
+            chunks.append(v)
+            self._mesh_slices[m.name()] = (voff[-1], V)
+            voff.append(voff[-1] + slot)
+            anim.append(m if (m._animated and m._anim_data_train is not None and m._anim_data_eval is not None) else None)
+        self.verts = torch.cat(chunks)
+        self.Vtot = voff[-1]
+        self._anim_meshes = anim
+        M = len(self.meshes)
+        if M > nat.FFB_MAX_MESHES:
+            raise NotImplementedError(f"more than {nat.FFB_MAX_MESHES} randomizable meshes per launch")
+        self._voff = voff
+        if any(a is not None for a in anim):
+            self._anim_cur = torch.tensor([(a._animation_sampler._current_step if a is not None else 0) for a in anim],
+                                          dtype=torch.int32, device=self.device)
+
+    def _mesh_table(self, train: bool) -> nat.MeshTable:
+        mt = nat.MeshTable()
+        mt.M = len(self.meshes)
+        self._frames_keepalive = []
+        for i, m in enumerate(self.meshes):
+            mt.voff[i] = self._voff[i]
+            mt.entity[i] = self._entity_index[m.name()]
+            a = self._anim_meshes[i]
+            if a is not None:
+                frames = a._anim_data_train if train else a._anim_data_eval
+                V = m._vertices.shape[0]
+                slot = self._voff[i + 1] - self._voff[i]
+                if frames.shape[1] != slot:                      # pad frames to the slot size once
+                    key = "_ffb_frames_train" if train else "_ffb_frames_eval"
+                    if getattr(a, key, None) is None:
+                        p = torch.zeros((frames.shape[0], slot, 3), dtype=torch.float32, device=self.device)
+                        p[:, :V] = frames
+                        setattr(a, key, p)
+                    frames = getattr(a, key)
+                self._frames_keepalive.append(frames)
+                mt.nframes[i] = frames.shape[0]
+                mt.frames[i] = frames.data_ptr()
+            else:
+                mt.nframes[i] = 0
+                mt.frames[i] = None
+        mt.voff[mt.M] = self._voff[mt.M]
+        return mt
+
+    def randomize(self, B: int, sample0: Optional[int] = None, variates: Optional[torch.Tensor] = None) -> BatchResult:
+        """B scene samples.  Train mode: sample ``sample0 + b`` depends only on (seed, sample0 + b, sampler row)
+        -- identical for any batch split or rank layout.  Eval mode: B successive ``sample_eval`` steps per
+        sampler.  ``variates`` ([B,S,3]) switches to injected mode (parity tests)."""
+        L = nat.lib()
+        train = bool(self.scene._train)
+        mode = nat.MODE_INJECTED if variates is not None else (nat.MODE_TRAIN if train else nat.MODE_EVAL)
+        if sample0 is None:
+            sample0 = self._next_sample
+            self._next_sample += B
+        S, E = self.S, self.E
+        sampled = torch.empty((B, max(S, 1), 3), dtype=torch.float32, device=self.device)
+        if S:
+            v = None if variates is None else nat.require_cuda(variates.contiguous(), torch.float32, "variates")
+            nat.check(L.ffb_sample(self.sampler_table.data_ptr(), S, B, mode, self.seed, int(sample0), nat.ptr(v),
+                                   sampled.data_ptr(), nat.stream()), "ffb_sample")
+            nat.count()
+        world = torch.empty((B, max(E, 1), 4, 4), dtype=torch.float32, device=self.device)
+        if E:
+            nat.check(L.ffb_compose_world(self.entity_table.data_ptr(), E, B, sampled.data_ptr(), S, world.data_ptr(),
+                                          nat.stream()), "ffb_compose_world")
+            nat.count()
+        verts = None
+        if self.meshes:
+            mt = self._mesh_table(train)
+            idx = None
+            if any(a is not None for a in self._anim_meshes):
+                M = len(self.meshes)
+                lo = [(a._animation_sampler._min_integer_train if train else a._animation_sampler._min_integer_eval) if a else 0
+                      for a in self._anim_meshes]
+                hi = [(a._animation_sampler._max_integer_train if train else a._animation_sampler._max_integer_eval) if a else 0
+                      for a in self._anim_meshes]
+                amin = torch.tensor(lo, dtype=torch.int32, device=self.device)
+                amax = torch.tensor(hi, dtype=torch.int32, device=self.device)
+                idx = torch.empty((B, M), dtype=torch.int32, device=self.device)
+                nat.check(L.ffb_sample_anim_index(amin.data_ptr(), amax.data_ptr(), self._anim_cur.data_ptr(), M, B,
+                                                  nat.MODE_TRAIN if train else nat.MODE_EVAL, self.seed, int(sample0),
+                                                  idx.data_ptr(), nat.stream()), "ffb_sample_anim_index")
+                nat.count()
+            verts = torch.empty((B, self.Vtot, 3), dtype=torch.float32, device=self.device)
+            nat.check(L.ffb_transform_vertices(C.byref(mt), self.verts.data_ptr(), E, B, nat.ptr(idx), world.data_ptr(),
+                                               verts.data_ptr(), nat.stream()), "ffb_transform_vertices")
+            nat.count()
+        return BatchResult(world, sampled, verts, self)
+
+
+class PatternStep:
+    """One pattern-optimisation step over B scene samples on this rank.
+
+    Mirrors the only in-tree optimisation loop of the reference (``test_point_reg``,
+    fireflies/graphics/rasterization.py:586-607): ``summed = baked_sum_2``, ``softored = baked_softor_2``,
+    ``loss = L1(softored, summed)``, backward to ``points`` -- for B samples at once, preceded by the batched scene
+    randomisation.  With ``upstream`` the loss stage is skipped and the given texture gradients (e.g. from the
+    renderer's backward pass) are consumed instead.  The only collective is the allreduce of ``d loss/d points``.
+    """
+
+    def __init__(self, n_points: int, texture_size, sigma: float, batch: int, scene_batch: Optional[SceneBatch] = None,
+                 num_std_sum: int = 4, num_std_softor: int = 5, sum_transposed: bool = True, per_sample_points: bool = True,
+                 device="cuda", process_group=None):
+        self.N, self.B = int(n_points), int(batch)
+        self.ts0, self.ts1 = R._ts(texture_size)
+        self.sigma = float(sigma)
+        self.ns, self.no, self.sum_t = int(num_std_sum), int(num_std_softor), bool(sum_transposed)
+        self.scene_batch = scene_batch
+        self.per_sample = per_sample_points
+        self.device = torch.device(device)
+        self.pg = process_group
+        self.pts_dev = torch.empty((self.B if per_sample_points else 1, self.N, 2), dtype=torch.float32, device=self.device)
+        self.last = None
+
+    def _allreduce(self, t: torch.Tensor) -> None:
+        from .parallel import allreduce_sum_
+        allreduce_sum_(t, self.pg)
+
+    def forward_backward(self, points: torch.Tensor, upstream: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                         sample0: Optional[int] = None):
+        """points: ``[N,2]`` or ``[B,N,2]`` (device, or pinned host -> copied inside).  Returns
+        ``(loss [B] or None, dpoints [N,2] summed over the B samples and all ranks, BatchResult or None)``."""
+        res = self.scene_batch.randomize(self.B, sample0=sample0) if self.scene_batch is not None else None
+        if points.dim() == 2:
+            self.pts_dev.copy_(points.unsqueeze(0).expand_as(self.pts_dev) if self.per_sample else points.unsqueeze(0),
+                               non_blocking=True)
+        else:
+            self.pts_dev.copy_(points, non_blocking=True)
+        pts = self.pts_dev if self.per_sample else self.pts_dev[0]
+        plan = R._SplatPlan(pts, self.B, self.sigma, self.ts0, self.ts1, self.ns, self.no)
+        s, o = plan.forward(pts, True, True, self.sum_t)
+        loss = None
+        if upstream is None:
+            # rasterization.py:589-599: L1(softored, summed) -- the reference compares against the transposed sum as-is
+            loss = torch.empty(self.B, dtype=torch.float32, device=self.device)
+            gs, go = torch.empty_like(s), torch.empty_like(o)
+            nat.check(nat.lib().ffb_l1_loss_fwd_bwd(o.data_ptr(), s.data_ptr(), 0, self.B, self.ts0, self.ts1, loss.data_ptr(),
+                                                    go.data_ptr(), gs.data_ptr(), nat.stream()), "ffb_l1_loss_fwd_bwd")
+            nat.count(2)
+        else:
+            gs, go = upstream
+        d = plan.backward(pts, gs, go, self.sum_t)
+        dp = R.reduce_over_samples(d) if self.B > 1 else d[0]
+        self._allreduce(dp)
+        self.last = (s, o, res)
+        return loss, dp, res
+
+    def step_host(self, points_host: torch.Tensor, out_host: torch.Tensor, loss_host: torch.Tensor, sample0: Optional[int] = None):
+        """End-to-end step with HOST buffers: pinned ``points_host`` [N,2] in, ``out_host`` [N,2] (gradient) and
+        ``loss_host`` [B] out; returns after the device->host copies have completed."""
+        loss, dp, _ = self.forward_backward(points_host, sample0=sample0)
+        out_host.copy_(dp, non_blocking=True)
+        loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return loss_host, out_host

@@ -61,6 +61,13 @@ __global__ void __launch_bounds__(256) sample_kernel(const ffb_sampler* __restri
     out[(size_t)i * 3] = v[0]; out[(size_t)i * 3 + 1] = v[1]; out[(size_t)i * 3 + 2] = v[2];
 }
 
+// utils/math.py:170-175 for arbitrary shapes: out = u * (b - a) + a
+__global__ void __launch_bounds__(256) uniform_between_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                              const float* __restrict__ u, long long n, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = lerp_ref(u[i], a[i], b[i]);
+}
+
 // Sampler.sample_eval (sampling/base.py:64-74) as a state machine, one thread per sampler walking the B
 // successive calls.  Reproduces the reference's aliasing: the value returned is the post-increment
 // _current_step; after the first wrap _current_step *is* _min_range, so stepping drifts vmin.
@@ -307,6 +314,35 @@ __global__ void __launch_bounds__(VT_THREADS) transform_points_kernel(const floa
     xform_block4<DIRS>(pts, out, ((long long)blockIdx.x * VT_THREADS + threadIdx.x) * VT_PER_THREAD, V, T);
 }
 
+// backward of transform_points / transform_directions w.r.t. the points (the laser rays are optimised
+// through projectRaysToNDC, projection/laser.py:262-275): y = h[:3]/h[3], h = T @ [x,1]
+template <bool DIRS>
+__global__ void __launch_bounds__(128) transform_points_bwd_kernel(const float* __restrict__ pts, long long V,
+                                                                   const float* __restrict__ Tg, const float* __restrict__ g,
+                                                                   float* __restrict__ d_pts) {
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    float T[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) T[k] = Tg[k];
+    const float x = pts[3 * v], y = pts[3 * v + 1], z = pts[3 * v + 2];
+    const float g0 = g[3 * v], g1 = g[3 * v + 1], g2 = g[3 * v + 2];
+    float d0, d1, d2, d3;
+    if (DIRS) { d0 = g0; d1 = g1; d2 = g2; d3 = 0.f; }
+    else {
+        const float h0 = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
+        const float h1 = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
+        const float h2 = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
+        const float h3 = fmaf(T[12], x, fmaf(T[13], y, fmaf(T[14], z, T[15])));
+        const float inv = 1.0f / h3;
+        d0 = g0 * inv; d1 = g1 * inv; d2 = g2 * inv;
+        d3 = -(g0 * h0 + g1 * h1 + g2 * h2) * inv * inv;
+    }
+    d_pts[3 * v] = fmaf(T[0], d0, fmaf(T[4], d1, fmaf(T[8], d2, T[12] * d3)));
+    d_pts[3 * v + 1] = fmaf(T[1], d0, fmaf(T[5], d1, fmaf(T[9], d2, T[13] * d3)));
+    d_pts[3 * v + 2] = fmaf(T[2], d0, fmaf(T[6], d1, fmaf(T[10], d2, T[14] * d3)));
+}
+
 __global__ void __launch_bounds__(128) clamp_fov_kernel(const float* __restrict__ rays, int N, const float* __restrict__ M,
                                                         const float* __restrict__ Minv, float lo, float hi, float* __restrict__ out) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -338,6 +374,14 @@ extern "C" int ffb_sample(ffb_sampler* samplers, int32_t S, int32_t B, int32_t m
     cudaStream_t st = as_stream(stream);
     if (mode == FFB_MODE_EVAL) sample_eval_kernel<<<(S + 127) / 128, 128, 0, st>>>(samplers, S, B, out);
     else sample_kernel<<<(unsigned)(((long long)B * S + 255) / 256), 256, 0, st>>>(samplers, S, B, mode, seed, sample0, variates, out);
+    FFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ffb_uniform_between(const float* a, const float* b, const float* u, int64_t n, float* out, void* stream) {
+    if (!a || !b || !u || !out || n < 0) return fail_arg(FFB_E_ARG, "uniform_between: bad argument");
+    if (n == 0) return 0;
+    uniform_between_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(a, b, u, n, out);
     FFB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -387,6 +431,17 @@ extern "C" int ffb_transform_points(const float* pts, int64_t V, const float* T,
     const unsigned grid = (unsigned)((V + VT_CHUNK - 1) / VT_CHUNK);
     if (as_directions) transform_points_kernel<true><<<grid, VT_THREADS, 0, as_stream(stream)>>>(pts, V, T, out);
     else transform_points_kernel<false><<<grid, VT_THREADS, 0, as_stream(stream)>>>(pts, V, T, out);
+    FFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ffb_transform_points_bwd(const float* pts, int64_t V, const float* T, int as_directions, const float* g_out,
+                                        float* d_pts, void* stream) {
+    if (!pts || !T || !g_out || !d_pts || V < 0) return fail_arg(FFB_E_ARG, "transform_points_bwd: bad argument");
+    if (V == 0) return 0;
+    const unsigned grid = (unsigned)((V + 127) / 128);
+    if (as_directions) transform_points_bwd_kernel<true><<<grid, 128, 0, as_stream(stream)>>>(pts, V, T, g_out, d_pts);
+    else transform_points_bwd_kernel<false><<<grid, 128, 0, as_stream(stream)>>>(pts, V, T, g_out, d_pts);
     FFB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -146,6 +146,10 @@ typedef struct ffb_sampler {
 FFB_API int ffb_sample(ffb_sampler* samplers, int32_t S, int32_t B, int32_t mode, uint64_t seed, uint64_t sample0,
                const float* variates, float* out, void* stream);
 
+/* randomBetweenTensors (utils/math.py:170-175) with the torch.rand variates supplied:
+ * out[i] = u[i]*(b[i]-a[i])+a[i], three separately rounded fp32 ops like torch.  All f32 [n]. */
+FFB_API int ffb_uniform_between(const float* a, const float* b, const float* u, int64_t n, float* out, void* stream);
+
 /* AnimationSampler frame indices (sampling/animation.py:27-45), int32 out[b,m].
  * train: min + floor(u*(max-min)) with Philox (python's random.randint stream is not reproducible
  * on a device; the injected path takes host-drawn indices instead); eval: min..max INCLUSIVE walk
@@ -198,6 +202,10 @@ FFB_API int ffb_transform_vertices(const ffb_mesh_table* meshes, const float* ve
 /* transform_points / transform_directions for one matrix (utils/math.py:220-235):
  * out[v] = persp_div(T @ [x,y,z,1])  or  (T @ [x,y,z,0])[:3].   T f32 [16] row-major, DEVICE. */
 FFB_API int ffb_transform_points(const float* pts, int64_t V, const float* T, int as_directions, float* out, void* stream);
+/* its backward w.r.t. pts (torch autograd in the reference; the laser rays are optimised through
+ * projectRaysToNDC): d_pts[v] = J(pts[v])^T g_out[v]. */
+FFB_API int ffb_transform_points_bwd(const float* pts, int64_t V, const float* T, int as_directions, const float* g_out,
+                                     float* d_pts, void* stream);
 
 /* Laser glue (projection/laser.py:199-206, 262-290).  M = K @ FLIP_Y and Minv are DEVICE f32 [16].
  * rays_to_ndc: ndc[n] = persp_div(M @ [ray,1]).
