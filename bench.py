@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- pattern-optimisation scene samples/sec on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload = BASELINE.json configs[2] ("batched pattern optimisation": 4096 laser points into a 2048x2048
+projector texture, 256 randomised scenes per step, fwd+bwd); with N GPUs every rank runs 256 scenes per step
+(weak scaling; N=8 is configs[4], 2048 scenes/step) and the only collective is the allreduce of the [4096,2]
+pattern gradient.  One step = randomise B scenes (sampling + 4x4 compose + 100k-vertex transform), bin + splat
+forward (baked_sum_2 + baked_softor_2 semantics), splat backward against resident upstream texture gradients,
+fold the per-sample gradients, allreduce.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with all inputs resident in HBM; `e2e` is the same step
+through the public API (fireflies_b200.PatternStep.step_host) with HOST buffers for the pattern, the loss and the
+gradient.  `cpu_baseline` / `--impl reference` time the CPU port of the reference algorithm (oracle/) on the host.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_POINTS, TS, SIGMA, V_MESH = 4096, (2048, 2048), 100.0, 100_000
+METRIC = "pattern-opt scene samples/sec (splat fwd+bwd + randomize)"
+UNIT = "scene samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="scene samples per step per GPU")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def config(batch, world):
+    return {"workload": "configs[2] batched pattern optimisation (configs[4] when n_gpus=8)", "points": N_POINTS,
+            "texture": list(TS), "sigma": SIGMA, "reductions": "baked_sum_2(num_std=4,transposed)+baked_softor_2(num_std=5)",
+            "scenes_per_step_per_gpu": batch, "scenes_per_step": batch * world, "mesh_vertices": V_MESH,
+            "mesh_randomisation": "translate+rotate+scale ranged, train mode (Philox)",
+            "parallelism": f"dp{world} over scene samples; allreduce of d(points) [4096,2]",
+            "l2": "inputs larger than L2 (per step 4 x 4.3 GB of textures/gradients vs 126 MB L2); no flush needed"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks (nvidia-smi recipe of B200_PROFILING.md, sampled through NVML during the timed region)
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+               0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop, self._t = [], set(), None, threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t is not None:
+            self._stop.set()
+            self._t.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm (test infrastructure used only as the timed baseline)
+# ---------------------------------------------------------------------------------------------------
+def cpu_scene_step(O, pts, gS, gO, verts, gen):
+    """One scene sample on the CPU: randomise (T,R,S draw + compose + vertex transform), baked_sum_2 + baked_softor_2
+    forward, backward to the points against the upstream gradients."""
+    u = torch.rand(3, 3, generator=gen)
+    t = O.uniform_between(torch.tensor([-0.5, -0.5, -0.5]), torch.tensor([0.5, 0.5, 0.5]), u[0])
+    r = O.uniform_between(torch.tensor([-3.1, -3.1, -3.1]), torch.tensor([3.1, 3.1, 3.1]), u[1])
+    s = O.uniform_between(torch.tensor([0.5, 0.5, 0.5]), torch.tensor([2.0, 2.0, 2.0]), u[2])
+    W = O.compose_world(t, r, s, [0.0, 0.0, 0.0], torch.eye(4), True)
+    v = O.transform_points(verts, W)
+    p = pts.clone().requires_grad_(True)
+    S = O.baked_sum(p, SIGMA, list(TS), transposed=True)
+    So = O.baked_softor(p, SIGMA, list(TS))
+    ((S * gS).sum() + (So * gO).sum()).backward()
+    return p.grad, v
+
+
+def cpu_inputs():
+    g = torch.Generator().manual_seed(0)
+    pts = torch.rand(N_POINTS, 2, generator=g) * 0.96 + 0.02
+    g4 = torch.Generator().manual_seed(4)
+    gS, gO = torch.randn(TS[0], TS[1], generator=g4), torch.randn(TS[1], TS[0], generator=g4)
+    verts = torch.rand(V_MESH, 3, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    return pts, gS, gO, verts
+
+
+def run_cpu(n_scenes, warm=1):
+    from oracle import ff_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pts, gS, gO, verts = cpu_inputs()
+    gen = torch.Generator().manual_seed(2)
+    for _ in range(warm):
+        cpu_scene_step(O, pts, gS, gO, verts, gen)
+    t0 = time.perf_counter()
+    for _ in range(n_scenes):
+        cpu_scene_step(O, pts, gS, gO, verts, gen)
+    dt = time.perf_counter() - t0
+    return n_scenes / dt, cores, dt
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ff_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pts, gS, gO, verts = cpu_inputs()
+    gen = torch.Generator().manual_seed(2)
+    per_step = 1                                  # bounded sample: one scene of the 256-scene step per "step"
+    for _ in range(args.warmup):
+        cpu_scene_step(O, pts, gS, gO, verts, gen)
+    t0 = time.perf_counter()
+    for _ in range(args.steps * per_step):
+        cpu_scene_step(O, pts, gS, gO, verts, gen)
+    dt = time.perf_counter() - t0
+    val = args.steps * per_step / dt
+    sample = f"{per_step} scene sample of the step's {args.batch} per step (full 4096-point / 2048^2 / 100k-vertex size)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(args.batch, 1),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU port of the reference algorithm (oracle/ff_oracle.py, vectorised scatter form of baked_sum_2/"
+                "baked_softor_2 + torch autograd) on all host threads; the reference itself is pure Python and cannot "
+                "travel to the GPU box"}))
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+class _Params(dict):
+    def update(self, *a, **k):
+        if a or k:
+            return super().update(*a, **k)
+
+
+def build_scene(ff, device):
+    verts = torch.rand(V_MESH, 3, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    sc = ff.Scene(_Params(), device=device)
+    m = ff.entity.Mesh("mesh-Bench", verts.to(device), device)
+    c = lambda v: torch.tensor(v, device=device)  # noqa: E731
+    m.translate(c([-0.5, -0.5, -0.5]), c([0.5, 0.5, 0.5]))
+    m.rotate(c([-3.1, -3.1, -3.1]), c([3.1, 3.1, 3.1]))
+    m.scale(c([0.5, 0.5, 0.5]), c([2.0, 2.0, 2.0]))
+    sc._meshes.append(m)
+    sc.train()
+    return sc
+
+
+def main_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: fireflies_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    import fireflies_b200 as ff
+    from fireflies_b200 import _native as nat
+    from fireflies_b200.graphics import rasterization as R
+    from fireflies_b200.parallel import allreduce_sum_, max_over_ranks, shard_samples
+
+    B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
+    hw = TS[0] * TS[1]
+    first, _ = shard_samples(B * world, rank, world)
+    # ---- resident inputs ----
+    g0 = torch.Generator().manual_seed(0)
+    pattern = (torch.rand(N_POINTS, 2, generator=g0) * 0.96 + 0.02).to(device)
+    ptsB = pattern.unsqueeze(0).repeat(B, 1, 1).contiguous()
+    gdev = torch.Generator(device=device).manual_seed(4 + rank)
+    gS = torch.randn(B, TS[0], TS[1], device=device, generator=gdev)       # layout of baked_sum_2 ([ts0, ts1])
+    gO = torch.randn(B, TS[1], TS[0], device=device, generator=gdev)
+    scene = build_scene(ff, device)
+    sb = scene.batch(seed=1234)
+    step_obj = ff.PatternStep(N_POINTS, TS, SIGMA, B, scene_batch=sb, device=device)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    phases = ["randomize", "prepare", "fwd", "bwd", "fold"]
+    marks = [[ev() for _ in range(len(phases) + 1)] for _ in range(K)]
+
+    def one_step(i, rec=None):
+        if rec: rec[0].record()
+        sb.randomize(B, sample0=i * B * world + first)
+        if rec: rec[1].record()
+        plan = R._SplatPlan(ptsB, B, SIGMA, TS[0], TS[1], 4, 5)
+        if rec: rec[2].record()
+        plan.forward(ptsB, True, True, True)
+        if rec: rec[3].record()
+        d = plan.backward(ptsB, gS, gO, True)
+        if rec: rec[4].record()
+        dp = R.reduce_over_samples(d)
+        allreduce_sum_(dp)
+        if rec: rec[5].record()
+        return dp
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(Wm):
+        one_step(i)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = nat.launch_count
+    e0, e1 = ev(), ev()
+    barrier()
+    e0.record()
+    for i in range(K):
+        one_step(Wm + i, marks[i])
+    e1.record()
+    barrier()
+    total_ms = max_over_ranks(e0.elapsed_time(e1), device)
+    launches = nat.launch_count - l0          # our kernels only (the NCCL allreduce is not counted)
+    clk = clocks.stop()
+    ms_step = total_ms / K
+    value = B * world * K / (total_ms * 1e-3)
+    ph_ms = {p: sum(m[j].elapsed_time(m[j + 1]) for m in marks) / K for j, p in enumerate(phases)}
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg = {"fwd": B * (8 * hw + 8 * N_POINTS), "bwd": B * (8 * hw + 16 * N_POINTS), "randomize": B * 24 * V_MESH}
+    dom = max(("fwd", "bwd"), key=lambda p: ph_ms[p])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath):
+        traffic = json.load(open(tpath)).get({"fwd": "splat_fwd_kernel", "bwd": "splat_bwd_kernel"}[dom])
+    ach = alg[dom] / (ph_ms[dom] * 1e-3) / 1e9
+    step_bytes = B * (16 * hw + 16 * N_POINTS + 24 * V_MESH)
+    roofline = {"bound": "hbm", "kernel": f"splat_{dom}_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
+                "whole_step": {"achieved": step_bytes / (ms_step * 1e-3) / 1e9, "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                               "algorithmic_bytes_per_step": step_bytes},
+                "kernels_ms": ph_ms,
+                "kernels_gbs": {p: alg[p] / (ph_ms[p] * 1e-3) / 1e9 for p in alg}}
+
+    # ---- e2e: public API with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        pts_host = pattern.cpu().pin_memory()
+        out_host = torch.empty(N_POINTS, 2).pin_memory()
+        loss_host = torch.empty(B).pin_memory()
+        del gS, gO
+        torch.cuda.empty_cache()
+        for i in range(2):
+            step_obj.step_host(pts_host, out_host, loss_host, sample0=i * B * world + first)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            step_obj.step_host(pts_host, out_host, loss_host, sample0=(2 + i) * B * world + first)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0, device)
+        e2e = {"value": B * world * K / dt, "unit": UNIT, "h2d_bytes_per_step": pts_host.numel() * 4,
+               "d2h_bytes_per_step": (out_host.numel() + loss_host.numel()) * 4, "ms_per_step": dt / K * 1e3,
+               "path": "PatternStep.step_host: pinned pattern H2D -> randomise -> splat fwd -> L1(softor,sum) loss+grad "
+                       "(rasterization.py:589-599) -> splat bwd -> fold -> allreduce -> gradient+loss D2H"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n = 12
+        v, cores, dt = run_cpu(n)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n} scene samples of the 256-scene step at full size ({dt:.1f} s of CPU work), linear extrapolation"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config(B, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clk}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)
