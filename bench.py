@@ -84,7 +84,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02)
 
     def start(self):
         if self.nv is not None:

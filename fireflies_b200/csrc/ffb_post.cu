@@ -9,7 +9,8 @@
 // HBM-bound stencil: each CTA produces a 128x32 output tile.  The input tile + halo is fetched by ONE
 // TMA tensor load (cp.async.bulk.tensor.3d) into shared memory -- out-of-image halo cells arrive as zeros
 // and are never read: the reflect border (kornia border_type="reflect", no edge repeat) is an index remap
-// onto in-tile cells.  Horizontal pass smem->smem, vertical pass smem->registers, noise/clip in registers,
+// onto in-tile cells.  (Measured on B200: the innermost TMA start coordinate must be a multiple of 16 bytes --
+// x = -1 raises 'illegal instruction', x = -4 works, any y works -- so the left halo is padded to 4 texels.)  Horizontal pass smem->smem, vertical pass smem->registers, noise/clip in registers,
 // 128-bit coalesced stores.  Traffic: 4 B read (+ halo re-reads served by L2) + 4 B written per texel.
 #include <cuda.h>
 
@@ -23,6 +24,7 @@ constexpr int TW = 128, TH = 32, THREADS = 256, KMAX = 15;
 struct PostParams {
     int B, H, W;
     int kx, ky, hx, hy;          // taps and left/top halo (k/2)
+    int padl;                    // left halo rounded up to 4 texels: TMA needs a 16-byte aligned inner start coordinate
     int boxw, boxh;              // TMA box (boxw multiple of 4)
     float wx[KMAX], wy[KMAX];
     int noise;
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(THREADS) blur_kernel(const __grid_constant__ C
     }
 
     // ---- stage input tile + halo ----
-    const int gx0 = x0 - q.hx, gy0 = y0 - q.hy;
+    const int gx0 = x0 - q.padl, gy0 = y0 - q.hy;
     if (USE_TMA) {
         if (tid == 0) {
             mbar_init(&bar, 1);
@@ -165,7 +167,8 @@ __global__ void __launch_bounds__(THREADS) blur_kernel(const __grid_constant__ C
         if (gy >= 0 && gy < q.H && x0 + i < q.W) {
             const float* row = in_s + j * q.boxw;
             if (!edge_x) {
-                for (int t = 0; t < q.kx; ++t) acc = fmaf(q.wx[t], row[i + t], acc);
+                const float* r2 = row + i + (q.padl - q.hx);
+                for (int t = 0; t < q.kx; ++t) acc = fmaf(q.wx[t], r2[t], acc);
             } else {
                 for (int t = 0; t < q.kx; ++t) acc = fmaf(q.wx[t], row[reflect(x0 + i + t - q.hx, q.W) - gx0], acc);
             }
@@ -280,7 +283,8 @@ extern "C" int ffb_postprocess(const ffb_post_desc* d, const float* img, const u
     if (q.hx >= d->W || q.hy >= d->H) return fail_arg(FFB_E_ARG, "postprocess: reflect border needs kernel/2 < image side");
     gaussian_taps(q.kx, d->blur_sx, q.wx);
     gaussian_taps(q.ky, d->blur_sy, q.wy);
-    q.boxw = (TW + q.kx - 1 + 3) & ~3;
+    q.padl = (q.hx + 3) & ~3;
+    q.boxw = (TW + q.padl + (q.kx - 1 - q.hx) + 3) & ~3;
     q.boxh = TH + q.ky - 1;
     const size_t smem = (size_t)q.boxh * (q.boxw + TW) * sizeof(float);
     const unsigned tiles = (unsigned)(((d->W + TW - 1) / TW) * ((d->H + TH - 1) / TH));

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import ff_oracle as O
-from tests import fake_mitsuba as fm
+import fake_mitsuba as fm
 
 pytestmark = pytest.mark.gpu
 
