@@ -18,6 +18,8 @@
 //     backward) and caches g in shared memory; pass 2 forms dL/dg per (texel, point), accumulates the two
 //     partial derivatives per lane, reduces them with warp shuffles and issues one shared-memory atomic
 //     per (warp, point), then one global atomic per (tile, point).
+#include <stdlib.h>
+
 #include "ffb_common.cuh"
 
 namespace ffb {
@@ -47,6 +49,9 @@ struct Plan {
     // window parameters
     int fp_s, half_s, h_s;    // baked: fp/half ; dense: h = cut-off half width
     int fp_o, half_o, h_o;
+    int H_s, H_o;             // nominal Chebyshev half widths around floor(P) (fast kernels)
+    bool mask_o;              // the baked soft-OR window is tighter than its exact no-op radius
+    bool fast_ok;             // texture larger than the footprints: clipping is plain intersection
 };
 
 static inline int iceil_sqrt(double x) {
@@ -78,6 +83,11 @@ static int make_plan(const ffb_splat_desc* d, Plan* p) {
     // (2% margin on d^2; exp_neg clamps at w = 87, i.e. g < 1.7e-38 is treated as 0)
     p->h_s = iceil_sqrt((double)d->sigma * sqrt(87.0) * 1.02);
     p->h_o = iceil_sqrt((double)d->sigma * sqrt(17.5) * 1.02);
+    p->H_s = d->num_std_sum > 0 ? p->half_s : p->h_s;
+    p->mask_o = d->num_std_softor > 0 && p->half_o < p->h_o;
+    p->H_o = p->mask_o ? p->half_o : p->h_o;
+    p->fast_ok = (d->num_std_sum == 0 || (d->ts0 > p->fp_s && d->ts1 > p->fp_s)) &&
+                 (d->num_std_softor == 0 || (d->ts0 > p->fp_o && d->ts1 > p->fp_o));
     int w_s = d->num_std_sum > 0 ? p->fp_s : 2 * p->h_s + 1;
     int w_o = d->num_std_softor > 0 ? (p->fp_o < 2 * p->h_o + 1 ? p->fp_o : 2 * p->h_o + 1) : 2 * p->h_o + 1;
     int w = (w_s > w_o ? w_s : w_o) + 1;
@@ -104,6 +114,7 @@ struct PrepParams {
     int N, ts0, ts1, tgx, tgy, T, cap;
     int baked_s, fp_s, half_s, h_s;
     int baked_o, fp_o, half_o, h_o;
+    int h_union;      // max Chebyshev half width of the two (nominal) reduction windows
     PointRec* recs;
     int* tile_off;
     int* list;
@@ -182,6 +193,18 @@ __device__ __forceinline__ PointRec make_rec(const PrepParams& q, float x, float
         else if (eo) { ulo[ax] = lo[0][ax]; uhi[ax] = hi[0][ax]; }
         else { ulo[ax] = min(lo[0][ax], lo[1][ax]); uhi[ax] = max(hi[0][ax], hi[1][ax]); }
     }
+    // the fast kernels mask with the nominal squares floor(P) +- H; make sure binning/culling covers them
+    // (they differ from the reference-exact windows above only when fp32 rounding of P - half crosses an integer)
+#pragma unroll
+    for (int ax = 0; ax < 2; ++ax) {
+        int l2, h2;
+        square_axis(P[ax], q.h_union, ts[ax], l2, h2);
+        if (h2 > l2) {
+            if (uhi[ax] <= ulo[ax]) { ulo[ax] = l2; uhi[ax] = h2; }
+            else { ulo[ax] = min(ulo[ax], l2); uhi[ax] = max(uhi[ax], h2); }
+        }
+    }
+    if (uhi[0] <= ulo[0] || uhi[1] <= ulo[1]) ulo[0] = uhi[0] = ulo[1] = uhi[1] = 0;
     r.uc = pack_win(ulo[0], uhi[0]); r.ur = pack_win(ulo[1], uhi[1]);
     return r;
 }
@@ -526,6 +549,29 @@ __global__ void __launch_bounds__(CTA) splat_bwd_kernel(RasterParams q) {
     }
 }
 
+#include "ffb_splat_fast.cuh"
+
+static FastConsts fast_consts(const ffb_splat_desc* d, const Plan& p) {
+    FastConsts fc;
+    fc.K2 = (float)(-1.4426950408889634 / ((double)d->sigma * (double)d->sigma));
+    fc.thr_s = 4.f * (float)p.H_s + 2.f;
+    fc.thr_o = 4.f * (float)p.H_o + 2.f;
+    return fc;
+}
+static bool use_fast(const Plan& p) {
+    const char* e = getenv("FFB_SPLAT_GENERAL");     // debugging / tests: force the general kernels
+    return p.fast_ok && !(e && e[0] == '1');
+}
+template <typename K>
+static int launch_fast(K kernel, const RasterParams& q, const FastConsts& fc, int B, cudaStream_t st, size_t smem = 0) {
+    const long long grid = (long long)B * q.T;
+    if (grid > 0x7fffffffLL) return fail_arg(FFB_E_LIMIT, "splat: B * tiles exceeds the grid limit");
+    if (smem > 16 * 1024) FFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<(unsigned)grid, CTA, smem, st>>>(q, fc);
+    FFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <typename K>
 static int launch_raster(K kernel, const RasterParams& q, int B, cudaStream_t st, size_t smem = 0) {
     const long long grid = (long long)B * q.T;
@@ -689,6 +735,7 @@ extern "C" int ffb_splat_prepare(const ffb_splat_desc* d, const float* pts, void
     q.N = d->N; q.ts0 = d->ts0; q.ts1 = d->ts1; q.tgx = p.tgx; q.tgy = p.tgy; q.T = p.T; q.cap = p.cap;
     q.baked_s = d->num_std_sum > 0; q.fp_s = p.fp_s; q.half_s = p.half_s; q.h_s = p.h_s;
     q.baked_o = d->num_std_softor > 0; q.fp_o = p.fp_o; q.half_o = p.half_o; q.h_o = p.h_o;
+    q.h_union = p.H_s > p.H_o ? p.H_s : p.H_o;
     q.recs = reinterpret_cast<PointRec*>(w + p.off_recs);
     q.tile_off = reinterpret_cast<int*>(w + p.off_tileoff);
     q.list = reinterpret_cast<int*>(w + p.off_list);
@@ -715,6 +762,16 @@ extern "C" int ffb_splat_fwd(const ffb_splat_desc* d, const float* pts, const vo
     fill_raster(d, p, workspace, q);
     q.out_sum = out_sum; q.out_softor = out_softor;
     cudaStream_t st = as_stream(stream);
+    if (use_fast(p)) {
+        const FastConsts fc = fast_consts(d, p);
+        const int B = d->B;
+#define FFB_FWD(S, O, T) (p.mask_o ? launch_fast(splat_fwd_fast<S, O, T, true>, q, fc, B, st) : launch_fast(splat_fwd_fast<S, O, T, false>, q, fc, B, st))
+        if (out_sum && out_softor) return sum_transposed ? FFB_FWD(true, true, true) : FFB_FWD(true, true, false);
+        if (out_sum) return sum_transposed ? launch_fast(splat_fwd_fast<true, false, true, false>, q, fc, B, st)
+                                           : launch_fast(splat_fwd_fast<true, false, false, false>, q, fc, B, st);
+        return FFB_FWD(false, true, false);
+#undef FFB_FWD
+    }
     if (out_sum && out_softor)
         return sum_transposed ? launch_raster(splat_fwd_kernel<true, true, true>, q, d->B, st)
                               : launch_raster(splat_fwd_kernel<true, true, false>, q, d->B, st);
@@ -738,6 +795,16 @@ extern "C" int ffb_splat_bwd(const ffb_splat_desc* d, const float* pts, const vo
     cudaStream_t st = as_stream(stream);
     FFB_CUDA(cudaMemsetAsync(d_pts, 0, (size_t)d->B * d->N * 2 * sizeof(float), st));
     const size_t gsm = (size_t)(CTA / 32) * KCACHE * WROWS * 32 * sizeof(float);
+    if (use_fast(p)) {
+        const FastConsts fc = fast_consts(d, p);
+        const int B = d->B;
+#define FFB_BWD(S, O, T) (p.mask_o ? launch_fast(splat_bwd_fast<S, O, T, true>, q, fc, B, st, gsm) : launch_fast(splat_bwd_fast<S, O, T, false>, q, fc, B, st, gsm))
+        if (g_sum && g_softor) return sum_transposed ? FFB_BWD(true, true, true) : FFB_BWD(true, true, false);
+        if (g_sum) return sum_transposed ? launch_fast(splat_bwd_fast<true, false, true, false>, q, fc, B, st)
+                                         : launch_fast(splat_bwd_fast<true, false, false, false>, q, fc, B, st);
+        return FFB_BWD(false, true, false);
+#undef FFB_BWD
+    }
     if (g_sum && g_softor)
         return sum_transposed ? launch_raster(splat_bwd_kernel<true, true, true>, q, d->B, st, gsm)
                               : launch_raster(splat_bwd_kernel<true, true, false>, q, d->B, st, gsm);
