@@ -274,7 +274,7 @@ class PatternStep:
             nat.count(2)
         else:
             gs, go = upstream
-        d = plan.backward(pts, gs, go, self.sum_t)
+        d = plan.backward(pts, gs, go, self.sum_t, o)
         dp = R.reduce_over_samples(d) if self.B > 1 else d[0]
         self._allreduce(dp)
         self.last = (s, o, res)

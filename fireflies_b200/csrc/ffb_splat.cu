@@ -7,10 +7,14 @@
 //   + the torch autograd of those w.r.t. `points`.
 //
 // Design (HBM-bound gather, no tensor cores -- nothing here is a contraction):
-//   * prepare: one CTA per sample bins its N points into 64x32 texture tiles (count / scan / fill in
-//     shared memory, lists sorted so accumulation order is deterministic) and writes one 32-byte record
-//     per point: scaled position + the integer clip windows of both reductions.
-//   * forward: one CTA per (tile, sample).  Each warp owns 8 rows x 32 columns, a lane owns one column
+//   * prepare: one CTA per sample bins its N points into texture tiles (count / scan / fill in shared
+//     memory, lists sorted so accumulation order is deterministic) and writes one 32-byte record per
+//     point: scaled position + the integer clip windows of both reductions.  Two tilings: 16x16 warp
+//     tiles with 16-byte list entries for the warp-tile kernels (ffb_splat_wt.cuh, the production path
+//     whenever the texture is larger than the footprints), 64x32 CTA tiles with index lists for the
+//     general kernels below (textures smaller than a footprint, where the reference's slice clipping
+//     is not a plain intersection).
+//   * general forward: one CTA per (tile, sample).  Each warp owns 8 rows x 32 columns, a lane owns one column
 //     (8 texels in registers).  Candidate records are staged in shared memory; rows outside a point's
 //     window are skipped with warp-uniform branches, so only the column overhang is wasted work.  Every
 //     output texel is written exactly once with 128-byte warp stores: traffic = 4 B/texel/reduction.
@@ -32,6 +36,7 @@ constexpr int CTA = 256;      // 8 warps: 2 column halves x 4 row groups
 constexpr int CHUNK = 128;    // candidate records staged per pass
 constexpr int KCACHE = 6;     // cached g slots per warp in the backward (8 rows x 32 lanes each; dynamic smem)
 constexpr int PREP_CTA = 1024;
+constexpr int WT = 16;        // warp tile side of the warp-tile kernels (ffb_splat_wt.cuh)
 
 struct __align__(16) PointRec {
     float p0, p1;             // points * texture_size
@@ -41,9 +46,23 @@ struct __align__(16) PointRec {
 };
 static_assert(sizeof(PointRec) == 32, "PointRec must be 32 bytes");
 
+// list entry of the warp-tile kernels: everything a warp needs about one candidate point
+struct __align__(16) Entry {
+    float p0, p1;             // points * texture_size
+    float f0, f1;             // window origin (integer valued): |c - f0| <= H, |r - f1| <= H
+    uint32_t ur;              // union row span     lo | hi << 16  (half open)
+    uint32_t uc;              // union column span  lo | hi << 16
+    int32_t idx;              // point index (backward: where d/dP goes)
+    uint32_t pad;
+};
+static_assert(sizeof(Entry) == 32, "Entry must be 32 bytes");
+
 struct Plan {
     int Bp;                   // number of binned pattern instances (1 when the pattern is shared)
+    bool fast;                // warp-tile kernels (64x16 super tiles, Entry lists) vs general kernels (64x32, index lists)
+    int tw, th;               // binning tile size
     int tgx, tgy, T;          // tile grid
+    int band_rows;            // tile rows binned per pass of the prepare kernel (shared-memory counters)
     int cap;                  // list capacity per instance
     size_t off_recs, off_tileoff, off_list, total;
     // window parameters
@@ -66,9 +85,6 @@ static int make_plan(const ffb_splat_desc* d, Plan* p) {
     if (!(d->sigma > 0.f)) return fail_arg(FFB_E_ARG, "splat: sigma must be > 0");
     if (d->num_std_sum < 0 || d->num_std_softor < 0) return fail_arg(FFB_E_ARG, "splat: num_std must be >= 0");
     p->Bp = d->pts_batch_stride == 0 ? 1 : d->B;
-    p->tgx = (d->ts0 + TW - 1) / TW;
-    p->tgy = (d->ts1 + TH - 1) / TH;
-    p->T = p->tgx * p->tgy;
     // footprint = odd(floor(sqrt(sigma)) * num_std)  (rasterization.py:180-182; sqrt in fp32 like sigma.sqrt())
     const int root = (int)floorf(sqrtf(d->sigma));
     auto fp_of = [&](int num_std, int* fp, int* half) {
@@ -88,10 +104,25 @@ static int make_plan(const ffb_splat_desc* d, Plan* p) {
     p->H_o = p->mask_o ? p->half_o : p->h_o;
     p->fast_ok = (d->num_std_sum == 0 || (d->ts0 > p->fp_s && d->ts1 > p->fp_s)) &&
                  (d->num_std_softor == 0 || (d->ts0 > p->fp_o && d->ts1 > p->fp_o));
+    {
+        const char* e = getenv("FFB_SPLAT_GENERAL");     // debugging / tests: force the general kernels
+        p->fast = p->fast_ok && d->ts0 <= 32000 && d->ts1 <= 32000 && !(e && e[0] == '1');
+    }
+    p->tw = p->fast ? 4 * WT : TW;
+    p->th = p->fast ? WT : TH;
+    p->tgx = (d->ts0 + p->tw - 1) / p->tw;
+    p->tgy = (d->ts1 + p->th - 1) / p->th;
+    p->T = p->tgx * p->tgy;
+    {
+        const int max_tiles = 20 * 1024;                 // 2 ints of shared memory per tile of a band
+        if (p->tgx > max_tiles) return fail_arg(FFB_E_LIMIT, "splat: texture too wide for the binning kernel");
+        p->band_rows = max_tiles / p->tgx;
+        if (p->band_rows > p->tgy) p->band_rows = p->tgy;
+    }
     int w_s = d->num_std_sum > 0 ? p->fp_s : 2 * p->h_s + 1;
     int w_o = d->num_std_softor > 0 ? (p->fp_o < 2 * p->h_o + 1 ? p->fp_o : 2 * p->h_o + 1) : 2 * p->h_o + 1;
     int w = (w_s > w_o ? w_s : w_o) + 1;
-    long tiles_x = (w + 1) / TW + 2, tiles_y = (w + 1) / TH + 2;
+    long tiles_x = (w + 1) / p->tw + 2, tiles_y = (w + 1) / p->th + 2;
     if (tiles_x > p->tgx) tiles_x = p->tgx;
     if (tiles_y > p->tgy) tiles_y = p->tgy;
     long cap = (long)d->N * tiles_x * tiles_y;
@@ -102,9 +133,8 @@ static int make_plan(const ffb_splat_desc* d, Plan* p) {
     o = (o + 255) & ~(size_t)255;
     p->off_tileoff = o;  o += (size_t)p->Bp * (p->T + 1) * sizeof(int);
     o = (o + 255) & ~(size_t)255;
-    p->off_list = o;     o += (size_t)p->Bp * p->cap * sizeof(int);
+    p->off_list = o;     o += (size_t)p->Bp * p->cap * (p->fast ? sizeof(Entry) : sizeof(int));
     p->total = (o + 255) & ~(size_t)255;
-    if ((size_t)p->T * 2 * sizeof(int) > 200 * 1024) return fail_arg(FFB_E_LIMIT, "splat: too many tiles for the binning kernel");
     return 0;
 }
 
@@ -112,12 +142,15 @@ struct PrepParams {
     const float* pts;
     long long stride;
     int N, ts0, ts1, tgx, tgy, T, cap;
+    int tw, th, band_rows;   // binning tile size, tile rows per shared-memory band
+    int has_sum;             // window origin of the Entry follows the sum's footprint when it has one
     int baked_s, fp_s, half_s, h_s;
     int baked_o, fp_o, half_o, h_o;
     int h_union;      // max Chebyshev half width of the two (nominal) reduction windows
     PointRec* recs;
     int* tile_off;
-    int* list;
+    int* list;        // general kernels: point indices per tile
+    Entry* entries;   // warp-tile kernels: records per super tile
     int* windows;     // nullable
 };
 
@@ -209,99 +242,150 @@ __device__ __forceinline__ PointRec make_rec(const PrepParams& q, float x, float
     return r;
 }
 
+// window origin of the warp-tile kernels' Chebyshev masks along one axis: the reference's (unclipped) slice start
+// floor(P - half) plus half for a baked window (rasterization.py:186), floor(P) otherwise; clamped to int16.
+__device__ __forceinline__ int origin_axis(float P, int baked, int half) {
+    const float fo = floorf(baked ? P - (float)half : P);
+    if (!(fo > -30000.f && fo < 30000.f)) return fo > 0.f ? 32767 : -32768;
+    return (int)fo + (baked ? half : 0);
+}
+
+// One CTA per binned pattern instance.  FAST: 64x16 super tiles, 32-byte entries; otherwise 64x32 CTA tiles,
+// index lists.  The tile grid is processed in bands of whole tile rows so that the
+// counters fit in shared memory for any texture size.
+template <bool FAST>
 __global__ void __launch_bounds__(PREP_CTA) prepare_kernel(PrepParams q) {
     extern __shared__ int sm[];
-    int* cnt = sm;            // [T] counts, then exclusive offsets
-    int* cur = sm + q.T;      // [T] fill cursors
+    const int band_tiles = q.band_rows * q.tgx;
+    int* cnt = sm;                 // [band_tiles] counts, then exclusive offsets
+    int* cur = sm + band_tiles;    // [band_tiles] fill cursors
     __shared__ int warp_tot[32];
+    __shared__ int band_base;
     const int bin = blockIdx.x, tid = threadIdx.x;
     const float* pts = q.pts + (long long)bin * q.stride;
     PointRec* recs = q.recs + (size_t)bin * q.N;
     int* tile_off = q.tile_off + (size_t)bin * (q.T + 1);
-    int* list = q.list + (size_t)bin * q.cap;
+    int* list = q.list + (FAST ? 0 : (size_t)bin * q.cap);
+    Entry* entries = q.entries + (FAST ? (size_t)bin * q.cap : 0);
 
-    for (int i = tid; i < q.T; i += PREP_CTA) cnt[i] = 0;
-    __syncthreads();
-    // 1. records + per-tile counts
+    // records (+ the reference's slice triples)
     for (int n = tid; n < q.N; n += PREP_CTA) {
         const float2 xy = reinterpret_cast<const float2*>(pts)[n];
         int win[12];
-        PointRec r = make_rec(q, xy.x, xy.y, q.windows ? win : nullptr);
-        recs[n] = r;
+        recs[n] = make_rec(q, xy.x, xy.y, q.windows ? win : nullptr);
         if (q.windows) {
             int* w = q.windows + ((size_t)bin * q.N + n) * 12;
 #pragma unroll
             for (int k = 0; k < 12; ++k) w[k] = win[k];
         }
-        const int c_lo = r.uc & 0xffff, c_hi = r.uc >> 16, r_lo = r.ur & 0xffff, r_hi = r.ur >> 16;
-        if (c_hi > c_lo && r_hi > r_lo) {
-            for (int ty = r_lo / TH; ty <= (r_hi - 1) / TH; ++ty)
-                for (int tx = c_lo / TW; tx <= (c_hi - 1) / TW; ++tx) atomicAdd(&cnt[ty * q.tgx + tx], 1);
+    }
+    if (tid == 0) band_base = 0;
+    __syncthreads();
+
+    for (int ty0 = 0; ty0 < q.tgy; ty0 += q.band_rows) {
+        const int ty1 = min(ty0 + q.band_rows, q.tgy);
+        const int nt = (ty1 - ty0) * q.tgx, t0 = ty0 * q.tgx;
+        for (int i = tid; i < nt; i += PREP_CTA) cnt[i] = 0;
+        __syncthreads();
+        // 1. per-tile counts (each thread re-reads the records it wrote itself)
+        for (int n = tid; n < q.N; n += PREP_CTA) {
+            const PointRec r = recs[n];
+            const int c_lo = r.uc & 0xffff, c_hi = r.uc >> 16, r_lo = r.ur & 0xffff, r_hi = r.ur >> 16;
+            if (c_hi > c_lo && r_hi > r_lo) {
+                const int ya = max(r_lo / q.th, ty0), yb = min((r_hi - 1) / q.th, ty1 - 1);
+                for (int ty = ya; ty <= yb; ++ty)
+                    for (int tx = c_lo / q.tw; tx <= (c_hi - 1) / q.tw; ++tx) atomicAdd(&cnt[(ty - ty0) * q.tgx + tx], 1);
+            }
         }
-    }
-    __syncthreads();
-    // 2. exclusive scan over tiles
-    const int per = (q.T + PREP_CTA - 1) / PREP_CTA;
-    const int beg = min(tid * per, q.T), end = min(beg + per, q.T);
-    int local = 0;
-    for (int i = beg; i < end; ++i) local += cnt[i];
-    int incl = local;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((tid & 31) >= o) incl += v;
-    }
-    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
-    __syncthreads();
-    if (tid < 32) {
-        int v = warp_tot[tid], s = v;
+        __syncthreads();
+        // 2. exclusive scan over the band's tiles
+        const int per = (nt + PREP_CTA - 1) / PREP_CTA;
+        const int beg = min(tid * per, nt), end = min(beg + per, nt);
+        int local = 0;
+        for (int i = beg; i < end; ++i) local += cnt[i];
+        int incl = local;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, s, o);
-            if (tid >= o) s += t;
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((tid & 31) >= o) incl += v;
         }
-        warp_tot[tid] = s - v;     // exclusive
-    }
-    __syncthreads();
-    int run = warp_tot[tid >> 5] + incl - local;
-    for (int i = beg; i < end; ++i) {
-        const int c = cnt[i];
-        cnt[i] = run; cur[i] = run; tile_off[i] = run;
-        run += c;
-    }
-    if (tid == PREP_CTA - 1) tile_off[q.T] = run;
-    __syncthreads();
-    // 3. fill
-    for (int n = tid; n < q.N; n += PREP_CTA) {
-        const PointRec r = recs[n];
-        const int c_lo = r.uc & 0xffff, c_hi = r.uc >> 16, r_lo = r.ur & 0xffff, r_hi = r.ur >> 16;
-        if (c_hi > c_lo && r_hi > r_lo) {
-            for (int ty = r_lo / TH; ty <= (r_hi - 1) / TH; ++ty)
-                for (int tx = c_lo / TW; tx <= (c_hi - 1) / TW; ++tx) {
-                    const int pos = atomicAdd(&cur[ty * q.tgx + tx], 1);
-                    if (pos < q.cap) list[pos] = n;
+        if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 32) {
+            int v = warp_tot[tid], sc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, sc, o);
+                if (tid >= o) sc += t;
+            }
+            warp_tot[tid] = sc - v;     // exclusive
+        }
+        __syncthreads();
+        const int base0 = band_base;
+        int run = base0 + warp_tot[tid >> 5] + incl - local;
+        for (int i = beg; i < end; ++i) {
+            const int c = cnt[i];
+            cnt[i] = run; cur[i] = run; tile_off[t0 + i] = run;
+            run += c;
+        }
+        __syncthreads();
+        if (tid == PREP_CTA - 1) band_base = run;      // the last thread's running total covers the whole band
+        // 3. fill
+        for (int n = tid; n < q.N; n += PREP_CTA) {
+            const PointRec r = recs[n];
+            const int c_lo = r.uc & 0xffff, c_hi = r.uc >> 16, r_lo = r.ur & 0xffff, r_hi = r.ur >> 16;
+            if (c_hi > c_lo && r_hi > r_lo) {
+                Entry e;
+                if (FAST) {
+                    const bool bs = q.baked_s != 0, use_s = q.has_sum != 0 && (bs || !q.baked_o);
+                    const int baked = use_s ? (int)bs : q.baked_o, half = use_s ? q.half_s : q.half_o;
+                    const int f0 = origin_axis(r.p0, baked, half), f1 = origin_axis(r.p1, baked, half);
+                    e.p0 = r.p0; e.p1 = r.p1;
+                    e.f0 = (float)f0; e.f1 = (float)f1;
+                    e.ur = r.ur; e.uc = r.uc; e.idx = n; e.pad = 0;
                 }
+                const int ya = max(r_lo / q.th, ty0), yb = min((r_hi - 1) / q.th, ty1 - 1);
+                for (int ty = ya; ty <= yb; ++ty)
+                    for (int tx = c_lo / q.tw; tx <= (c_hi - 1) / q.tw; ++tx) {
+                        const int pos = atomicAdd(&cur[(ty - ty0) * q.tgx + tx], 1);
+                        if (pos < q.cap) {
+                            if (FAST) entries[pos] = e;
+                            else list[pos] = n;
+                        }
+                    }
+            }
         }
-    }
-    __syncthreads();
-    // 4. sort every tile's list by point index -> deterministic accumulation order
-    for (int t = tid; t < q.T; t += PREP_CTA) {
-        const int b = cnt[t], e = min(cur[t], q.cap);
-        for (int i = b + 1; i < e; ++i) {
-            const int v = list[i];
-            int j = i - 1;
-            while (j >= b && list[j] > v) { list[j + 1] = list[j]; --j; }
-            list[j + 1] = v;
+        __syncthreads();
+        // 4. sort every tile's list by point index -> deterministic accumulation order
+        for (int t = tid; t < nt; t += PREP_CTA) {
+            const int b = cnt[t], e = min(cur[t], q.cap);
+            for (int i = b + 1; i < e; ++i) {
+                if (FAST) {
+                    const Entry ev = entries[i];
+                    int j = i - 1;
+                    while (j >= b && entries[j].idx > ev.idx) { entries[j + 1] = entries[j]; --j; }
+                    entries[j + 1] = ev;
+                } else {
+                    const int v = list[i];
+                    int j = i - 1;
+                    while (j >= b && list[j] > v) { list[j + 1] = list[j]; --j; }
+                    list[j + 1] = v;
+                }
+            }
         }
+        __syncthreads();
     }
+    if (tid == 0) tile_off[q.T] = band_base;
 }
 
 struct RasterParams {
     const PointRec* recs;
     const int* tile_off;
     const int* list;
+    const Entry* entries;     // warp-tile kernels
+    const float* saved_softor;
     int shared_pattern;       // 1: every sample uses bin 0
-    int N, ts0, ts1, tgx, T, cap;
+    int N, ts0, ts1, tgx, tgy, T, cap;
     float sigma, rcp_sigma;
     float* out_sum; float* out_softor;            // forward
     const float* g_sum; const float* g_softor;    // backward
@@ -549,25 +633,24 @@ __global__ void __launch_bounds__(CTA) splat_bwd_kernel(RasterParams q) {
     }
 }
 
-#include "ffb_splat_fast.cuh"
+#include "ffb_splat_wt.cuh"
 
-static FastConsts fast_consts(const ffb_splat_desc* d, const Plan& p) {
-    FastConsts fc;
+static WtConsts wt_consts(const ffb_splat_desc* d, const Plan& p) {
+    WtConsts fc;
     fc.K2 = (float)(-1.4426950408889634 / ((double)d->sigma * (double)d->sigma));
     fc.thr_s = 4.f * (float)p.H_s + 2.f;
     fc.thr_o = 4.f * (float)p.H_o + 2.f;
+    fc.hs = (float)p.H_s + 0.5f;
+    fc.ho = (float)p.H_o + 0.5f;
+    fc.c1 = 1.00000011920928955078125f;      // 1 + 2^-23
     return fc;
 }
-static bool use_fast(const Plan& p) {
-    const char* e = getenv("FFB_SPLAT_GENERAL");     // debugging / tests: force the general kernels
-    return p.fast_ok && !(e && e[0] == '1');
-}
 template <typename K>
-static int launch_fast(K kernel, const RasterParams& q, const FastConsts& fc, int B, cudaStream_t st, size_t smem = 0) {
-    const long long grid = (long long)B * q.T;
-    if (grid > 0x7fffffffLL) return fail_arg(FFB_E_LIMIT, "splat: B * tiles exceeds the grid limit");
-    if (smem > 16 * 1024) FFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<(unsigned)grid, CTA, smem, st>>>(q, fc);
+static int launch_wt(K kernel, const RasterParams& q, const WtConsts& fc, int B, cudaStream_t st, size_t smem = 0) {
+    const unsigned gy = (unsigned)((q.tgy + WT_WARPS - 1) / WT_WARPS);
+    if (B > 65535 || gy > 65535) return fail_arg(FFB_E_LIMIT, "splat: B or the tile rows exceed the grid limit (65535)");
+    if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<dim3((unsigned)q.tgx, gy, (unsigned)B), WT_CTA, smem, st>>>(q, fc);
     FFB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -588,8 +671,10 @@ static void fill_raster(const ffb_splat_desc* d, const Plan& p, const void* ws, 
     q.recs = reinterpret_cast<const PointRec*>(w + p.off_recs);
     q.tile_off = reinterpret_cast<const int*>(w + p.off_tileoff);
     q.list = reinterpret_cast<const int*>(w + p.off_list);
+    q.entries = reinterpret_cast<const Entry*>(w + p.off_list);
+    q.saved_softor = nullptr;
     q.shared_pattern = d->pts_batch_stride == 0;
-    q.N = d->N; q.ts0 = d->ts0; q.ts1 = d->ts1; q.tgx = p.tgx; q.T = p.T; q.cap = p.cap;
+    q.N = d->N; q.ts0 = d->ts0; q.ts1 = d->ts1; q.tgx = p.tgx; q.tgy = p.tgy; q.T = p.T; q.cap = p.cap;
     q.sigma = d->sigma; q.rcp_sigma = 1.0f / d->sigma;
     q.out_sum = nullptr; q.out_softor = nullptr; q.g_sum = nullptr; q.g_softor = nullptr; q.d_pts = nullptr;
 }
@@ -733,20 +818,23 @@ extern "C" int ffb_splat_prepare(const ffb_splat_desc* d, const float* pts, void
     PrepParams q;
     q.pts = pts; q.stride = d->pts_batch_stride;
     q.N = d->N; q.ts0 = d->ts0; q.ts1 = d->ts1; q.tgx = p.tgx; q.tgy = p.tgy; q.T = p.T; q.cap = p.cap;
+    q.tw = p.tw; q.th = p.th; q.band_rows = p.band_rows; q.has_sum = 1;
     q.baked_s = d->num_std_sum > 0; q.fp_s = p.fp_s; q.half_s = p.half_s; q.h_s = p.h_s;
     q.baked_o = d->num_std_softor > 0; q.fp_o = p.fp_o; q.half_o = p.half_o; q.h_o = p.h_o;
     q.h_union = p.H_s > p.H_o ? p.H_s : p.H_o;
     q.recs = reinterpret_cast<PointRec*>(w + p.off_recs);
     q.tile_off = reinterpret_cast<int*>(w + p.off_tileoff);
     q.list = reinterpret_cast<int*>(w + p.off_list);
+    q.entries = reinterpret_cast<Entry*>(w + p.off_list);
     q.windows = windows_out;
-    const size_t smem = (size_t)p.T * 2 * sizeof(int);
-    static thread_local size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        FFB_CUDA(cudaFuncSetAttribute(prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+    const size_t smem = (size_t)p.band_rows * p.tgx * 2 * sizeof(int);
+    if (p.fast) {
+        if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prepare_kernel<true><<<p.Bp, PREP_CTA, smem, as_stream(stream)>>>(q);
+    } else {
+        if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(prepare_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prepare_kernel<false><<<p.Bp, PREP_CTA, smem, as_stream(stream)>>>(q);
     }
-    prepare_kernel<<<p.Bp, PREP_CTA, smem, as_stream(stream)>>>(q);
     FFB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -762,13 +850,13 @@ extern "C" int ffb_splat_fwd(const ffb_splat_desc* d, const float* pts, const vo
     fill_raster(d, p, workspace, q);
     q.out_sum = out_sum; q.out_softor = out_softor;
     cudaStream_t st = as_stream(stream);
-    if (use_fast(p)) {
-        const FastConsts fc = fast_consts(d, p);
+    if (p.fast) {
+        const WtConsts fc = wt_consts(d, p);
         const int B = d->B;
-#define FFB_FWD(S, O, T) (p.mask_o ? launch_fast(splat_fwd_fast<S, O, T, true>, q, fc, B, st) : launch_fast(splat_fwd_fast<S, O, T, false>, q, fc, B, st))
+#define FFB_FWD(S, O, T) (p.mask_o ? launch_wt(splat_fwd_wt<S, O, T, true>, q, fc, B, st) : launch_wt(splat_fwd_wt<S, O, T, false>, q, fc, B, st))
         if (out_sum && out_softor) return sum_transposed ? FFB_FWD(true, true, true) : FFB_FWD(true, true, false);
-        if (out_sum) return sum_transposed ? launch_fast(splat_fwd_fast<true, false, true, false>, q, fc, B, st)
-                                           : launch_fast(splat_fwd_fast<true, false, false, false>, q, fc, B, st);
+        if (out_sum) return sum_transposed ? launch_wt(splat_fwd_wt<true, false, true, false>, q, fc, B, st)
+                                           : launch_wt(splat_fwd_wt<true, false, false, false>, q, fc, B, st);
         return FFB_FWD(false, true, false);
 #undef FFB_FWD
     }
@@ -782,7 +870,7 @@ extern "C" int ffb_splat_fwd(const ffb_splat_desc* d, const float* pts, const vo
 }
 
 extern "C" int ffb_splat_bwd(const ffb_splat_desc* d, const float* pts, const void* workspace,
-                             const float* g_sum, int sum_transposed, const float* g_softor,
+                             const float* g_sum, int sum_transposed, const float* g_softor, const float* saved_softor,
                              float* d_pts, void* stream) {
     (void)pts;
     Plan p;
@@ -795,15 +883,19 @@ extern "C" int ffb_splat_bwd(const ffb_splat_desc* d, const float* pts, const vo
     cudaStream_t st = as_stream(stream);
     FFB_CUDA(cudaMemsetAsync(d_pts, 0, (size_t)d->B * d->N * 2 * sizeof(float), st));
     const size_t gsm = (size_t)(CTA / 32) * KCACHE * WROWS * 32 * sizeof(float);
-    if (use_fast(p)) {
-        const FastConsts fc = fast_consts(d, p);
+    if (p.fast) {
+        const WtConsts fc = wt_consts(d, p);
         const int B = d->B;
-#define FFB_BWD(S, O, T) (p.mask_o ? launch_fast(splat_bwd_fast<S, O, T, true>, q, fc, B, st, gsm) : launch_fast(splat_bwd_fast<S, O, T, false>, q, fc, B, st, gsm))
+        q.saved_softor = g_softor ? saved_softor : nullptr;
+        const size_t wsm = 0;
+#define FFB_BWD2(S, O, T, M) (q.saved_softor ? launch_wt(splat_bwd_wt<S, O, T, M, true>, q, fc, B, st, wsm) : launch_wt(splat_bwd_wt<S, O, T, M, false>, q, fc, B, st, wsm))
+#define FFB_BWD(S, O, T) (p.mask_o ? FFB_BWD2(S, O, T, true) : FFB_BWD2(S, O, T, false))
         if (g_sum && g_softor) return sum_transposed ? FFB_BWD(true, true, true) : FFB_BWD(true, true, false);
-        if (g_sum) return sum_transposed ? launch_fast(splat_bwd_fast<true, false, true, false>, q, fc, B, st)
-                                         : launch_fast(splat_bwd_fast<true, false, false, false>, q, fc, B, st);
+        if (g_sum) return sum_transposed ? launch_wt(splat_bwd_wt<true, false, true, false, false>, q, fc, B, st, wsm)
+                                         : launch_wt(splat_bwd_wt<true, false, false, false, false>, q, fc, B, st, wsm);
         return FFB_BWD(false, true, false);
 #undef FFB_BWD
+#undef FFB_BWD2
     }
     if (g_sum && g_softor)
         return sum_transposed ? launch_raster(splat_bwd_kernel<true, true, true>, q, d->B, st, gsm)

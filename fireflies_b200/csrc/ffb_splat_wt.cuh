@@ -1,0 +1,454 @@
+// Warp-tile splat kernels (included by ffb_splat.cu inside namespace ffb::splat).
+//
+// What the ncu captures of the earlier CTA-tile kernels showed (profiles/r01a_baseline): DRAM traffic equals the
+// algorithmic bytes, but only ~22 % of the issued instructions were splat arithmetic -- the rest was per-CTA staging,
+// three block barriers per candidate chunk (29 % of the stall samples) and per-lane culling -- and half of the
+// evaluated (texel, point) pairs lay outside the point's window (8x32 warp blocks around a 43x43 footprint).
+//
+// This version removes the CTA from the picture:
+//   * the binning kernel builds one candidate list per 64x16 SUPER TILE; a list entry is the 32-byte record the
+//     kernel needs (scaled position, window origin, row / column span, point index) -- no index indirection, no
+//     in-kernel culling;
+//   * a warp owns its super tile from the first load to the last store: no __syncthreads, only __syncwarp around a
+//     small per-warp shared table.  It stages the candidates once and then walks the four 16x16 tiles of the super
+//     tile; the 16 rows are common to all four, so everything that depends on (candidate, row) only -- (r - P1)^2,
+//     r - P1, the row masks -- is computed once per warp and read back with one LDS.128 per group;
+//   * inside a 16x16 tile lane = (column 0..15, row half 0..1); the packed fp32 pipe (FADD2/FMUL2/FFMA2) handles
+//     two rows per lane, so one warp instruction covers a 16x4 texel group.  Tiles outside a candidate's column
+//     span and groups outside its row span are skipped with warp-uniform branches: 2668 evaluated pairs per
+//     point for a 43x43 window instead of 3700;
+//   * the column mask of the sum window is a lane predicate on the accumulate, so masks cost no arithmetic;
+//   * g = 2^(d2^2 * K), K = -log2(e)/sigma^2, with d2 = dc*dc + dr*dr rounded exactly like the reference: the inner
+//     group is LDS.128 + FADD2 + 2 FMUL2 + 2 MUFU.EX2 + 2 FFMA2.  With 16 MUFU lanes per SM the exp is the busiest
+//     pipe, which is why the evaluated-pair count above matters;
+//   * soft-OR needs no window at all when the footprint is at least the exact no-op radius (g <= 2^-25 rounds 1-g
+//     to 1): texels outside contribute a bit-exact factor of 1;
+//   * backward: with the forward's soft-OR output at hand (saved_softor) the per-texel product is 1 - O and a single
+//     pass suffices; otherwise a first pass rebuilds it.  Per-lane d/dP partial sums are parked in shared memory
+//     across the four tiles, then folded across the warp with five shuffles for both components at once and leave
+//     the warp as one atomic per component per (candidate, super tile).
+#pragma once
+
+constexpr int WCH = 16;                   // candidates staged per warp per chunk
+constexpr int WT_CTA = 256;               // 8 warps = 8 vertically stacked super tiles = 64 x 128 texels
+constexpr int WT_WARPS = WT_CTA / 32;
+
+struct WtConsts {
+    float K2;                             // -log2(e) / sigma^2
+    float thr_s, thr_o;                   // 4*H + 2 for the sum / soft-OR row masks
+    float hs, ho;                         // H + 0.5 for the column predicates
+    float c1;                             // 1 + 2^-23: keeps 1 - g away from 0 in the backward quotient
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float cheb_mask(float e, float thr) {      // 1 if |e| <= H else 0 (e integer valued)
+    return __saturatef(fmaf(fabsf(e), -4.f, thr));
+}
+__device__ __forceinline__ float2 bc(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+
+// Per-warp staging: candidate records and the (candidate, row pair) tables of the warp's 16 rows.
+template <bool TABB>
+struct WarpStage {
+    float4 cand[WCH];                     // p0, f0, point index (bits), -
+    float2 prow[WCH];                     // p1, f1
+    float4 tabA[WCH][WT / 2];             // dy^2 (2 rows), sum row mask (2 rows)
+    float4 tabB[TABB ? WCH : 1][WT / 2];  // dy (2 rows), soft-OR row mask (2 rows)
+};
+
+// Which staged candidates touch which 16x16 tile / 16x4 row group: warp-uniform ballots, 16 bits per tile / group.
+struct WtMasks {
+    unsigned long long tb, gb;
+};
+
+template <bool TABB>
+__device__ __forceinline__ WtMasks stage_warp(WarpStage<TABB>& s, const Entry* __restrict__ entries, int base, int n,
+                                              int c0, int r0, const WtConsts& fc, int lane) {
+    __syncwarp();                         // previous chunk fully consumed
+    bool ga[4] = {false, false, false, false}, ta[4] = {false, false, false, false};
+    if (lane < n) {
+        const float4 e = __ldg(reinterpret_cast<const float4*>(entries + base + lane));
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(entries + base + lane) + 1);
+        const int rlo = (int)(x.x & 0xffff) - r0, rhi = (int)(x.x >> 16) - r0;      // spans relative to the super tile
+        const int clo = (int)(x.y & 0xffff) - c0, chi = (int)(x.y >> 16) - c0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            ga[i] = rlo < 4 * i + 4 && rhi > 4 * i;
+            ta[i] = clo < WT * i + WT && chi > WT * i;
+        }
+        s.cand[lane] = make_float4(e.x, e.z, __uint_as_float(x.z), 0.f);
+        s.prow[lane] = make_float2(e.y, e.w);
+    }
+    WtMasks m;
+    m.tb = 0; m.gb = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m.tb |= (unsigned long long)__ballot_sync(0xffffffffu, ta[i]) << (16 * i);
+        m.gb |= (unsigned long long)__ballot_sync(0xffffffffu, ga[i]) << (16 * i);
+    }
+    __syncwarp();
+    const float rp = (float)(r0 + 2 * (lane & 7));
+    for (int t = lane; t < n * (WT / 2); t += 32) {
+        const int k = t >> 3, p = t & 7;
+        const float2 pf = s.prow[k];
+        const float ra = rp, rb = rp + 1.f;
+        const float da = ra - pf.x, db = rb - pf.x;
+        const float ea = ra - pf.y, eb = rb - pf.y;
+        s.tabA[k][p] = make_float4(__fmul_rn(da, da), __fmul_rn(db, db), cheb_mask(ea, fc.thr_s), cheb_mask(eb, fc.thr_s));
+        if (TABB) s.tabB[k][p] = make_float4(da, db, cheb_mask(ea, fc.thr_o), cheb_mask(eb, fc.thr_o));
+    }
+    __syncwarp();
+    return m;
+}
+
+// rows held by lane (c, h): 4i + 2h + {0,1}, i = 0..3  <->  one contiguous run of 8 rows (8h .. 8h+7) for the
+// transposed ([ts0, ts1]) layout.  v[2i + j] in, w[0..7] = rows 8h..8h+7 out (and back).
+__device__ __forceinline__ void rows_to_run(const float (&v)[8], float (&w)[8], int h) {
+    float snd[4], rcv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) snd[k] = h ? v[k] : v[4 + k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rcv[k] = __shfl_xor_sync(0xffffffffu, snd[k], 16);
+    // h = 0 keeps its groups 0,1 (rows 0,1,4,5) and receives the partner's groups 0,1 (rows 2,3,6,7);
+    // h = 1 keeps its groups 2,3 (rows 10,11,14,15) and receives the partner's groups 2,3 (rows 8,9,12,13)
+    if (h == 0) { w[0] = v[0]; w[1] = v[1]; w[2] = rcv[0]; w[3] = rcv[1]; w[4] = v[2]; w[5] = v[3]; w[6] = rcv[2]; w[7] = rcv[3]; }
+    else        { w[0] = rcv[0]; w[1] = rcv[1]; w[2] = v[4]; w[3] = v[5]; w[4] = rcv[2]; w[5] = rcv[3]; w[6] = v[6]; w[7] = v[7]; }
+}
+__device__ __forceinline__ void run_to_rows(const float (&w)[8], float (&v)[8], int h) {
+    float snd[4], rcv[4];
+    // h = 0 holds rows 0..7: rows 2,3,6,7 belong to the partner; h = 1 holds rows 8..15: rows 8,9,12,13 belong to the partner
+    if (h == 0) { snd[0] = w[2]; snd[1] = w[3]; snd[2] = w[6]; snd[3] = w[7]; }
+    else        { snd[0] = w[0]; snd[1] = w[1]; snd[2] = w[4]; snd[3] = w[5]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rcv[k] = __shfl_xor_sync(0xffffffffu, snd[k], 16);
+    if (h == 0) { v[0] = w[0]; v[1] = w[1]; v[2] = w[4]; v[3] = w[5]; v[4] = rcv[0]; v[5] = rcv[1]; v[6] = rcv[2]; v[7] = rcv[3]; }
+    else        { v[0] = rcv[0]; v[1] = rcv[1]; v[2] = rcv[2]; v[3] = rcv[3]; v[4] = w[2]; v[5] = w[3]; v[6] = w[6]; v[7] = w[7]; }
+}
+
+// Super tile owned by this warp: grid = (super-tile columns, ceil(super-tile rows / 8), samples).
+struct WtCoord {
+    int b, bin, stile, c0, r0, lane, h, lc;
+    bool valid;
+};
+__device__ __forceinline__ WtCoord wt_coord(const RasterParams& q) {
+    WtCoord w;
+    w.b = blockIdx.z;
+    w.bin = q.shared_pattern ? 0 : w.b;
+    w.lane = threadIdx.x & 31;
+    const int sty = blockIdx.y * WT_WARPS + (threadIdx.x >> 5);
+    w.valid = sty < q.tgy;
+    w.stile = sty * q.tgx + blockIdx.x;
+    w.c0 = blockIdx.x * (4 * WT);
+    w.r0 = sty * WT;
+    w.lc = w.lane & 15;
+    w.h = w.lane >> 4;
+    return w;
+}
+
+// natural [ts1, ts0] tile access: v[2i + j] <-> row r0 + 4i + 2h + j, column c
+__device__ __forceinline__ void store_natural(float* __restrict__ out, const RasterParams& q, const WtCoord& w, int c, const float (&v)[8]) {
+    const int rb = w.r0 + 2 * w.h;
+    float* o = out + ((size_t)w.b * q.ts1 + rb) * q.ts0 + c;
+    if (w.r0 + WT <= q.ts1 && (c | 15) < q.ts0) {          // interior tile (warp-uniform)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            o[0] = v[2 * i];
+            o[q.ts0] = v[2 * i + 1];
+            o += 4 * (size_t)q.ts0;
+        }
+    } else if (c < q.ts0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                if (rb + 4 * i + j < q.ts1) o[(size_t)(4 * i + j) * q.ts0] = v[2 * i + j];
+    }
+}
+__device__ __forceinline__ void load_natural(const float* __restrict__ in, const RasterParams& q, const WtCoord& w, int c, float (&v)[8]) {
+    const int rb = w.r0 + 2 * w.h;
+    const float* p = in + ((size_t)w.b * q.ts1 + rb) * q.ts0 + c;
+    if (w.r0 + WT <= q.ts1 && (c | 15) < q.ts0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = __ldg(p);
+            v[2 * i + 1] = __ldg(p + q.ts0);
+            p += 4 * (size_t)q.ts0;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                v[2 * i + j] = (c < q.ts0 && rb + 4 * i + j < q.ts1) ? __ldg(p + (size_t)(4 * i + j) * q.ts0) : 0.f;
+    }
+}
+// transposed [ts0, ts1] tile access (baked_sum_2's orientation): a lane moves rows 8h..8h+7 of its column as 2 x 128 bit
+__device__ __forceinline__ void store_transposed(float* __restrict__ out, const RasterParams& q, const WtCoord& w, int c, const float (&v)[8]) {
+    float run[8];
+    rows_to_run(v, run, w.h);
+    if (c >= q.ts0) return;
+    const int rr = w.r0 + 8 * w.h;
+    float* o = out + ((size_t)w.b * q.ts0 + c) * q.ts1 + rr;
+    if ((q.ts1 & 3) == 0 && rr + 8 <= q.ts1) {
+        reinterpret_cast<float4*>(o)[0] = make_float4(run[0], run[1], run[2], run[3]);
+        reinterpret_cast<float4*>(o)[1] = make_float4(run[4], run[5], run[6], run[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (rr + k < q.ts1) o[k] = run[k];
+    }
+}
+__device__ __forceinline__ void load_transposed(const float* __restrict__ in, const RasterParams& q, const WtCoord& w, int c, float (&v)[8]) {
+    float run[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) run[k] = 0.f;
+    if (c < q.ts0) {
+        const int rr = w.r0 + 8 * w.h;
+        const float* p = in + ((size_t)w.b * q.ts0 + c) * q.ts1 + rr;
+        if ((q.ts1 & 3) == 0 && rr + 8 <= q.ts1) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p)), d = __ldg(reinterpret_cast<const float4*>(p) + 1);
+            run[0] = a.x; run[1] = a.y; run[2] = a.z; run[3] = a.w; run[4] = d.x; run[5] = d.y; run[6] = d.z; run[7] = d.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (rr + k < q.ts1) run[k] = __ldg(p + k);
+        }
+    }
+    run_to_rows(run, v, w.h);
+}
+
+// one 16x4 group of the soft-OR product (shared by the forward and the backward's first pass)
+template <bool MASK_O>
+__device__ __forceinline__ void prod_group(float2& acc_p, float2 g, bool pco, float2 mo) {
+    if (MASK_O) {
+        if (pco) acc_p = __ffma2_rn(__fmul2_rn(neg2(g), mo), acc_p, acc_p);          // p -= p * g * m
+    } else {
+        acc_p = __ffma2_rn(neg2(g), acc_p, acc_p);                                    // p *= (1 - g)
+    }
+}
+
+// sum and/or soft-OR product of one 16x16 tile over the staged candidates that touch it
+template <bool SUM, bool SOFTOR, bool MASK_O, typename Stage>
+__device__ __forceinline__ void accumulate_tile(const Stage& st, const WtMasks& mk, int j, float cf, int h, const WtConsts& fc,
+                                                float2 (&acc_s)[4], float2 (&acc_p)[4]) {
+    unsigned tm = (unsigned)(mk.tb >> (16 * j)) & 0xffffu;                            // warp-uniform
+    while (tm) {
+        const int k = __ffs(tm) - 1;
+        tm &= tm - 1;
+        const unsigned long long gk = mk.gb >> k;
+        const float4 cd = st.cand[k];
+        const float dx = cf - cd.x;
+        const float dx2 = __fmul_rn(dx, dx);
+        const float ec = fabsf(cf - cd.y);
+        const bool pcs = ec <= fc.hs, pco = ec <= fc.ho;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (gk & (1ull << (16 * i))) {                                            // warp-uniform
+                const float4 A = st.tabA[k][2 * i + h];
+                const float2 d2 = __fadd2_rn(bc(dx2), make_float2(A.x, A.y));        // dc*dc + dr*dr, as the reference
+                const float2 t = __fmul2_rn(__fmul2_rn(d2, d2), bc(fc.K2));
+                const float2 g = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+                if (SUM) { if (pcs) acc_s[i] = __ffma2_rn(g, make_float2(A.z, A.w), acc_s[i]); }
+                if (SOFTOR) {
+                    float2 mo = bc(1.f);
+                    if (MASK_O) { const float4 Bq = st.tabB[k][2 * i + h]; mo = make_float2(Bq.z, Bq.w); }
+                    prod_group<MASK_O>(acc_p[i], g, pco, mo);
+                }
+            }
+        }
+    }
+}
+
+template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O>
+__global__ void __launch_bounds__(WT_CTA, 5) splat_fwd_wt(RasterParams q, WtConsts fc) {
+    __shared__ WarpStage<MASK_O> stage[WT_WARPS];
+    const WtCoord w = wt_coord(q);
+    if (!w.valid) return;                                  // whole warp; no block-level barriers below
+    WarpStage<MASK_O>& st = stage[threadIdx.x >> 5];
+    const int* toff = q.tile_off + (size_t)w.bin * (q.T + 1) + w.stile;
+    const int beg = __ldg(toff), end = __ldg(toff + 1);
+    const Entry* entries = q.entries + (size_t)w.bin * q.cap;
+    const bool single = end - beg <= WCH;
+    WtMasks mk;
+    mk.tb = 0; mk.gb = 0;
+    if (single) mk = stage_warp(st, entries, beg, end - beg, w.c0, w.r0, fc, w.lane);
+
+    for (int j = 0; j < 4; ++j) {
+        const int c = w.c0 + WT * j + w.lc;
+        if (w.c0 + WT * j >= q.ts0) break;
+        const float cf = (float)c;
+        float2 acc_s[4], acc_p[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc_s[i] = bc(0.f); acc_p[i] = bc(1.f); }
+        if (single) {
+            accumulate_tile<SUM, SOFTOR, MASK_O>(st, mk, j, cf, w.h, fc, acc_s, acc_p);
+        } else {
+            for (int base = beg; base < end; base += WCH) {
+                const WtMasks mc = stage_warp(st, entries, base, min(WCH, end - base), w.c0, w.r0, fc, w.lane);
+                accumulate_tile<SUM, SOFTOR, MASK_O>(st, mc, j, cf, w.h, fc, acc_s, acc_p);
+            }
+        }
+        // epilogue: every texel of the tile is written exactly once
+        float v[8];
+        if (SOFTOR) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { v[2 * i] = 1.f - acc_p[i].x; v[2 * i + 1] = 1.f - acc_p[i].y; }
+            store_natural(q.out_softor, q, w, c, v);
+        }
+        if (SUM) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { v[2 * i] = acc_s[i].x; v[2 * i + 1] = acc_s[i].y; }
+            if (SUM_T) store_transposed(q.out_sum, q, w, c, v);
+            else store_natural(q.out_sum, q, w, c, v);
+        }
+    }
+}
+
+// Backward.  dL/dg = gS * m_s + gO * m_o * prod / (1 - g) per (texel, point); dg/dP = 4 g d2 (c - P) / sigma^2.
+// SAVED: the forward's soft-OR output is available, prod = 1 - O; otherwise a first pass rebuilds prod.
+// 1 - g is evaluated as (1 + 2^-23) - g so that a point sitting on a texel centre (g = 1) gives a finite
+// quotient; the texel's weight g*d2*(c - P) vanishes there, and the bias is <= 1.2e-7 relative elsewhere.
+// Each (candidate, tile) partial is folded across the warp at once (lanes 0-15 end up with d/dp0, lanes 16-31 with
+// d/dp1) and kept by the lane whose number is the candidate's slot: `accv` of lane k / k+16 is candidate k's sum.
+template <bool SUM, bool SOFTOR, bool MASK_O, typename Stage>
+__device__ __forceinline__ void weigh_tile(const Stage& st, const WtMasks& mk, int j, float cf, int h, int lc, const WtConsts& fc,
+                                           const float2 (&gs)[4], const float2 (&gp)[4], float& accv) {
+    unsigned tm = (unsigned)(mk.tb >> (16 * j)) & 0xffffu;
+    while (tm) {
+        const int k = __ffs(tm) - 1;
+        tm &= tm - 1;
+        const unsigned long long gk = mk.gb >> k;
+        const float4 cd = st.cand[k];
+        const float dx = cf - cd.x;
+        const float dx2 = __fmul_rn(dx, dx);
+        const float ec = fabsf(cf - cd.y);
+        const bool pcs = ec <= fc.hs, pco = ec <= fc.ho;
+        float2 a0 = bc(0.f), a1 = bc(0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (gk & (1ull << (16 * i))) {
+                const float4 A = st.tabA[k][2 * i + h];
+                const float4 Bq = st.tabB[k][2 * i + h];
+                const float2 d2 = __fadd2_rn(bc(dx2), make_float2(A.x, A.y));
+                const float2 t = __fmul2_rn(__fmul2_rn(d2, d2), bc(fc.K2));
+                const float2 g = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+                float2 coef = bc(0.f);
+                if (SOFTOR) {
+                    if (MASK_O) {
+                        const float2 mm = pco ? make_float2(Bq.z, Bq.w) : bc(0.f);
+                        const float2 om = __ffma2_rn(neg2(g), mm, bc(fc.c1));
+                        coef = __fmul2_rn(__fmul2_rn(gp[i], mm), make_float2(rcp_approx(om.x), rcp_approx(om.y)));
+                    } else {
+                        const float2 om = __fadd2_rn(bc(fc.c1), neg2(g));
+                        coef = __fmul2_rn(gp[i], make_float2(rcp_approx(om.x), rcp_approx(om.y)));   // gO * prod_{m != n}(1 - g_m)
+                    }
+                }
+                if (SUM) { if (pcs) coef = __ffma2_rn(gs[i], make_float2(A.z, A.w), coef); }
+                const float2 wgt = __fmul2_rn(__fmul2_rn(coef, g), d2);
+                a0 = __ffma2_rn(wgt, bc(dx), a0);
+                a1 = __ffma2_rn(wgt, make_float2(Bq.x, Bq.y), a1);
+            }
+        }
+        const float s0 = a0.x + a0.y, s1 = a1.x + a1.y;
+        float x = h ? s1 : s0;
+        const float y = h ? s0 : s1;
+        x += __shfl_xor_sync(0xffffffffu, y, 16);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lc == k) accv += x;
+    }
+}
+
+template <typename Stage>
+__device__ __forceinline__ void flush_warp(const Stage& st, int n, int lc, float kh, float* __restrict__ dp, float& accv) {
+    if (lc < n) {
+        const float val = accv * kh;
+        if (val != 0.f) atomicAdd(dp + (size_t)__float_as_int(st.cand[lc].z) * 2, val);
+    }
+    accv = 0.f;
+}
+
+template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O, bool SAVED>
+__global__ void __launch_bounds__(WT_CTA, 4) splat_bwd_wt(RasterParams q, WtConsts fc) {
+    typedef WarpStage<true> Stage;
+    __shared__ Stage stage[WT_WARPS];
+    const WtCoord w = wt_coord(q);
+    if (!w.valid) return;
+    Stage& st = stage[threadIdx.x >> 5];
+    const int* toff = q.tile_off + (size_t)w.bin * (q.T + 1) + w.stile;
+    const int beg = __ldg(toff), end = __ldg(toff + 1);
+    if (beg == end) return;
+    const Entry* entries = q.entries + (size_t)w.bin * q.cap;
+    const bool single = end - beg <= WCH;
+    const float inv_s2 = q.rcp_sigma * q.rcp_sigma;
+    const float kh = 4.f * (w.h ? (float)q.ts1 : (float)q.ts0) * inv_s2;     // lanes 0-15 report d/dp0, lanes 16-31 d/dp1
+    float* dp = q.d_pts + (size_t)w.b * q.N * 2 + w.h;
+    float accv = 0.f;
+    WtMasks mk;
+    mk.tb = 0; mk.gb = 0;
+    if (single) mk = stage_warp(st, entries, beg, end - beg, w.c0, w.r0, fc, w.lane);
+
+    for (int j = 0; j < 4; ++j) {
+        const int c = w.c0 + WT * j + w.lc;
+        if (w.c0 + WT * j >= q.ts0) break;
+        const float cf = (float)c;
+        // upstream gradients of this lane's 8 texels
+        float2 gs[4], gp[4];
+        {
+            float v[8];
+            if (SUM) {
+                if (SUM_T) load_transposed(q.g_sum, q, w, c, v);
+                else load_natural(q.g_sum, q, w, c, v);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) gs[i] = make_float2(v[2 * i], v[2 * i + 1]);
+            }
+            if (SOFTOR) {
+                load_natural(q.g_softor, q, w, c, v);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) gp[i] = make_float2(v[2 * i], v[2 * i + 1]);
+                if (SAVED) {
+                    load_natural(q.saved_softor, q, w, c, v);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) gp[i] = __fmul2_rn(gp[i], make_float2(1.f - v[2 * i], 1.f - v[2 * i + 1]));
+                }
+            }
+        }
+        // pass 1 (only without the saved output): per-texel product of (1 - g)
+        if (SOFTOR && !SAVED) {
+            float2 prod[4], unused[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) prod[i] = bc(1.f);
+            if (single) {
+                accumulate_tile<false, true, MASK_O>(st, mk, j, cf, w.h, fc, unused, prod);
+            } else {
+                for (int base = beg; base < end; base += WCH) {
+                    const WtMasks mc = stage_warp(st, entries, base, min(WCH, end - base), w.c0, w.r0, fc, w.lane);
+                    accumulate_tile<false, true, MASK_O>(st, mc, j, cf, w.h, fc, unused, prod);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) gp[i] = __fmul2_rn(gp[i], prod[i]);
+        }
+        // pass 2: weights
+        if (single) {
+            weigh_tile<SUM, SOFTOR, MASK_O>(st, mk, j, cf, w.h, w.lc, fc, gs, gp, accv);
+        } else {
+            for (int base = beg; base < end; base += WCH) {
+                const int n = min(WCH, end - base);
+                const WtMasks mc = stage_warp(st, entries, base, n, w.c0, w.r0, fc, w.lane);
+                weigh_tile<SUM, SOFTOR, MASK_O>(st, mc, j, cf, w.h, w.lc, fc, gs, gp, accv);
+                flush_warp(st, n, w.lc, kh, dp, accv);
+            }
+        }
+    }
+    if (single) flush_warp(st, end - beg, w.lc, kh, dp, accv);
+}

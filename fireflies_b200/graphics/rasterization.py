@@ -87,11 +87,13 @@ class _SplatPlan:
         nat.count()
         return out_s, out_o
 
-    def backward(self, points, g_sum, g_softor, sum_transposed: bool) -> torch.Tensor:
+    def backward(self, points, g_sum, g_softor, sum_transposed: bool, saved_softor=None) -> torch.Tensor:
+        """``saved_softor``: the forward's soft-OR output (what autograd saves for ``prod``'s backward); lets the
+        kernel read the per-texel product back instead of rebuilding it."""
         d_pts = torch.empty((self.B, self.N, 2), dtype=torch.float32, device=points.device)
         nat.check(nat.lib().ffb_splat_bwd(C.byref(self.desc), points.data_ptr(), self.ws.data_ptr(), nat.ptr(g_sum),
-                                          int(sum_transposed), nat.ptr(g_softor), d_pts.data_ptr(), nat.stream()),
-                  "ffb_splat_bwd")
+                                          int(sum_transposed), nat.ptr(g_softor), nat.ptr(saved_softor), d_pts.data_ptr(),
+                                          nat.stream()), "ffb_splat_bwd")
         nat.count(2)      # memset + kernel
         return d_pts
 
@@ -117,6 +119,8 @@ class _SplatReduceFn(torch.autograd.Function):
         empty = pts.new_empty(0)
         outs = (out_s if want_sum else empty, out_o if want_softor else empty)
         ctx.mark_non_differentiable(*[o for o, w in zip(outs, (want_sum, want_softor)) if not w])
+        if want_softor:
+            ctx.save_for_backward(outs[1])      # like torch.prod's backward, keep the output (version-checked)
         return outs
 
     @staticmethod
@@ -127,7 +131,7 @@ class _SplatReduceFn(torch.autograd.Function):
         if gs is None and go is None:
             return (None,) * 10
         plan = ctx.plan
-        d = plan.backward(ctx.pts, gs, go, sum_t)
+        d = plan.backward(ctx.pts, gs, go, sum_t, ctx.saved_tensors[0] if go is not None else None)
         if plan.shared:
             d = d[0] if plan.B == 1 else reduce_over_samples(d)
         return (d,) + (None,) * 9

@@ -88,10 +88,13 @@ FFB_API int ffb_splat_fwd(const ffb_splat_desc* d, const float* pts, const void*
 
 /* Backward of ffb_splat_fwd w.r.t. pts (the autograd the reference gets from torch,
  * SURVEY.md 8(a) a7).  d_pts [B,N,2] f32 is OVERWRITTEN (zeroed, then accumulated).
- *   g_sum     NULL or upstream gradient of out_sum, same layout as out_sum
- *   g_softor  NULL or upstream gradient of out_softor */
+ *   g_sum        NULL or upstream gradient of out_sum, same layout as out_sum
+ *   g_softor     NULL or upstream gradient of out_softor
+ *   saved_softor NULL or the out_softor that ffb_splat_fwd wrote for these points (what torch autograd
+ *                keeps for prod's backward): the per-texel product is then read back as 1 - out_softor
+ *                instead of being rebuilt by a first pass over the candidates */
 FFB_API int ffb_splat_bwd(const ffb_splat_desc* d, const float* pts, const void* workspace,
-                  const float* g_sum, int sum_transposed, const float* g_softor,
+                  const float* g_sum, int sum_transposed, const float* g_softor, const float* saved_softor,
                   float* d_pts, void* stream);
 
 /* sum over the sample axis: out[N*2] = sum_b in[b, N*2]  (fixed order -> deterministic);

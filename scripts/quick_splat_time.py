@@ -12,7 +12,7 @@ ptsB = pts.unsqueeze(0).repeat(B, 1, 1).contiguous()
 plan = R._SplatPlan(ptsB, B, 100.0, ts[0], ts[1], 4, 5)
 gS = torch.randn(B, ts[0], ts[1], device="cuda")
 gO = torch.randn(B, ts[1], ts[0], device="cuda")
-def t(fn, n=5):
+def t(fn, n=3):
     fn(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
@@ -21,7 +21,10 @@ def t(fn, n=5):
     return e0.elapsed_time(e1) / n
 tp = t(lambda: R._SplatPlan(ptsB, B, 100.0, ts[0], ts[1], 4, 5))
 tf = t(lambda: plan.forward(ptsB, True, True, True))
-tb = t(lambda: plan.backward(ptsB, gS, gO, True))
+S_, O_ = plan.forward(ptsB, True, True, True)
+tb = t(lambda: plan.backward(ptsB, gS, gO, True, O_))
+tb2 = t(lambda: plan.backward(ptsB, gS, gO, True))
+print(f"bwd without saved softor: {tb2:.3f} ms")
 hw = ts[0] * ts[1]
 print(f"B={B} prepare {tp:.3f} ms  fwd {tf:.3f} ms ({B*8*hw/tf/1e6:.0f} GB/s)  bwd {tb:.3f} ms ({B*8*hw/tb/1e6:.0f} GB/s)"
       f"  fwd+bwd per sample {(tf+tb)/B*1e3:.2f} us -> {B/(tf+tb)*1e3:.0f} samples/s, roofline frac {(B*(16*hw+16*N)/((tp+tf+tb)*1e-3))/6445.6e9:.3f}")
