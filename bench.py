@@ -235,9 +235,9 @@ def main_ours(args):
         if rec: rec[1].record()
         plan = R._SplatPlan(ptsB, B, SIGMA, TS[0], TS[1], 4, 5)
         if rec: rec[2].record()
-        plan.forward(ptsB, True, True, True)
+        _, softor = plan.forward(ptsB, True, True, True)
         if rec: rec[3].record()
-        d = plan.backward(ptsB, gS, gO, True)
+        d = plan.backward(ptsB, gS, gO, True, softor)      # like autograd: the forward's soft-OR output is kept for the backward
         if rec: rec[4].record()
         dp = R.reduce_over_samples(d)
         allreduce_sum_(dp)
@@ -279,10 +279,10 @@ def main_ours(args):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath):
-        traffic = json.load(open(tpath)).get({"fwd": "splat_fwd_kernel", "bwd": "splat_bwd_kernel"}[dom])
+        traffic = json.load(open(tpath)).get({"fwd": "splat_fwd_wt", "bwd": "splat_bwd_wt"}[dom])
     ach = alg[dom] / (ph_ms[dom] * 1e-3) / 1e9
     step_bytes = B * (16 * hw + 16 * N_POINTS + 24 * V_MESH)
-    roofline = {"bound": "hbm", "kernel": f"splat_{dom}_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+    roofline = {"bound": "hbm", "kernel": f"splat_{dom}_wt", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
                 "whole_step": {"achieved": step_bytes / (ms_step * 1e-3) / 1e9, "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
                                "algorithmic_bytes_per_step": step_bytes},

@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libffb200.so")
+LIB_PATH = os.environ.get("FFB_LIB") or os.path.join(_HERE, "_lib", "libffb200.so")   # FFB_LIB: kernel A/B builds (scripts/ab_build.py)
 
 FFB_MAX_MESHES = 32
 MODE_TRAIN, MODE_EVAL, MODE_INJECTED = 0, 1, 2

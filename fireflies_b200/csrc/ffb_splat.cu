@@ -64,7 +64,7 @@ struct Plan {
     int tgx, tgy, T;          // tile grid
     int band_rows;            // tile rows binned per pass of the prepare kernel (shared-memory counters)
     int cap;                  // list capacity per instance
-    size_t off_recs, off_tileoff, off_list, total;
+    size_t off_recs, off_tileoff, off_list, off_entries, total;
     // window parameters
     int fp_s, half_s, h_s;    // baked: fp/half ; dense: h = cut-off half width
     int fp_o, half_o, h_o;
@@ -133,7 +133,9 @@ static int make_plan(const ffb_splat_desc* d, Plan* p) {
     o = (o + 255) & ~(size_t)255;
     p->off_tileoff = o;  o += (size_t)p->Bp * (p->T + 1) * sizeof(int);
     o = (o + 255) & ~(size_t)255;
-    p->off_list = o;     o += (size_t)p->Bp * p->cap * (p->fast ? sizeof(Entry) : sizeof(int));
+    p->off_list = o;     o += (size_t)p->Bp * p->cap * sizeof(int);
+    o = (o + 255) & ~(size_t)255;
+    p->off_entries = o;  o += p->fast ? (size_t)p->Bp * p->cap * sizeof(Entry) : 0;
     p->total = (o + 255) & ~(size_t)255;
     return 0;
 }
@@ -143,7 +145,6 @@ struct PrepParams {
     long long stride;
     int N, ts0, ts1, tgx, tgy, T, cap;
     int tw, th, band_rows;   // binning tile size, tile rows per shared-memory band
-    int has_sum;             // window origin of the Entry follows the sum's footprint when it has one
     int baked_s, fp_s, half_s, h_s;
     int baked_o, fp_o, half_o, h_o;
     int h_union;      // max Chebyshev half width of the two (nominal) reduction windows
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(PREP_CTA) prepare_kernel(PrepParams q) {
     const float* pts = q.pts + (long long)bin * q.stride;
     PointRec* recs = q.recs + (size_t)bin * q.N;
     int* tile_off = q.tile_off + (size_t)bin * (q.T + 1);
-    int* list = q.list + (FAST ? 0 : (size_t)bin * q.cap);
+    int* list = q.list + (size_t)bin * q.cap;          // FAST: unsorted scratch; otherwise the final index lists
     Entry* entries = q.entries + (FAST ? (size_t)bin * q.cap : 0);
 
     // records (+ the reference's slice triples)
@@ -330,42 +331,40 @@ __global__ void __launch_bounds__(PREP_CTA) prepare_kernel(PrepParams q) {
         }
         __syncthreads();
         if (tid == PREP_CTA - 1) band_base = run;      // the last thread's running total covers the whole band
-        // 3. fill
+        // 3. fill (arrival order)
         for (int n = tid; n < q.N; n += PREP_CTA) {
             const PointRec r = recs[n];
             const int c_lo = r.uc & 0xffff, c_hi = r.uc >> 16, r_lo = r.ur & 0xffff, r_hi = r.ur >> 16;
             if (c_hi > c_lo && r_hi > r_lo) {
-                Entry e;
-                if (FAST) {
-                    const bool bs = q.baked_s != 0, use_s = q.has_sum != 0 && (bs || !q.baked_o);
-                    const int baked = use_s ? (int)bs : q.baked_o, half = use_s ? q.half_s : q.half_o;
-                    const int f0 = origin_axis(r.p0, baked, half), f1 = origin_axis(r.p1, baked, half);
-                    e.p0 = r.p0; e.p1 = r.p1;
-                    e.f0 = (float)f0; e.f1 = (float)f1;
-                    e.ur = r.ur; e.uc = r.uc; e.idx = n; e.pad = 0;
-                }
                 const int ya = max(r_lo / q.th, ty0), yb = min((r_hi - 1) / q.th, ty1 - 1);
                 for (int ty = ya; ty <= yb; ++ty)
                     for (int tx = c_lo / q.tw; tx <= (c_hi - 1) / q.tw; ++tx) {
                         const int pos = atomicAdd(&cur[(ty - ty0) * q.tgx + tx], 1);
-                        if (pos < q.cap) {
-                            if (FAST) entries[pos] = e;
-                            else list[pos] = n;
-                        }
+                        if (pos < q.cap) list[pos] = n;
                     }
             }
         }
         __syncthreads();
-        // 4. sort every tile's list by point index -> deterministic accumulation order
+        // 4. order every tile's list by point index -> deterministic accumulation order
         for (int t = tid; t < nt; t += PREP_CTA) {
             const int b = cnt[t], e = min(cur[t], q.cap);
-            for (int i = b + 1; i < e; ++i) {
-                if (FAST) {
-                    const Entry ev = entries[i];
-                    int j = i - 1;
-                    while (j >= b && entries[j].idx > ev.idx) { entries[j + 1] = entries[j]; --j; }
-                    entries[j + 1] = ev;
-                } else {
+            if (FAST) {
+                // rank sort straight into the entry list: independent loads, no serial chain through global memory
+                for (int i = b; i < e; ++i) {
+                    const int v = list[i];
+                    int rank = 0;
+                    for (int j = b; j < e; ++j) rank += list[j] < v;
+                    const PointRec r = recs[v];
+                    const bool bs = q.baked_s != 0;
+                    const int baked = (bs || !q.baked_o) ? (int)bs : 1, half = (bs || !q.baked_o) ? q.half_s : q.half_o;
+                    Entry en;
+                    en.p0 = r.p0; en.p1 = r.p1;
+                    en.f0 = (float)origin_axis(r.p0, baked, half); en.f1 = (float)origin_axis(r.p1, baked, half);
+                    en.ur = r.ur; en.uc = r.uc; en.idx = v; en.pad = 0;
+                    entries[b + rank] = en;
+                }
+            } else {
+                for (int i = b + 1; i < e; ++i) {
                     const int v = list[i];
                     int j = i - 1;
                     while (j >= b && list[j] > v) { list[j + 1] = list[j]; --j; }
@@ -671,7 +670,7 @@ static void fill_raster(const ffb_splat_desc* d, const Plan& p, const void* ws, 
     q.recs = reinterpret_cast<const PointRec*>(w + p.off_recs);
     q.tile_off = reinterpret_cast<const int*>(w + p.off_tileoff);
     q.list = reinterpret_cast<const int*>(w + p.off_list);
-    q.entries = reinterpret_cast<const Entry*>(w + p.off_list);
+    q.entries = reinterpret_cast<const Entry*>(w + p.off_entries);
     q.saved_softor = nullptr;
     q.shared_pattern = d->pts_batch_stride == 0;
     q.N = d->N; q.ts0 = d->ts0; q.ts1 = d->ts1; q.tgx = p.tgx; q.tgy = p.tgy; q.T = p.T; q.cap = p.cap;
@@ -818,14 +817,14 @@ extern "C" int ffb_splat_prepare(const ffb_splat_desc* d, const float* pts, void
     PrepParams q;
     q.pts = pts; q.stride = d->pts_batch_stride;
     q.N = d->N; q.ts0 = d->ts0; q.ts1 = d->ts1; q.tgx = p.tgx; q.tgy = p.tgy; q.T = p.T; q.cap = p.cap;
-    q.tw = p.tw; q.th = p.th; q.band_rows = p.band_rows; q.has_sum = 1;
+    q.tw = p.tw; q.th = p.th; q.band_rows = p.band_rows;
     q.baked_s = d->num_std_sum > 0; q.fp_s = p.fp_s; q.half_s = p.half_s; q.h_s = p.h_s;
     q.baked_o = d->num_std_softor > 0; q.fp_o = p.fp_o; q.half_o = p.half_o; q.h_o = p.h_o;
     q.h_union = p.H_s > p.H_o ? p.H_s : p.H_o;
     q.recs = reinterpret_cast<PointRec*>(w + p.off_recs);
     q.tile_off = reinterpret_cast<int*>(w + p.off_tileoff);
     q.list = reinterpret_cast<int*>(w + p.off_list);
-    q.entries = reinterpret_cast<Entry*>(w + p.off_list);
+    q.entries = reinterpret_cast<Entry*>(w + p.off_entries);
     q.windows = windows_out;
     const size_t smem = (size_t)p.band_rows * p.tgx * 2 * sizeof(int);
     if (p.fast) {

@@ -32,6 +32,18 @@
 constexpr int WCH = 16;                   // candidates staged per warp per chunk
 constexpr int WT_CTA = 256;               // 8 warps = 8 vertically stacked super tiles = 64 x 128 texels
 constexpr int WT_WARPS = WT_CTA / 32;
+#ifndef FFB_GROUP_SKIP_FWD
+#define FFB_GROUP_SKIP_FWD 0              // 1: skip 16x4 row groups outside a candidate's row span with warp-uniform branches
+#endif
+#ifndef FFB_GROUP_SKIP_BWD
+#define FFB_GROUP_SKIP_BWD 0
+#endif
+#ifndef FFB_FWD_MINB
+#define FFB_FWD_MINB 4                    // resident CTAs per SM the register allocation aims for
+#endif
+#ifndef FFB_BWD_MINB
+#define FFB_BWD_MINB 3
+#endif
 
 struct WtConsts {
     float K2;                             // -log2(e) / sigma^2
@@ -59,42 +71,40 @@ __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y
 // Per-warp staging: candidate records and the (candidate, row pair) tables of the warp's 16 rows.
 template <bool TABB>
 struct WarpStage {
-    float4 cand[WCH];                     // p0, f0, point index (bits), -
+    float4 cand[WCH];                     // p0, f0, point index (bits), row-group mask (bits)
     float2 prow[WCH];                     // p1, f1
     float4 tabA[WCH][WT / 2];             // dy^2 (2 rows), sum row mask (2 rows)
     float4 tabB[TABB ? WCH : 1][WT / 2];  // dy (2 rows), soft-OR row mask (2 rows)
 };
 
-// Which staged candidates touch which 16x16 tile / 16x4 row group: warp-uniform ballots, 16 bits per tile / group.
+// Which staged candidates touch which 16x16 tile: warp-uniform ballots, 16 bits per tile.  (Which 16x4 row groups a
+// candidate touches travels with its record.)
 struct WtMasks {
-    unsigned long long tb, gb;
+    unsigned tb01, tb23;
 };
 
 template <bool TABB>
 __device__ __forceinline__ WtMasks stage_warp(WarpStage<TABB>& s, const Entry* __restrict__ entries, int base, int n,
                                               int c0, int r0, const WtConsts& fc, int lane) {
     __syncwarp();                         // previous chunk fully consumed
-    bool ga[4] = {false, false, false, false}, ta[4] = {false, false, false, false};
+    bool ta[4] = {false, false, false, false};
     if (lane < n) {
         const float4 e = __ldg(reinterpret_cast<const float4*>(entries + base + lane));
         const uint4 x = __ldg(reinterpret_cast<const uint4*>(entries + base + lane) + 1);
         const int rlo = (int)(x.x & 0xffff) - r0, rhi = (int)(x.x >> 16) - r0;      // spans relative to the super tile
         const int clo = (int)(x.y & 0xffff) - c0, chi = (int)(x.y >> 16) - c0;
+        unsigned gm = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            ga[i] = rlo < 4 * i + 4 && rhi > 4 * i;
+            if (rlo < 4 * i + 4 && rhi > 4 * i) gm |= 1u << i;
             ta[i] = clo < WT * i + WT && chi > WT * i;
         }
-        s.cand[lane] = make_float4(e.x, e.z, __uint_as_float(x.z), 0.f);
+        s.cand[lane] = make_float4(e.x, e.z, __uint_as_float(x.z), __uint_as_float(gm));
         s.prow[lane] = make_float2(e.y, e.w);
     }
     WtMasks m;
-    m.tb = 0; m.gb = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        m.tb |= (unsigned long long)__ballot_sync(0xffffffffu, ta[i]) << (16 * i);
-        m.gb |= (unsigned long long)__ballot_sync(0xffffffffu, ga[i]) << (16 * i);
-    }
+    m.tb01 = __ballot_sync(0xffffffffu, ta[0]) | (__ballot_sync(0xffffffffu, ta[1]) << 16);
+    m.tb23 = __ballot_sync(0xffffffffu, ta[2]) | (__ballot_sync(0xffffffffu, ta[3]) << 16);
     __syncwarp();
     const float rp = (float)(r0 + 2 * (lane & 7));
     for (int t = lane; t < n * (WT / 2); t += 32) {
@@ -154,18 +164,32 @@ __device__ __forceinline__ WtCoord wt_coord(const RasterParams& q) {
     return w;
 }
 
-// natural [ts1, ts0] tile access: v[2i + j] <-> row r0 + 4i + 2h + j, column c
-__device__ __forceinline__ void store_natural(float* __restrict__ out, const RasterParams& q, const WtCoord& w, int c, const float (&v)[8]) {
-    const int rb = w.r0 + 2 * w.h;
-    float* o = out + ((size_t)w.b * q.ts1 + rb) * q.ts0 + c;
-    if (w.r0 + WT <= q.ts1 && (c | 15) < q.ts0) {          // interior tile (warp-uniform)
+// Tile access.  A lane addresses its first texel once per super tile (TilePtr) and then steps from tile to tile;
+// natural [ts1, ts0]: v[2i + j] <-> row r0 + 4i + 2h + j, column c;  transposed [ts0, ts1] (baked_sum_2's
+// orientation): the lane moves rows 8h..8h+7 of its column as 2 x 128 bit.
+struct TilePtr {
+    size_t nat;        // element offset of (row r0 + 2h, column c0 + lc) in a natural frame of sample b
+    size_t tr;         // element offset of (column c0 + lc, row r0 + 8h) in a transposed frame of sample b
+};
+__device__ __forceinline__ TilePtr tile_ptr(const RasterParams& q, const WtCoord& w) {
+    TilePtr t;
+    t.nat = ((size_t)w.b * q.ts1 + (w.r0 + 2 * w.h)) * q.ts0 + w.c0 + w.lc;
+    t.tr = ((size_t)w.b * q.ts0 + w.c0 + w.lc) * q.ts1 + w.r0 + 8 * w.h;
+    return t;
+}
+
+__device__ __forceinline__ void store_natural(float* __restrict__ o, const RasterParams& q, const WtCoord& w, int c, bool interior,
+                                              const float (&v)[8]) {
+    if (interior) {                                        // warp-uniform
+        float* r = o;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            o[0] = v[2 * i];
-            o[q.ts0] = v[2 * i + 1];
-            o += 4 * (size_t)q.ts0;
+            r[0] = v[2 * i];
+            r[q.ts0] = v[2 * i + 1];
+            r += 4 * (size_t)q.ts0;
         }
     } else if (c < q.ts0) {
+        const int rb = w.r0 + 2 * w.h;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -173,17 +197,18 @@ __device__ __forceinline__ void store_natural(float* __restrict__ out, const Ras
                 if (rb + 4 * i + j < q.ts1) o[(size_t)(4 * i + j) * q.ts0] = v[2 * i + j];
     }
 }
-__device__ __forceinline__ void load_natural(const float* __restrict__ in, const RasterParams& q, const WtCoord& w, int c, float (&v)[8]) {
-    const int rb = w.r0 + 2 * w.h;
-    const float* p = in + ((size_t)w.b * q.ts1 + rb) * q.ts0 + c;
-    if (w.r0 + WT <= q.ts1 && (c | 15) < q.ts0) {
+__device__ __forceinline__ void load_natural(const float* __restrict__ p, const RasterParams& q, const WtCoord& w, int c, bool interior,
+                                             float (&v)[8]) {
+    if (interior) {
+        const float* r = p;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            v[2 * i] = __ldg(p);
-            v[2 * i + 1] = __ldg(p + q.ts0);
-            p += 4 * (size_t)q.ts0;
+            v[2 * i] = __ldg(r);
+            v[2 * i + 1] = __ldg(r + q.ts0);
+            r += 4 * (size_t)q.ts0;
         }
     } else {
+        const int rb = w.r0 + 2 * w.h;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -191,39 +216,28 @@ __device__ __forceinline__ void load_natural(const float* __restrict__ in, const
                 v[2 * i + j] = (c < q.ts0 && rb + 4 * i + j < q.ts1) ? __ldg(p + (size_t)(4 * i + j) * q.ts0) : 0.f;
     }
 }
-// transposed [ts0, ts1] tile access (baked_sum_2's orientation): a lane moves rows 8h..8h+7 of its column as 2 x 128 bit
-__device__ __forceinline__ void store_transposed(float* __restrict__ out, const RasterParams& q, const WtCoord& w, int c, const float (&v)[8]) {
-    float run[8];
-    rows_to_run(v, run, w.h);
-    if (c >= q.ts0) return;
-    const int rr = w.r0 + 8 * w.h;
-    float* o = out + ((size_t)w.b * q.ts0 + c) * q.ts1 + rr;
-    if ((q.ts1 & 3) == 0 && rr + 8 <= q.ts1) {
-        reinterpret_cast<float4*>(o)[0] = make_float4(run[0], run[1], run[2], run[3]);
-        reinterpret_cast<float4*>(o)[1] = make_float4(run[4], run[5], run[6], run[7]);
-    } else {
+__device__ __forceinline__ void store_run(float* __restrict__ o, const RasterParams& q, const WtCoord& w, int c, bool interior,
+                                          const float (&run)[8]) {
+    if (interior && (q.ts1 & 7) == 0) {                     // one 256-bit store: a full 32-byte sector per lane
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o), "f"(run[0]), "f"(run[1]), "f"(run[2]),
+                     "f"(run[3]), "f"(run[4]), "f"(run[5]), "f"(run[6]), "f"(run[7]) : "memory");
+    } else if (c < q.ts0) {
+        const int rr = w.r0 + 8 * w.h;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             if (rr + k < q.ts1) o[k] = run[k];
     }
 }
-__device__ __forceinline__ void load_transposed(const float* __restrict__ in, const RasterParams& q, const WtCoord& w, int c, float (&v)[8]) {
-    float run[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) run[k] = 0.f;
-    if (c < q.ts0) {
+__device__ __forceinline__ void load_run(const float* __restrict__ p, const RasterParams& q, const WtCoord& w, int c, bool interior,
+                                         float (&run)[8]) {
+    if (interior && (q.ts1 & 7) == 0) {                     // one 256-bit load: a full 32-byte sector per lane
+        asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=f"(run[0]), "=f"(run[1]), "=f"(run[2]),
+                     "=f"(run[3]), "=f"(run[4]), "=f"(run[5]), "=f"(run[6]), "=f"(run[7]) : "l"(p));
+    } else {
         const int rr = w.r0 + 8 * w.h;
-        const float* p = in + ((size_t)w.b * q.ts0 + c) * q.ts1 + rr;
-        if ((q.ts1 & 3) == 0 && rr + 8 <= q.ts1) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(p)), d = __ldg(reinterpret_cast<const float4*>(p) + 1);
-            run[0] = a.x; run[1] = a.y; run[2] = a.z; run[3] = a.w; run[4] = d.x; run[5] = d.y; run[6] = d.z; run[7] = d.w;
-        } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (rr + k < q.ts1) run[k] = __ldg(p + k);
-        }
+        for (int k = 0; k < 8; ++k) run[k] = (c < q.ts0 && rr + k < q.ts1) ? __ldg(p + k) : 0.f;
     }
-    run_to_rows(run, v, w.h);
 }
 
 // one 16x4 group of the soft-OR product (shared by the forward and the backward's first pass)
@@ -238,22 +252,22 @@ __device__ __forceinline__ void prod_group(float2& acc_p, float2 g, bool pco, fl
 
 // sum and/or soft-OR product of one 16x16 tile over the staged candidates that touch it
 template <bool SUM, bool SOFTOR, bool MASK_O, typename Stage>
-__device__ __forceinline__ void accumulate_tile(const Stage& st, const WtMasks& mk, int j, float cf, int h, const WtConsts& fc,
+__device__ __forceinline__ void accumulate_tile(const Stage& st, unsigned tm, float cf, int h, const WtConsts& fc,
                                                 float2 (&acc_s)[4], float2 (&acc_p)[4]) {
-    unsigned tm = (unsigned)(mk.tb >> (16 * j)) & 0xffffu;                            // warp-uniform
-    while (tm) {
+    while (tm) {                                                                      // warp-uniform
         const int k = __ffs(tm) - 1;
         tm &= tm - 1;
-        const unsigned long long gk = mk.gb >> k;
         const float4 cd = st.cand[k];
+        const unsigned gm = __float_as_uint(cd.w);
         const float dx = cf - cd.x;
         const float dx2 = __fmul_rn(dx, dx);
         const float ec = fabsf(cf - cd.y);
         const bool pcs = ec <= fc.hs, pco = ec <= fc.ho;
+        const float4* tA = &st.tabA[k][h];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            if (gk & (1ull << (16 * i))) {                                            // warp-uniform
-                const float4 A = st.tabA[k][2 * i + h];
+            if (!FFB_GROUP_SKIP_FWD || (gm & (1u << i))) {                            // warp-uniform
+                const float4 A = tA[2 * i];
                 const float2 d2 = __fadd2_rn(bc(dx2), make_float2(A.x, A.y));        // dc*dc + dr*dr, as the reference
                 const float2 t = __fmul2_rn(__fmul2_rn(d2, d2), bc(fc.K2));
                 const float2 g = make_float2(ex2_approx(t.x), ex2_approx(t.y));
@@ -268,8 +282,12 @@ __device__ __forceinline__ void accumulate_tile(const Stage& st, const WtMasks& 
     }
 }
 
+__device__ __forceinline__ unsigned tile_mask(const WtMasks& mk, int j) {
+    return (((j & 2) ? mk.tb23 : mk.tb01) >> (16 * (j & 1))) & 0xffffu;
+}
+
 template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O>
-__global__ void __launch_bounds__(WT_CTA, 5) splat_fwd_wt(RasterParams q, WtConsts fc) {
+__global__ void __launch_bounds__(WT_CTA, FFB_FWD_MINB) splat_fwd_wt(RasterParams q, WtConsts fc) {
     __shared__ WarpStage<MASK_O> stage[WT_WARPS];
     const WtCoord w = wt_coord(q);
     if (!w.valid) return;                                  // whole warp; no block-level barriers below
@@ -279,22 +297,28 @@ __global__ void __launch_bounds__(WT_CTA, 5) splat_fwd_wt(RasterParams q, WtCons
     const Entry* entries = q.entries + (size_t)w.bin * q.cap;
     const bool single = end - beg <= WCH;
     WtMasks mk;
-    mk.tb = 0; mk.gb = 0;
+    mk.tb01 = 0; mk.tb23 = 0;
     if (single) mk = stage_warp(st, entries, beg, end - beg, w.c0, w.r0, fc, w.lane);
+    const TilePtr tp = tile_ptr(q, w);
+    float* po = SOFTOR ? q.out_softor + tp.nat : nullptr;
+    float* ps = SUM ? q.out_sum + (SUM_T ? tp.tr : tp.nat) : nullptr;
+    const bool rows_in = w.r0 + WT <= q.ts1;
 
     for (int j = 0; j < 4; ++j) {
-        const int c = w.c0 + WT * j + w.lc;
-        if (w.c0 + WT * j >= q.ts0) break;
+        const int ct = w.c0 + WT * j;
+        if (ct >= q.ts0) break;
+        const int c = ct + w.lc;
+        const bool interior = rows_in && ct + WT <= q.ts0;
         const float cf = (float)c;
         float2 acc_s[4], acc_p[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) { acc_s[i] = bc(0.f); acc_p[i] = bc(1.f); }
         if (single) {
-            accumulate_tile<SUM, SOFTOR, MASK_O>(st, mk, j, cf, w.h, fc, acc_s, acc_p);
+            accumulate_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mk, j), cf, w.h, fc, acc_s, acc_p);
         } else {
             for (int base = beg; base < end; base += WCH) {
                 const WtMasks mc = stage_warp(st, entries, base, min(WCH, end - base), w.c0, w.r0, fc, w.lane);
-                accumulate_tile<SUM, SOFTOR, MASK_O>(st, mc, j, cf, w.h, fc, acc_s, acc_p);
+                accumulate_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mc, j), cf, w.h, fc, acc_s, acc_p);
             }
         }
         // epilogue: every texel of the tile is written exactly once
@@ -302,13 +326,21 @@ __global__ void __launch_bounds__(WT_CTA, 5) splat_fwd_wt(RasterParams q, WtCons
         if (SOFTOR) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) { v[2 * i] = 1.f - acc_p[i].x; v[2 * i + 1] = 1.f - acc_p[i].y; }
-            store_natural(q.out_softor, q, w, c, v);
+            store_natural(po, q, w, c, interior, v);
+            po += WT;
         }
         if (SUM) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) { v[2 * i] = acc_s[i].x; v[2 * i + 1] = acc_s[i].y; }
-            if (SUM_T) store_transposed(q.out_sum, q, w, c, v);
-            else store_natural(q.out_sum, q, w, c, v);
+            if (SUM_T) {
+                float run[8];
+                rows_to_run(v, run, w.h);
+                store_run(ps, q, w, c, interior, run);
+                ps += (size_t)WT * q.ts1;
+            } else {
+                store_natural(ps, q, w, c, interior, v);
+                ps += WT;
+            }
         }
     }
 }
@@ -320,24 +352,25 @@ __global__ void __launch_bounds__(WT_CTA, 5) splat_fwd_wt(RasterParams q, WtCons
 // Each (candidate, tile) partial is folded across the warp at once (lanes 0-15 end up with d/dp0, lanes 16-31 with
 // d/dp1) and kept by the lane whose number is the candidate's slot: `accv` of lane k / k+16 is candidate k's sum.
 template <bool SUM, bool SOFTOR, bool MASK_O, typename Stage>
-__device__ __forceinline__ void weigh_tile(const Stage& st, const WtMasks& mk, int j, float cf, int h, int lc, const WtConsts& fc,
+__device__ __forceinline__ void weigh_tile(const Stage& st, unsigned tm, float cf, int h, int lc, const WtConsts& fc,
                                            const float2 (&gs)[4], const float2 (&gp)[4], float& accv) {
-    unsigned tm = (unsigned)(mk.tb >> (16 * j)) & 0xffffu;
     while (tm) {
         const int k = __ffs(tm) - 1;
         tm &= tm - 1;
-        const unsigned long long gk = mk.gb >> k;
         const float4 cd = st.cand[k];
+        const unsigned gm = __float_as_uint(cd.w);
         const float dx = cf - cd.x;
         const float dx2 = __fmul_rn(dx, dx);
         const float ec = fabsf(cf - cd.y);
         const bool pcs = ec <= fc.hs, pco = ec <= fc.ho;
+        const float4* tA = &st.tabA[k][h];
+        const float4* tB = &st.tabB[k][h];
         float2 a0 = bc(0.f), a1 = bc(0.f);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            if (gk & (1ull << (16 * i))) {
-                const float4 A = st.tabA[k][2 * i + h];
-                const float4 Bq = st.tabB[k][2 * i + h];
+            if (!FFB_GROUP_SKIP_BWD || (gm & (1u << i))) {
+                const float4 A = tA[2 * i];
+                const float4 Bq = tB[2 * i];
                 const float2 d2 = __fadd2_rn(bc(dx2), make_float2(A.x, A.y));
                 const float2 t = __fmul2_rn(__fmul2_rn(d2, d2), bc(fc.K2));
                 const float2 g = make_float2(ex2_approx(t.x), ex2_approx(t.y));
@@ -377,8 +410,28 @@ __device__ __forceinline__ void flush_warp(const Stage& st, int n, int lc, float
     accv = 0.f;
 }
 
+// raw upstream values of one tile, as loaded (the transposed sum gradient still in run order)
+template <bool SUM, bool SOFTOR, bool SUM_T, bool SAVED>
+struct TileIn {
+    float s[8], o[8], sv[8];       // unused members are never touched and cost no registers
+};
+template <bool SUM, bool SOFTOR, bool SUM_T, bool SAVED>
+__device__ __forceinline__ void load_tile_in(TileIn<SUM, SOFTOR, SUM_T, SAVED>& t, const RasterParams& q, const WtCoord& w,
+                                             const TilePtr& tp, int j) {
+    const int ct = w.c0 + WT * j, c = ct + w.lc;
+    const bool interior = w.r0 + WT <= q.ts1 && ct + WT <= q.ts0;
+    if (SUM) {
+        if (SUM_T) load_run(q.g_sum + tp.tr + (size_t)(WT * j) * q.ts1, q, w, c, interior, t.s);
+        else load_natural(q.g_sum + tp.nat + WT * j, q, w, c, interior, t.s);
+    }
+    if (SOFTOR) {
+        load_natural(q.g_softor + tp.nat + WT * j, q, w, c, interior, t.o);
+        if (SAVED) load_natural(q.saved_softor + tp.nat + WT * j, q, w, c, interior, t.sv);
+    }
+}
+
 template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O, bool SAVED>
-__global__ void __launch_bounds__(WT_CTA, 4) splat_bwd_wt(RasterParams q, WtConsts fc) {
+__global__ void __launch_bounds__(WT_CTA, FFB_BWD_MINB) splat_bwd_wt(RasterParams q, WtConsts fc) {
     typedef WarpStage<true> Stage;
     __shared__ Stage stage[WT_WARPS];
     const WtCoord w = wt_coord(q);
@@ -387,6 +440,9 @@ __global__ void __launch_bounds__(WT_CTA, 4) splat_bwd_wt(RasterParams q, WtCons
     const int* toff = q.tile_off + (size_t)w.bin * (q.T + 1) + w.stile;
     const int beg = __ldg(toff), end = __ldg(toff + 1);
     if (beg == end) return;
+    const TilePtr tp = tile_ptr(q, w);
+    TileIn<SUM, SOFTOR, SUM_T, SAVED> in;
+    load_tile_in(in, q, w, tp, 0);                          // in flight while the candidates are staged
     const Entry* entries = q.entries + (size_t)w.bin * q.cap;
     const bool single = end - beg <= WCH;
     const float inv_s2 = q.rcp_sigma * q.rcp_sigma;
@@ -394,45 +450,40 @@ __global__ void __launch_bounds__(WT_CTA, 4) splat_bwd_wt(RasterParams q, WtCons
     float* dp = q.d_pts + (size_t)w.b * q.N * 2 + w.h;
     float accv = 0.f;
     WtMasks mk;
-    mk.tb = 0; mk.gb = 0;
+    mk.tb01 = 0; mk.tb23 = 0;
     if (single) mk = stage_warp(st, entries, beg, end - beg, w.c0, w.r0, fc, w.lane);
 
     for (int j = 0; j < 4; ++j) {
-        const int c = w.c0 + WT * j + w.lc;
-        if (w.c0 + WT * j >= q.ts0) break;
-        const float cf = (float)c;
+        const int ct = w.c0 + WT * j;
+        if (ct >= q.ts0) break;
+        const float cf = (float)(ct + w.lc);
         // upstream gradients of this lane's 8 texels
         float2 gs[4], gp[4];
-        {
+        if (SUM) {
             float v[8];
-            if (SUM) {
-                if (SUM_T) load_transposed(q.g_sum, q, w, c, v);
-                else load_natural(q.g_sum, q, w, c, v);
+            if (SUM_T) run_to_rows(in.s, v, w.h);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) gs[i] = make_float2(v[2 * i], v[2 * i + 1]);
-            }
-            if (SOFTOR) {
-                load_natural(q.g_softor, q, w, c, v);
+            for (int i = 0; i < 4; ++i) gs[i] = SUM_T ? make_float2(v[2 * i], v[2 * i + 1]) : make_float2(in.s[2 * i], in.s[2 * i + 1]);
+        }
+        if (SOFTOR) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) gp[i] = make_float2(v[2 * i], v[2 * i + 1]);
-                if (SAVED) {
-                    load_natural(q.saved_softor, q, w, c, v);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) gp[i] = __fmul2_rn(gp[i], make_float2(1.f - v[2 * i], 1.f - v[2 * i + 1]));
-                }
+            for (int i = 0; i < 4; ++i) {
+                gp[i] = make_float2(in.o[2 * i], in.o[2 * i + 1]);
+                if (SAVED) gp[i] = __fmul2_rn(gp[i], make_float2(1.f - in.sv[2 * i], 1.f - in.sv[2 * i + 1]));
             }
         }
+        if (j < 3 && ct + WT < q.ts0) load_tile_in(in, q, w, tp, j + 1);      // prefetch the next tile
         // pass 1 (only without the saved output): per-texel product of (1 - g)
         if (SOFTOR && !SAVED) {
             float2 prod[4], unused[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) prod[i] = bc(1.f);
             if (single) {
-                accumulate_tile<false, true, MASK_O>(st, mk, j, cf, w.h, fc, unused, prod);
+                accumulate_tile<false, true, MASK_O>(st, tile_mask(mk, j), cf, w.h, fc, unused, prod);
             } else {
                 for (int base = beg; base < end; base += WCH) {
                     const WtMasks mc = stage_warp(st, entries, base, min(WCH, end - base), w.c0, w.r0, fc, w.lane);
-                    accumulate_tile<false, true, MASK_O>(st, mc, j, cf, w.h, fc, unused, prod);
+                    accumulate_tile<false, true, MASK_O>(st, tile_mask(mc, j), cf, w.h, fc, unused, prod);
                 }
             }
 #pragma unroll
@@ -440,12 +491,12 @@ __global__ void __launch_bounds__(WT_CTA, 4) splat_bwd_wt(RasterParams q, WtCons
         }
         // pass 2: weights
         if (single) {
-            weigh_tile<SUM, SOFTOR, MASK_O>(st, mk, j, cf, w.h, w.lc, fc, gs, gp, accv);
+            weigh_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mk, j), cf, w.h, w.lc, fc, gs, gp, accv);
         } else {
             for (int base = beg; base < end; base += WCH) {
                 const int n = min(WCH, end - base);
                 const WtMasks mc = stage_warp(st, entries, base, n, w.c0, w.r0, fc, w.lane);
-                weigh_tile<SUM, SOFTOR, MASK_O>(st, mc, j, cf, w.h, w.lc, fc, gs, gp, accv);
+                weigh_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mc, j), cf, w.h, w.lc, fc, gs, gp, accv);
                 flush_warp(st, n, w.lc, kh, dp, accv);
             }
         }
