@@ -37,6 +37,7 @@ constexpr int CHUNK = 128;    // candidate records staged per pass
 constexpr int KCACHE = 6;     // cached g slots per warp in the backward (8 rows x 32 lanes each; dynamic smem)
 constexpr int PREP_CTA = 1024;
 constexpr int WT = 16;        // warp tile side of the warp-tile kernels (ffb_splat_wt.cuh)
+constexpr int WCH = 16;       // candidates a warp stages at once; longer super-tile lists go to the overflow kernels
 
 struct __align__(16) PointRec {
     float p0, p1;             // points * texture_size
@@ -64,7 +65,7 @@ struct Plan {
     int tgx, tgy, T;          // tile grid
     int band_rows;            // tile rows binned per pass of the prepare kernel (shared-memory counters)
     int cap;                  // list capacity per instance
-    size_t off_recs, off_tileoff, off_list, off_entries, total;
+    size_t off_recs, off_tileoff, off_list, off_entries, off_ovf, total;
     // window parameters
     int fp_s, half_s, h_s;    // baked: fp/half ; dense: h = cut-off half width
     int fp_o, half_o, h_o;
@@ -136,6 +137,8 @@ static int make_plan(const ffb_splat_desc* d, Plan* p) {
     p->off_list = o;     o += (size_t)p->Bp * p->cap * sizeof(int);
     o = (o + 255) & ~(size_t)255;
     p->off_entries = o;  o += p->fast ? (size_t)p->Bp * p->cap * sizeof(Entry) : 0;
+    o = (o + 255) & ~(size_t)255;
+    p->off_ovf = o;      o += p->fast ? ((size_t)p->Bp * p->T + 1) * sizeof(int) : 0;      // [0] = count, then bin * T + super tile
     p->total = (o + 255) & ~(size_t)255;
     return 0;
 }
@@ -152,6 +155,7 @@ struct PrepParams {
     int* tile_off;
     int* list;        // general kernels: point indices per tile
     Entry* entries;   // warp-tile kernels: records per super tile
+    int* ovf;         // warp-tile kernels: [0] = number of super tiles with more than WCH candidates, then their codes
     int* windows;     // nullable
 };
 
@@ -328,6 +332,7 @@ __global__ void __launch_bounds__(PREP_CTA) prepare_kernel(PrepParams q) {
             const int c = cnt[i];
             cnt[i] = run; cur[i] = run; tile_off[t0 + i] = run;
             run += c;
+            if (FAST && c > WCH) q.ovf[1 + atomicAdd(q.ovf, 1)] = bin * q.T + t0 + i;
         }
         __syncthreads();
         if (tid == PREP_CTA - 1) band_base = run;      // the last thread's running total covers the whole band
@@ -382,6 +387,7 @@ struct RasterParams {
     const int* tile_off;
     const int* list;
     const Entry* entries;     // warp-tile kernels
+    const int* ovf;           // [0] = overflow count, then the overflow super tiles
     const float* saved_softor;
     int shared_pattern;       // 1: every sample uses bin 0
     int N, ts0, ts1, tgx, tgy, T, cap;
@@ -644,12 +650,19 @@ static WtConsts wt_consts(const ffb_splat_desc* d, const Plan& p) {
     fc.c1 = 1.00000011920928955078125f;      // 1 + 2^-23
     return fc;
 }
-template <typename K>
-static int launch_wt(K kernel, const RasterParams& q, const WtConsts& fc, int B, cudaStream_t st, size_t smem = 0) {
-    const unsigned gy = (unsigned)((q.tgy + WT_WARPS - 1) / WT_WARPS);
+// main kernel over the strip grid, then the overflow kernel over its (normally empty) list
+template <typename K, typename KO>
+static int launch_wt(K kernel, KO overflow, const RasterParams& q, const WtConsts& fc, const OvfParams& o, int B, cudaStream_t st,
+                     size_t smem = 0) {
+    const unsigned gy = (unsigned)((q.tgy + WT_WARPS * WT_S - 1) / (WT_WARPS * WT_S));
     if (B > 65535 || gy > 65535) return fail_arg(FFB_E_LIMIT, "splat: B or the tile rows exceed the grid limit (65535)");
-    if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) {
+        FFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FFB_CUDA(cudaFuncSetAttribute(overflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     kernel<<<dim3((unsigned)q.tgx, gy, (unsigned)B), WT_CTA, smem, st>>>(q, fc);
+    FFB_CUDA(cudaGetLastError());
+    overflow<<<kNumSMs, WT_CTA, smem, st>>>(q, fc, o);
     FFB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -671,6 +684,7 @@ static void fill_raster(const ffb_splat_desc* d, const Plan& p, const void* ws, 
     q.tile_off = reinterpret_cast<const int*>(w + p.off_tileoff);
     q.list = reinterpret_cast<const int*>(w + p.off_list);
     q.entries = reinterpret_cast<const Entry*>(w + p.off_entries);
+    q.ovf = reinterpret_cast<const int*>(w + p.off_ovf);
     q.saved_softor = nullptr;
     q.shared_pattern = d->pts_batch_stride == 0;
     q.N = d->N; q.ts0 = d->ts0; q.ts1 = d->ts1; q.tgx = p.tgx; q.tgy = p.tgy; q.T = p.T; q.cap = p.cap;
@@ -825,9 +839,11 @@ extern "C" int ffb_splat_prepare(const ffb_splat_desc* d, const float* pts, void
     q.tile_off = reinterpret_cast<int*>(w + p.off_tileoff);
     q.list = reinterpret_cast<int*>(w + p.off_list);
     q.entries = reinterpret_cast<Entry*>(w + p.off_entries);
+    q.ovf = reinterpret_cast<int*>(w + p.off_ovf);
     q.windows = windows_out;
     const size_t smem = (size_t)p.band_rows * p.tgx * 2 * sizeof(int);
     if (p.fast) {
+        FFB_CUDA(cudaMemsetAsync(q.ovf, 0, sizeof(int), as_stream(stream)));
         if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         prepare_kernel<true><<<p.Bp, PREP_CTA, smem, as_stream(stream)>>>(q);
     } else {
@@ -852,12 +868,14 @@ extern "C" int ffb_splat_fwd(const ffb_splat_desc* d, const float* pts, const vo
     if (p.fast) {
         const WtConsts fc = wt_consts(d, p);
         const int B = d->B;
-#define FFB_FWD(S, O, T) (p.mask_o ? launch_wt(splat_fwd_wt<S, O, T, true>, q, fc, B, st) : launch_wt(splat_fwd_wt<S, O, T, false>, q, fc, B, st))
+        const OvfParams ov = {q.ovf, q.ovf + 1, B};
+#define FFB_FWD1(S, O, T, M) launch_wt(splat_fwd_wt<S, O, T, M>, splat_fwd_ovf<S, O, T, M>, q, fc, ov, B, st)
+#define FFB_FWD(S, O, T) (p.mask_o ? FFB_FWD1(S, O, T, true) : FFB_FWD1(S, O, T, false))
         if (out_sum && out_softor) return sum_transposed ? FFB_FWD(true, true, true) : FFB_FWD(true, true, false);
-        if (out_sum) return sum_transposed ? launch_wt(splat_fwd_wt<true, false, true, false>, q, fc, B, st)
-                                           : launch_wt(splat_fwd_wt<true, false, false, false>, q, fc, B, st);
+        if (out_sum) return sum_transposed ? FFB_FWD1(true, false, true, false) : FFB_FWD1(true, false, false, false);
         return FFB_FWD(false, true, false);
 #undef FFB_FWD
+#undef FFB_FWD1
     }
     if (out_sum && out_softor)
         return sum_transposed ? launch_raster(splat_fwd_kernel<true, true, true>, q, d->B, st)
@@ -885,16 +903,18 @@ extern "C" int ffb_splat_bwd(const ffb_splat_desc* d, const float* pts, const vo
     if (p.fast) {
         const WtConsts fc = wt_consts(d, p);
         const int B = d->B;
+        const OvfParams ov = {q.ovf, q.ovf + 1, B};
         q.saved_softor = g_softor ? saved_softor : nullptr;
-        const size_t wsm = 0;
-#define FFB_BWD2(S, O, T, M) (q.saved_softor ? launch_wt(splat_bwd_wt<S, O, T, M, true>, q, fc, B, st, wsm) : launch_wt(splat_bwd_wt<S, O, T, M, false>, q, fc, B, st, wsm))
+        const size_t wsm = sizeof(WarpStage<true, true>) * WT_WARPS;
+#define FFB_BWD1(S, O, T, M, V) launch_wt(splat_bwd_wt<S, O, T, M, V>, splat_bwd_ovf<S, O, T, M, V>, q, fc, ov, B, st, wsm)
+#define FFB_BWD2(S, O, T, M) (q.saved_softor ? FFB_BWD1(S, O, T, M, true) : FFB_BWD1(S, O, T, M, false))
 #define FFB_BWD(S, O, T) (p.mask_o ? FFB_BWD2(S, O, T, true) : FFB_BWD2(S, O, T, false))
         if (g_sum && g_softor) return sum_transposed ? FFB_BWD(true, true, true) : FFB_BWD(true, true, false);
-        if (g_sum) return sum_transposed ? launch_wt(splat_bwd_wt<true, false, true, false, false>, q, fc, B, st, wsm)
-                                         : launch_wt(splat_bwd_wt<true, false, false, false, false>, q, fc, B, st, wsm);
+        if (g_sum) return sum_transposed ? FFB_BWD1(true, false, true, false, false) : FFB_BWD1(true, false, false, false, false);
         return FFB_BWD(false, true, false);
 #undef FFB_BWD
 #undef FFB_BWD2
+#undef FFB_BWD1
     }
     if (g_sum && g_softor)
         return sum_transposed ? launch_raster(splat_bwd_kernel<true, true, true>, q, d->B, st, gsm)

@@ -9,14 +9,18 @@
 //   * the binning kernel builds one candidate list per 64x16 SUPER TILE; a list entry is the 32-byte record the
 //     kernel needs (scaled position, window origin, row / column span, point index) -- no index indirection, no
 //     in-kernel culling;
-//   * a warp owns its super tile from the first load to the last store: no __syncthreads, only __syncwarp around a
-//     small per-warp shared table.  It stages the candidates once and then walks the four 16x16 tiles of the super
-//     tile; the 16 rows are common to all four, so everything that depends on (candidate, row) only -- (r - P1)^2,
+//   * a warp owns a strip of four vertically adjacent super tiles from the first load to the last store: no
+//     __syncthreads, only __syncwarp around a small per-warp shared table.  The strip's list offsets are fetched with
+//     one load, and the candidate records (and, in the backward, the upstream gradients) of the next super tile are
+//     in flight while the current one is computed -- the two dependent global loads at the head of a warp's life
+//     were a quarter of all stall samples before.  Per super tile it stages the candidates once and then walks the
+//     four 16x16 tiles; the 16 rows are common to all four, so everything that depends on (candidate, row) only -- (r - P1)^2,
 //     r - P1, the row masks -- is computed once per warp and read back with one LDS.128 per group;
 //   * inside a 16x16 tile lane = (column 0..15, row half 0..1); the packed fp32 pipe (FADD2/FMUL2/FFMA2) handles
 //     two rows per lane, so one warp instruction covers a 16x4 texel group.  Tiles outside a candidate's column
-//     span and groups outside its row span are skipped with warp-uniform branches: 2668 evaluated pairs per
-//     point for a 43x43 window instead of 3700;
+//     span are skipped through warp-uniform ballot masks; all four row groups of a touched tile are evaluated
+//     (branch-free, four independent dependency chains per lane): 3364 evaluated pairs per point for a 43x43 window
+//     instead of 3700, at a third of the instructions;
 //   * the column mask of the sum window is a lane predicate on the accumulate, so masks cost no arithmetic;
 //   * g = 2^(d2^2 * K), K = -log2(e)/sigma^2, with d2 = dc*dc + dr*dr rounded exactly like the reference: the inner
 //     group is LDS.128 + FADD2 + 2 FMUL2 + 2 MUFU.EX2 + 2 FFMA2.  With 16 MUFU lanes per SM the exp is the busiest
@@ -26,23 +30,19 @@
 //   * backward: with the forward's soft-OR output at hand (saved_softor) the per-texel product is 1 - O and a single
 //     pass suffices; otherwise a first pass rebuilds it.  Per-lane d/dP partial sums are parked in shared memory
 //     across the four tiles, then folded across the warp with five shuffles for both components at once and leave
-//     the warp as one atomic per component per (candidate, super tile).
+//     the warp as one atomic per component per (candidate, super tile);
+//   * super tiles with more than 16 candidates (clustered patterns) are left to the overflow kernels at the end of
+//     this file, which walk the binning kernel's overflow list with the same device functions in chunks of 16.
 #pragma once
 
-constexpr int WCH = 16;                   // candidates staged per warp per chunk
-constexpr int WT_CTA = 256;               // 8 warps = 8 vertically stacked super tiles = 64 x 128 texels
+constexpr int WT_S = 4;                   // vertically adjacent super tiles per warp
+constexpr int WT_CTA = 256;               // 8 warps x 4 super tiles (64 x 16 texels each) = 64 x 512 texels
 constexpr int WT_WARPS = WT_CTA / 32;
-#ifndef FFB_GROUP_SKIP_FWD
-#define FFB_GROUP_SKIP_FWD 0              // 1: skip 16x4 row groups outside a candidate's row span with warp-uniform branches
-#endif
-#ifndef FFB_GROUP_SKIP_BWD
-#define FFB_GROUP_SKIP_BWD 0
-#endif
 #ifndef FFB_FWD_MINB
 #define FFB_FWD_MINB 4                    // resident CTAs per SM the register allocation aims for
 #endif
 #ifndef FFB_BWD_MINB
-#define FFB_BWD_MINB 3
+#define FFB_BWD_MINB 2
 #endif
 
 struct WtConsts {
@@ -69,44 +69,82 @@ __device__ __forceinline__ float2 bc(float x) { return make_float2(x, x); }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 
 // Per-warp staging: candidate records and the (candidate, row pair) tables of the warp's 16 rows.
-template <bool TABB>
+template <bool TABB, bool ACC = false>
 struct WarpStage {
-    float4 cand[WCH];                     // p0, f0, point index (bits), row-group mask (bits)
+    float4 cand[WCH];                     // p0, f0, point index (bits), -
     float2 prow[WCH];                     // p1, f1
     float4 tabA[WCH][WT / 2];             // dy^2 (2 rows), sum row mask (2 rows)
     float4 tabB[TABB ? WCH : 1][WT / 2];  // dy (2 rows), soft-OR row mask (2 rows)
+    uint4 raw[2][2 * WCH];                // candidate records as fetched by cp.async, double buffered across super tiles
+    float acc[ACC ? WCH : 1][33];         // backward: per-lane d/dP partial sums (lanes 0-15: d/dp0, 16-31: d/dp1), row padded
 };
 
-// Which staged candidates touch which 16x16 tile: warp-uniform ballots, 16 bits per tile.  (Which 16x4 row groups a
-// candidate touches travels with its record.)
+// Which staged candidates touch which 16x16 tile: warp-uniform ballots, 16 bits per tile.
 struct WtMasks {
     unsigned tb01, tb23;
 };
+__device__ __forceinline__ unsigned tile_mask(const WtMasks& mk, int j) {
+    return (((j & 2) ? mk.tb23 : mk.tb01) >> (16 * (j & 1))) & 0xffffu;
+}
 
-template <bool TABB>
-__device__ __forceinline__ WtMasks stage_warp(WarpStage<TABB>& s, const Entry* __restrict__ entries, int base, int n,
-                                              int c0, int r0, const WtConsts& fc, int lane) {
+// a lane's candidate record, as loaded (lane k holds candidate k of the chunk)
+struct EntryRegs {
+    float4 a;                             // p0, p1, f0, f1
+    uint4 b;                              // row span, column span, point index, -
+};
+__device__ __forceinline__ EntryRegs load_entry(const Entry* __restrict__ entries, int base, int n, int lane) {
+    EntryRegs e;
+    e.a = make_float4(0.f, 0.f, 0.f, 0.f);
+    e.b = make_uint4(0u, 0u, 0u, 0u);
+    if (lane < n) {
+        e.a = __ldg(reinterpret_cast<const float4*>(entries + base + lane));
+        e.b = __ldg(reinterpret_cast<const uint4*>(entries + base + lane) + 1);
+    }
+    return e;
+}
+
+// asynchronous copy of n (<= WCH) records into a raw buffer: no registers held while the data is in flight
+__device__ __forceinline__ void prefetch_entries(uint4* raw, const Entry* __restrict__ src, int n, int lane) {
+    if (lane < 2 * n) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(raw + lane);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(reinterpret_cast<const uint4*>(src) + lane) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ EntryRegs take_entry(const uint4* raw, int n, int lane) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    EntryRegs e;
+    e.a = make_float4(0.f, 0.f, 0.f, 0.f);
+    e.b = make_uint4(0u, 0u, 0u, 0u);
+    if (lane < n) {
+        const uint4 a = raw[2 * lane];
+        e.a = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
+        e.b = raw[2 * lane + 1];
+    }
+    return e;
+}
+
+template <bool TABB, bool ACC>
+__device__ __forceinline__ WtMasks stage_regs(WarpStage<TABB, ACC>& s, const EntryRegs& e, int n, int c0, const float r0f,
+                                              const WtConsts& fc, int lane) {
     __syncwarp();                         // previous chunk fully consumed
     bool ta[4] = {false, false, false, false};
     if (lane < n) {
-        const float4 e = __ldg(reinterpret_cast<const float4*>(entries + base + lane));
-        const uint4 x = __ldg(reinterpret_cast<const uint4*>(entries + base + lane) + 1);
-        const int rlo = (int)(x.x & 0xffff) - r0, rhi = (int)(x.x >> 16) - r0;      // spans relative to the super tile
-        const int clo = (int)(x.y & 0xffff) - c0, chi = (int)(x.y >> 16) - c0;
-        unsigned gm = 0;
+        const int clo = (int)(e.b.y & 0xffff) - c0, chi = (int)(e.b.y >> 16) - c0;  // column span relative to the super tile
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (rlo < 4 * i + 4 && rhi > 4 * i) gm |= 1u << i;
-            ta[i] = clo < WT * i + WT && chi > WT * i;
-        }
-        s.cand[lane] = make_float4(e.x, e.z, __uint_as_float(x.z), __uint_as_float(gm));
-        s.prow[lane] = make_float2(e.y, e.w);
+        for (int i = 0; i < 4; ++i) ta[i] = clo < WT * i + WT && chi > WT * i;
+        s.cand[lane] = make_float4(e.a.x, e.a.z, __uint_as_float(e.b.z), 0.f);
+        s.prow[lane] = make_float2(e.a.y, e.a.w);
+    }
+    if (ACC) {
+        for (int k = 0; k < n; ++k) s.acc[k][lane] = 0.f;
     }
     WtMasks m;
     m.tb01 = __ballot_sync(0xffffffffu, ta[0]) | (__ballot_sync(0xffffffffu, ta[1]) << 16);
     m.tb23 = __ballot_sync(0xffffffffu, ta[2]) | (__ballot_sync(0xffffffffu, ta[3]) << 16);
     __syncwarp();
-    const float rp = (float)(r0 + 2 * (lane & 7));
+    const float rp = r0f + (float)(2 * (lane & 7));
     for (int t = lane; t < n * (WT / 2); t += 32) {
         const int k = t >> 3, p = t & 7;
         const float2 pf = s.prow[k];
@@ -144,25 +182,10 @@ __device__ __forceinline__ void run_to_rows(const float (&w)[8], float (&v)[8], 
     else        { v[0] = rcv[0]; v[1] = rcv[1]; v[2] = rcv[2]; v[3] = rcv[3]; v[4] = w[2]; v[5] = w[3]; v[6] = w[6]; v[7] = w[7]; }
 }
 
-// Super tile owned by this warp: grid = (super-tile columns, ceil(super-tile rows / 8), samples).
+// Position of a lane inside the super tile whose first texel is (r0, c0) of sample b.
 struct WtCoord {
-    int b, bin, stile, c0, r0, lane, h, lc;
-    bool valid;
+    int b, c0, r0, h, lc;
 };
-__device__ __forceinline__ WtCoord wt_coord(const RasterParams& q) {
-    WtCoord w;
-    w.b = blockIdx.z;
-    w.bin = q.shared_pattern ? 0 : w.b;
-    w.lane = threadIdx.x & 31;
-    const int sty = blockIdx.y * WT_WARPS + (threadIdx.x >> 5);
-    w.valid = sty < q.tgy;
-    w.stile = sty * q.tgx + blockIdx.x;
-    w.c0 = blockIdx.x * (4 * WT);
-    w.r0 = sty * WT;
-    w.lc = w.lane & 15;
-    w.h = w.lane >> 4;
-    return w;
-}
 
 // Tile access.  A lane addresses its first texel once per super tile (TilePtr) and then steps from tile to tile;
 // natural [ts1, ts0]: v[2i + j] <-> row r0 + 4i + 2h + j, column c;  transposed [ts0, ts1] (baked_sum_2's
@@ -250,15 +273,14 @@ __device__ __forceinline__ void prod_group(float2& acc_p, float2 g, bool pco, fl
     }
 }
 
-// sum and/or soft-OR product of one 16x16 tile over the staged candidates that touch it
+// sum and/or soft-OR product of one 16x16 tile over the staged candidates that touch it (bit k of tm: candidate k)
 template <bool SUM, bool SOFTOR, bool MASK_O, typename Stage>
 __device__ __forceinline__ void accumulate_tile(const Stage& st, unsigned tm, float cf, int h, const WtConsts& fc,
                                                 float2 (&acc_s)[4], float2 (&acc_p)[4]) {
     while (tm) {                                                                      // warp-uniform
         const int k = __ffs(tm) - 1;
         tm &= tm - 1;
-        const float4 cd = st.cand[k];
-        const unsigned gm = __float_as_uint(cd.w);
+        const float2 cd = *reinterpret_cast<const float2*>(&st.cand[k]);
         const float dx = cf - cd.x;
         const float dx2 = __fmul_rn(dx, dx);
         const float ec = fabsf(cf - cd.y);
@@ -266,82 +288,99 @@ __device__ __forceinline__ void accumulate_tile(const Stage& st, unsigned tm, fl
         const float4* tA = &st.tabA[k][h];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            if (!FFB_GROUP_SKIP_FWD || (gm & (1u << i))) {                            // warp-uniform
-                const float4 A = tA[2 * i];
-                const float2 d2 = __fadd2_rn(bc(dx2), make_float2(A.x, A.y));        // dc*dc + dr*dr, as the reference
-                const float2 t = __fmul2_rn(__fmul2_rn(d2, d2), bc(fc.K2));
-                const float2 g = make_float2(ex2_approx(t.x), ex2_approx(t.y));
-                if (SUM) { if (pcs) acc_s[i] = __ffma2_rn(g, make_float2(A.z, A.w), acc_s[i]); }
-                if (SOFTOR) {
-                    float2 mo = bc(1.f);
-                    if (MASK_O) { const float4 Bq = st.tabB[k][2 * i + h]; mo = make_float2(Bq.z, Bq.w); }
-                    prod_group<MASK_O>(acc_p[i], g, pco, mo);
-                }
+            const float4 A = tA[2 * i];
+            const float2 d2 = __fadd2_rn(bc(dx2), make_float2(A.x, A.y));            // dc*dc + dr*dr, as the reference
+            const float2 t = __fmul2_rn(__fmul2_rn(d2, d2), bc(fc.K2));
+            const float2 g = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+            if (SUM) { if (pcs) acc_s[i] = __ffma2_rn(g, make_float2(A.z, A.w), acc_s[i]); }
+            if (SOFTOR) {
+                float2 mo = bc(1.f);
+                if (MASK_O) { const float4 Bq = st.tabB[k][2 * i + h]; mo = make_float2(Bq.z, Bq.w); }
+                prod_group<MASK_O>(acc_p[i], g, pco, mo);
             }
         }
     }
 }
 
-__device__ __forceinline__ unsigned tile_mask(const WtMasks& mk, int j) {
-    return (((j & 2) ? mk.tb23 : mk.tb01) >> (16 * (j & 1))) & 0xffffu;
+// writes one finished 16x16 tile
+template <bool SUM, bool SOFTOR, bool SUM_T>
+__device__ __forceinline__ void store_tile(const RasterParams& q, const WtCoord& w, const TilePtr& tp, int j,
+                                           const float2 (&acc_s)[4], const float2 (&acc_p)[4]) {
+    const int ct = w.c0 + WT * j, c = ct + w.lc;
+    const bool interior = w.r0 + WT <= q.ts1 && ct + WT <= q.ts0;
+    float v[8];
+    if (SOFTOR) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = 1.f - acc_p[i].x; v[2 * i + 1] = 1.f - acc_p[i].y; }
+        store_natural(q.out_softor + tp.nat + WT * j, q, w, c, interior, v);
+    }
+    if (SUM) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = acc_s[i].x; v[2 * i + 1] = acc_s[i].y; }
+        if (SUM_T) {
+            float run[8];
+            rows_to_run(v, run, w.h);
+            store_run(q.out_sum + tp.tr + (size_t)(WT * j) * q.ts1, q, w, c, interior, run);
+        } else {
+            store_natural(q.out_sum + tp.nat + WT * j, q, w, c, interior, v);
+        }
+    }
+}
+
+// The strip of super tiles a warp owns, and its list offsets (one load for the whole strip).
+struct Strip {
+    int b, bin, c0, sty0, nst, lane, tv;
+};
+__device__ __forceinline__ bool strip_init(Strip& s, const RasterParams& q) {
+    s.b = blockIdx.z;
+    s.bin = q.shared_pattern ? 0 : s.b;
+    s.lane = threadIdx.x & 31;
+    s.sty0 = (blockIdx.y * WT_WARPS + (threadIdx.x >> 5)) * WT_S;
+    if (s.sty0 >= q.tgy) return false;
+    s.nst = min(WT_S, q.tgy - s.sty0);
+    s.c0 = blockIdx.x * (4 * WT);
+    const int* toff = q.tile_off + (size_t)s.bin * (q.T + 1) + (size_t)s.sty0 * q.tgx + blockIdx.x;
+    s.tv = 0;
+    if (s.lane < 2 * s.nst) s.tv = __ldg(toff + (s.lane >> 1) * q.tgx + (s.lane & 1));   // lane 2k: begin, lane 2k+1: end of super tile k
+    return true;
 }
 
 template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O>
 __global__ void __launch_bounds__(WT_CTA, FFB_FWD_MINB) splat_fwd_wt(RasterParams q, WtConsts fc) {
     __shared__ WarpStage<MASK_O> stage[WT_WARPS];
-    const WtCoord w = wt_coord(q);
-    if (!w.valid) return;                                  // whole warp; no block-level barriers below
+    Strip sp;
+    if (!strip_init(sp, q)) return;                        // whole warp; no block-level barriers below
     WarpStage<MASK_O>& st = stage[threadIdx.x >> 5];
-    const int* toff = q.tile_off + (size_t)w.bin * (q.T + 1) + w.stile;
-    const int beg = __ldg(toff), end = __ldg(toff + 1);
-    const Entry* entries = q.entries + (size_t)w.bin * q.cap;
-    const bool single = end - beg <= WCH;
-    WtMasks mk;
-    mk.tb01 = 0; mk.tb23 = 0;
-    if (single) mk = stage_warp(st, entries, beg, end - beg, w.c0, w.r0, fc, w.lane);
-    const TilePtr tp = tile_ptr(q, w);
-    float* po = SOFTOR ? q.out_softor + tp.nat : nullptr;
-    float* ps = SUM ? q.out_sum + (SUM_T ? tp.tr : tp.nat) : nullptr;
-    const bool rows_in = w.r0 + WT <= q.ts1;
+    const Entry* entries = q.entries + (size_t)sp.bin * q.cap;
+    WtCoord w;
+    w.b = sp.b; w.c0 = sp.c0; w.lc = sp.lane & 15; w.h = sp.lane >> 4;
+    int n = __shfl_sync(0xffffffffu, sp.tv, 1) - __shfl_sync(0xffffffffu, sp.tv, 0);
+    prefetch_entries(st.raw[0], entries + __shfl_sync(0xffffffffu, sp.tv, 0), n <= WCH ? n : 0, sp.lane);
 
-    for (int j = 0; j < 4; ++j) {
-        const int ct = w.c0 + WT * j;
-        if (ct >= q.ts0) break;
-        const int c = ct + w.lc;
-        const bool interior = rows_in && ct + WT <= q.ts0;
-        const float cf = (float)c;
-        float2 acc_s[4], acc_p[4];
+    for (int s = 0; s < sp.nst; ++s) {
+        const EntryRegs e = take_entry(st.raw[s & 1], n <= WCH ? n : 0, sp.lane);
+        // candidate records of the next super tile: in flight while this one is computed
+        int nn = 0;
+        if (s + 1 < sp.nst) {
+            const int nb = __shfl_sync(0xffffffffu, sp.tv, 2 * s + 2);
+            nn = __shfl_sync(0xffffffffu, sp.tv, 2 * s + 3) - nb;
+            prefetch_entries(st.raw[(s + 1) & 1], entries + nb, nn <= WCH ? nn : 0, sp.lane);
+        }
+        if (n <= WCH) {                                    // larger lists belong to the overflow kernel
+            w.r0 = (sp.sty0 + s) * WT;
+            const WtMasks mk = stage_regs(st, e, n, w.c0, (float)w.r0, fc, sp.lane);
+            const TilePtr tp = tile_ptr(q, w);
+            for (int j = 0; j < 4; ++j) {
+                const int ct = w.c0 + WT * j;
+                if (ct >= q.ts0) break;
+                float2 acc_s[4], acc_p[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { acc_s[i] = bc(0.f); acc_p[i] = bc(1.f); }
-        if (single) {
-            accumulate_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mk, j), cf, w.h, fc, acc_s, acc_p);
-        } else {
-            for (int base = beg; base < end; base += WCH) {
-                const WtMasks mc = stage_warp(st, entries, base, min(WCH, end - base), w.c0, w.r0, fc, w.lane);
-                accumulate_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mc, j), cf, w.h, fc, acc_s, acc_p);
+                for (int i = 0; i < 4; ++i) { acc_s[i] = bc(0.f); acc_p[i] = bc(1.f); }
+                accumulate_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mk, j), (float)(ct + w.lc), w.h, fc, acc_s, acc_p);
+                store_tile<SUM, SOFTOR, SUM_T>(q, w, tp, j, acc_s, acc_p);      // every texel of the tile is written exactly once
             }
         }
-        // epilogue: every texel of the tile is written exactly once
-        float v[8];
-        if (SOFTOR) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { v[2 * i] = 1.f - acc_p[i].x; v[2 * i + 1] = 1.f - acc_p[i].y; }
-            store_natural(po, q, w, c, interior, v);
-            po += WT;
-        }
-        if (SUM) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { v[2 * i] = acc_s[i].x; v[2 * i + 1] = acc_s[i].y; }
-            if (SUM_T) {
-                float run[8];
-                rows_to_run(v, run, w.h);
-                store_run(ps, q, w, c, interior, run);
-                ps += (size_t)WT * q.ts1;
-            } else {
-                store_natural(ps, q, w, c, interior, v);
-                ps += WT;
-            }
-        }
+        n = nn;
     }
 }
 
@@ -349,16 +388,15 @@ __global__ void __launch_bounds__(WT_CTA, FFB_FWD_MINB) splat_fwd_wt(RasterParam
 // SAVED: the forward's soft-OR output is available, prod = 1 - O; otherwise a first pass rebuilds prod.
 // 1 - g is evaluated as (1 + 2^-23) - g so that a point sitting on a texel centre (g = 1) gives a finite
 // quotient; the texel's weight g*d2*(c - P) vanishes there, and the bias is <= 1.2e-7 relative elsewhere.
-// Each (candidate, tile) partial is folded across the warp at once (lanes 0-15 end up with d/dp0, lanes 16-31 with
-// d/dp1) and kept by the lane whose number is the candidate's slot: `accv` of lane k / k+16 is candidate k's sum.
+// Each (candidate, tile) partial is folded once across the half warps (lanes 0-15 then hold d/dp0 parts, lanes 16-31
+// d/dp1 parts) and parked in shared memory; flush_warp sums a candidate's 16 parts in one lane, all candidates at once.
 template <bool SUM, bool SOFTOR, bool MASK_O, typename Stage>
-__device__ __forceinline__ void weigh_tile(const Stage& st, unsigned tm, float cf, int h, int lc, const WtConsts& fc,
-                                           const float2 (&gs)[4], const float2 (&gp)[4], float& accv) {
+__device__ __forceinline__ void weigh_tile(Stage& st, unsigned tm, float cf, int h, int lane, const WtConsts& fc,
+                                           const float2 (&gs)[4], const float2 (&gp)[4]) {
     while (tm) {
         const int k = __ffs(tm) - 1;
         tm &= tm - 1;
-        const float4 cd = st.cand[k];
-        const unsigned gm = __float_as_uint(cd.w);
+        const float2 cd = *reinterpret_cast<const float2*>(&st.cand[k]);
         const float dx = cf - cd.x;
         const float dx2 = __fmul_rn(dx, dx);
         const float ec = fabsf(cf - cd.y);
@@ -368,56 +406,53 @@ __device__ __forceinline__ void weigh_tile(const Stage& st, unsigned tm, float c
         float2 a0 = bc(0.f), a1 = bc(0.f);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            if (!FFB_GROUP_SKIP_BWD || (gm & (1u << i))) {
-                const float4 A = tA[2 * i];
-                const float4 Bq = tB[2 * i];
-                const float2 d2 = __fadd2_rn(bc(dx2), make_float2(A.x, A.y));
-                const float2 t = __fmul2_rn(__fmul2_rn(d2, d2), bc(fc.K2));
-                const float2 g = make_float2(ex2_approx(t.x), ex2_approx(t.y));
-                float2 coef = bc(0.f);
-                if (SOFTOR) {
-                    if (MASK_O) {
-                        const float2 mm = pco ? make_float2(Bq.z, Bq.w) : bc(0.f);
-                        const float2 om = __ffma2_rn(neg2(g), mm, bc(fc.c1));
-                        coef = __fmul2_rn(__fmul2_rn(gp[i], mm), make_float2(rcp_approx(om.x), rcp_approx(om.y)));
-                    } else {
-                        const float2 om = __fadd2_rn(bc(fc.c1), neg2(g));
-                        coef = __fmul2_rn(gp[i], make_float2(rcp_approx(om.x), rcp_approx(om.y)));   // gO * prod_{m != n}(1 - g_m)
-                    }
+            const float4 A = tA[2 * i];
+            const float4 Bq = tB[2 * i];
+            const float2 d2 = __fadd2_rn(bc(dx2), make_float2(A.x, A.y));
+            const float2 t = __fmul2_rn(__fmul2_rn(d2, d2), bc(fc.K2));
+            const float2 g = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+            float2 coef = bc(0.f);
+            if (SOFTOR) {
+                if (MASK_O) {
+                    const float2 mm = pco ? make_float2(Bq.z, Bq.w) : bc(0.f);
+                    const float2 om = __ffma2_rn(neg2(g), mm, bc(fc.c1));
+                    coef = __fmul2_rn(__fmul2_rn(gp[i], mm), make_float2(rcp_approx(om.x), rcp_approx(om.y)));
+                } else {
+                    const float2 om = __fadd2_rn(bc(fc.c1), neg2(g));
+                    coef = __fmul2_rn(gp[i], make_float2(rcp_approx(om.x), rcp_approx(om.y)));   // gO * prod_{m != n}(1 - g_m)
                 }
-                if (SUM) { if (pcs) coef = __ffma2_rn(gs[i], make_float2(A.z, A.w), coef); }
-                const float2 wgt = __fmul2_rn(__fmul2_rn(coef, g), d2);
-                a0 = __ffma2_rn(wgt, bc(dx), a0);
-                a1 = __ffma2_rn(wgt, make_float2(Bq.x, Bq.y), a1);
             }
+            if (SUM) { if (pcs) coef = __ffma2_rn(gs[i], make_float2(A.z, A.w), coef); }
+            const float2 wgt = __fmul2_rn(__fmul2_rn(coef, g), d2);
+            a0 = __ffma2_rn(wgt, bc(dx), a0);
+            a1 = __ffma2_rn(wgt, make_float2(Bq.x, Bq.y), a1);
         }
         const float s0 = a0.x + a0.y, s1 = a1.x + a1.y;
-        float x = h ? s1 : s0;
-        const float y = h ? s0 : s1;
-        x += __shfl_xor_sync(0xffffffffu, y, 16);
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lc == k) accv += x;
+        const float keep = h ? s1 : s0, give = h ? s0 : s1;
+        st.acc[k][lane] += keep + __shfl_xor_sync(0xffffffffu, give, 16);
     }
 }
 
+// lane k (k < n) sums candidate k's d/dp0 parts, lane 16 + k its d/dp1 parts; one atomic each
 template <typename Stage>
-__device__ __forceinline__ void flush_warp(const Stage& st, int n, int lc, float kh, float* __restrict__ dp, float& accv) {
+__device__ __forceinline__ void flush_warp(const Stage& st, int n, int h, int lc, float kh, float* __restrict__ dp) {
+    __syncwarp();
     if (lc < n) {
-        const float val = accv * kh;
+        const float* a = &st.acc[lc][16 * h];
+        float x = 0.f, y = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) { x += a[j]; y += a[j + 1]; }
+        const float val = (x + y) * kh;
         if (val != 0.f) atomicAdd(dp + (size_t)__float_as_int(st.cand[lc].z) * 2, val);
     }
-    accv = 0.f;
 }
 
 // raw upstream values of one tile, as loaded (the transposed sum gradient still in run order)
-template <bool SUM, bool SOFTOR, bool SUM_T, bool SAVED>
 struct TileIn {
-    float s[8], o[8], sv[8];       // unused members are never touched and cost no registers
+    float s[8], o[8], sv[8];       // members a kernel variant does not use are never touched and cost no registers
 };
 template <bool SUM, bool SOFTOR, bool SUM_T, bool SAVED>
-__device__ __forceinline__ void load_tile_in(TileIn<SUM, SOFTOR, SUM_T, SAVED>& t, const RasterParams& q, const WtCoord& w,
-                                             const TilePtr& tp, int j) {
+__device__ __forceinline__ void load_tile_in(TileIn& t, const RasterParams& q, const WtCoord& w, const TilePtr& tp, int j) {
     const int ct = w.c0 + WT * j, c = ct + w.lc;
     const bool interior = w.r0 + WT <= q.ts1 && ct + WT <= q.ts0;
     if (SUM) {
@@ -429,77 +464,188 @@ __device__ __forceinline__ void load_tile_in(TileIn<SUM, SOFTOR, SUM_T, SAVED>& 
         if (SAVED) load_natural(q.saved_softor + tp.nat + WT * j, q, w, c, interior, t.sv);
     }
 }
+// upstream gradients of this lane's 8 texels: gs = gS, gp = gO (* prod when the forward's output is at hand)
+template <bool SUM, bool SOFTOR, bool SUM_T, bool SAVED>
+__device__ __forceinline__ void unpack_tile_in(const TileIn& in, int h, float2 (&gs)[4], float2 (&gp)[4]) {
+    if (SUM) {
+        float v[8];
+        if (SUM_T) run_to_rows(in.s, v, h);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gs[i] = SUM_T ? make_float2(v[2 * i], v[2 * i + 1]) : make_float2(in.s[2 * i], in.s[2 * i + 1]);
+    }
+    if (SOFTOR) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            gp[i] = make_float2(in.o[2 * i], in.o[2 * i + 1]);
+            if (SAVED) gp[i] = __fmul2_rn(gp[i], make_float2(1.f - in.sv[2 * i], 1.f - in.sv[2 * i + 1]));
+        }
+    }
+}
 
 template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O, bool SAVED>
 __global__ void __launch_bounds__(WT_CTA, FFB_BWD_MINB) splat_bwd_wt(RasterParams q, WtConsts fc) {
-    typedef WarpStage<true> Stage;
-    __shared__ Stage stage[WT_WARPS];
-    const WtCoord w = wt_coord(q);
-    if (!w.valid) return;
-    Stage& st = stage[threadIdx.x >> 5];
-    const int* toff = q.tile_off + (size_t)w.bin * (q.T + 1) + w.stile;
-    const int beg = __ldg(toff), end = __ldg(toff + 1);
-    if (beg == end) return;
-    const TilePtr tp = tile_ptr(q, w);
-    TileIn<SUM, SOFTOR, SUM_T, SAVED> in;
-    load_tile_in(in, q, w, tp, 0);                          // in flight while the candidates are staged
-    const Entry* entries = q.entries + (size_t)w.bin * q.cap;
-    const bool single = end - beg <= WCH;
+    typedef WarpStage<true, true> Stage;
+    extern __shared__ __align__(16) unsigned char wt_smem[];
+    Strip sp;
+    if (!strip_init(sp, q)) return;
+    Stage& st = reinterpret_cast<Stage*>(wt_smem)[threadIdx.x >> 5];
+    const Entry* entries = q.entries + (size_t)sp.bin * q.cap;
+    WtCoord w;
+    w.b = sp.b; w.c0 = sp.c0; w.lc = sp.lane & 15; w.h = sp.lane >> 4;
     const float inv_s2 = q.rcp_sigma * q.rcp_sigma;
     const float kh = 4.f * (w.h ? (float)q.ts1 : (float)q.ts0) * inv_s2;     // lanes 0-15 report d/dp0, lanes 16-31 d/dp1
-    float* dp = q.d_pts + (size_t)w.b * q.N * 2 + w.h;
-    float accv = 0.f;
-    WtMasks mk;
-    mk.tb01 = 0; mk.tb23 = 0;
-    if (single) mk = stage_warp(st, entries, beg, end - beg, w.c0, w.r0, fc, w.lane);
+    float* dp = q.d_pts + (size_t)sp.b * q.N * 2 + w.h;
+    int n = __shfl_sync(0xffffffffu, sp.tv, 1) - __shfl_sync(0xffffffffu, sp.tv, 0);
+    prefetch_entries(st.raw[0], entries + __shfl_sync(0xffffffffu, sp.tv, 0), n <= WCH ? n : 0, sp.lane);
+    TileIn in;
+    bool have = false;                                     // `in` holds tile 0 of the current super tile
 
-    for (int j = 0; j < 4; ++j) {
-        const int ct = w.c0 + WT * j;
-        if (ct >= q.ts0) break;
-        const float cf = (float)(ct + w.lc);
-        // upstream gradients of this lane's 8 texels
-        float2 gs[4], gp[4];
-        if (SUM) {
-            float v[8];
-            if (SUM_T) run_to_rows(in.s, v, w.h);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) gs[i] = SUM_T ? make_float2(v[2 * i], v[2 * i + 1]) : make_float2(in.s[2 * i], in.s[2 * i + 1]);
+    for (int s = 0; s < sp.nst; ++s) {
+        const EntryRegs e = take_entry(st.raw[s & 1], n <= WCH ? n : 0, sp.lane);
+        int nn = 0;
+        if (s + 1 < sp.nst) {
+            const int nb = __shfl_sync(0xffffffffu, sp.tv, 2 * s + 2);
+            nn = __shfl_sync(0xffffffffu, sp.tv, 2 * s + 3) - nb;
+            prefetch_entries(st.raw[(s + 1) & 1], entries + nb, nn <= WCH ? nn : 0, sp.lane);
         }
-        if (SOFTOR) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                gp[i] = make_float2(in.o[2 * i], in.o[2 * i + 1]);
-                if (SAVED) gp[i] = __fmul2_rn(gp[i], make_float2(1.f - in.sv[2 * i], 1.f - in.sv[2 * i + 1]));
-            }
-        }
-        if (j < 3 && ct + WT < q.ts0) load_tile_in(in, q, w, tp, j + 1);      // prefetch the next tile
-        // pass 1 (only without the saved output): per-texel product of (1 - g)
-        if (SOFTOR && !SAVED) {
-            float2 prod[4], unused[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) prod[i] = bc(1.f);
-            if (single) {
-                accumulate_tile<false, true, MASK_O>(st, tile_mask(mk, j), cf, w.h, fc, unused, prod);
-            } else {
-                for (int base = beg; base < end; base += WCH) {
-                    const WtMasks mc = stage_warp(st, entries, base, min(WCH, end - base), w.c0, w.r0, fc, w.lane);
-                    accumulate_tile<false, true, MASK_O>(st, tile_mask(mc, j), cf, w.h, fc, unused, prod);
+        const bool next_live = nn > 0 && nn <= WCH;
+        if (n > 0 && n <= WCH) {                           // empty: nothing to do; larger lists: overflow kernel
+            w.r0 = (sp.sty0 + s) * WT;
+            const TilePtr tp = tile_ptr(q, w);
+            if (!have) load_tile_in<SUM, SOFTOR, SUM_T, SAVED>(in, q, w, tp, 0);      // in flight while the candidates are staged
+            const WtMasks mk = stage_regs(st, e, n, w.c0, (float)w.r0, fc, sp.lane);
+            for (int j = 0; j < 4; ++j) {
+                const int ct = w.c0 + WT * j;
+                if (ct >= q.ts0) break;
+                float2 gs[4], gp[4];
+                unpack_tile_in<SUM, SOFTOR, SUM_T, SAVED>(in, w.h, gs, gp);
+                // prefetch the next tile (of this super tile, or tile 0 of the next one)
+                if (j < 3 && ct + WT < q.ts0) {
+                    load_tile_in<SUM, SOFTOR, SUM_T, SAVED>(in, q, w, tp, j + 1);
+                } else if (next_live) {
+                    WtCoord wn = w;
+                    wn.r0 = w.r0 + WT;
+                    load_tile_in<SUM, SOFTOR, SUM_T, SAVED>(in, q, wn, tile_ptr(q, wn), 0);
                 }
-            }
+                const unsigned tm = tile_mask(mk, j);
+                const float cf = (float)(ct + w.lc);
+                if (SOFTOR && !SAVED) {                    // pass 1 (only without the saved output): per-texel product of (1 - g)
+                    float2 prod[4], unused[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) gp[i] = __fmul2_rn(gp[i], prod[i]);
-        }
-        // pass 2: weights
-        if (single) {
-            weigh_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mk, j), cf, w.h, w.lc, fc, gs, gp, accv);
+                    for (int i = 0; i < 4; ++i) prod[i] = bc(1.f);
+                    accumulate_tile<false, true, MASK_O>(st, tm, cf, w.h, fc, unused, prod);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) gp[i] = __fmul2_rn(gp[i], prod[i]);
+                }
+                weigh_tile<SUM, SOFTOR, MASK_O>(st, tm, cf, w.h, sp.lane, fc, gs, gp);
+            }
+            flush_warp(st, n, w.h, w.lc, kh, dp);
+            have = next_live;
         } else {
+            have = false;
+        }
+        n = nn;
+    }
+}
+
+// ---- overflow: super tiles whose list is longer than one chunk ---------------------------------------------------------
+// The binning kernel appends such super tiles to a list; these kernels walk it with a small fixed grid, one warp per
+// (super tile, sample), staging 16 candidates at a time.  Same arithmetic, no prefetching.
+struct OvfParams {
+    const int* count;          // number of overflow super tiles (device)
+    const int* list;           // bin * T + super tile
+    int B;
+};
+__device__ __forceinline__ bool ovf_item(const RasterParams& q, const OvfParams& o, long long it, WtCoord& w, int& bin, int& stile) {
+    const int cnt = __ldg(o.count);
+    const long long items = (long long)cnt * (q.shared_pattern ? o.B : 1);
+    if (it >= items) return false;
+    const int li = (int)(it % cnt);
+    const int code = __ldg(o.list + li);
+    bin = code / q.T;
+    stile = code - bin * q.T;
+    w.b = q.shared_pattern ? (int)(it / cnt) : bin;
+    w.c0 = (stile % q.tgx) * (4 * WT);
+    w.r0 = (stile / q.tgx) * WT;
+    w.lc = threadIdx.x & 15;
+    w.h = (threadIdx.x & 31) >> 4;
+    return true;
+}
+
+template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O>
+__global__ void __launch_bounds__(WT_CTA) splat_fwd_ovf(RasterParams q, WtConsts fc, OvfParams o) {
+    __shared__ WarpStage<MASK_O> stage[WT_WARPS];
+    WarpStage<MASK_O>& st = stage[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * WT_WARPS;
+    for (long long it = (long long)blockIdx.x * WT_WARPS + (threadIdx.x >> 5);; it += nwarps) {
+        WtCoord w;
+        int bin, stile;
+        if (!ovf_item(q, o, it, w, bin, stile)) break;
+        const int* toff = q.tile_off + (size_t)bin * (q.T + 1) + stile;
+        const int beg = __ldg(toff), end = __ldg(toff + 1);
+        const Entry* entries = q.entries + (size_t)bin * q.cap;
+        const TilePtr tp = tile_ptr(q, w);
+        for (int j = 0; j < 4; ++j) {
+            const int ct = w.c0 + WT * j;
+            if (ct >= q.ts0) break;
+            float2 acc_s[4], acc_p[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { acc_s[i] = bc(0.f); acc_p[i] = bc(1.f); }
             for (int base = beg; base < end; base += WCH) {
                 const int n = min(WCH, end - base);
-                const WtMasks mc = stage_warp(st, entries, base, n, w.c0, w.r0, fc, w.lane);
-                weigh_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mc, j), cf, w.h, w.lc, fc, gs, gp, accv);
-                flush_warp(st, n, w.lc, kh, dp, accv);
+                const WtMasks mk = stage_regs(st, load_entry(entries, base, n, lane), n, w.c0, (float)w.r0, fc, lane);
+                accumulate_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mk, j), (float)(ct + w.lc), w.h, fc, acc_s, acc_p);
+            }
+            store_tile<SUM, SOFTOR, SUM_T>(q, w, tp, j, acc_s, acc_p);
+        }
+    }
+}
+
+template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O, bool SAVED>
+__global__ void __launch_bounds__(WT_CTA) splat_bwd_ovf(RasterParams q, WtConsts fc, OvfParams o) {
+    typedef WarpStage<true, true> Stage;
+    extern __shared__ __align__(16) unsigned char wt_smem[];
+    Stage& st = reinterpret_cast<Stage*>(wt_smem)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const float inv_s2 = q.rcp_sigma * q.rcp_sigma;
+    const long long nwarps = (long long)gridDim.x * WT_WARPS;
+    for (long long it = (long long)blockIdx.x * WT_WARPS + (threadIdx.x >> 5);; it += nwarps) {
+        WtCoord w;
+        int bin, stile;
+        if (!ovf_item(q, o, it, w, bin, stile)) break;
+        const int* toff = q.tile_off + (size_t)bin * (q.T + 1) + stile;
+        const int beg = __ldg(toff), end = __ldg(toff + 1);
+        const Entry* entries = q.entries + (size_t)bin * q.cap;
+        const TilePtr tp = tile_ptr(q, w);
+        const float kh = 4.f * (w.h ? (float)q.ts1 : (float)q.ts0) * inv_s2;
+        float* dp = q.d_pts + (size_t)w.b * q.N * 2 + w.h;
+        for (int j = 0; j < 4; ++j) {
+            const int ct = w.c0 + WT * j;
+            if (ct >= q.ts0) break;
+            const float cf = (float)(ct + w.lc);
+            TileIn in;
+            load_tile_in<SUM, SOFTOR, SUM_T, SAVED>(in, q, w, tp, j);
+            float2 gs[4], gp[4];
+            unpack_tile_in<SUM, SOFTOR, SUM_T, SAVED>(in, w.h, gs, gp);
+            if (SOFTOR && !SAVED) {
+                float2 prod[4], unused[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) prod[i] = bc(1.f);
+                for (int base = beg; base < end; base += WCH) {
+                    const int n = min(WCH, end - base);
+                    const WtMasks mk = stage_regs(st, load_entry(entries, base, n, lane), n, w.c0, (float)w.r0, fc, lane);
+                    accumulate_tile<false, true, MASK_O>(st, tile_mask(mk, j), cf, w.h, fc, unused, prod);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) gp[i] = __fmul2_rn(gp[i], prod[i]);
+            }
+            for (int base = beg; base < end; base += WCH) {
+                const int n = min(WCH, end - base);
+                const WtMasks mk = stage_regs(st, load_entry(entries, base, n, lane), n, w.c0, (float)w.r0, fc, lane);
+                weigh_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mk, j), cf, w.h, lane, fc, gs, gp);
+                flush_warp(st, n, w.h, w.lc, kh, dp);
             }
         }
     }
-    if (single) flush_warp(st, end - beg, w.lc, kh, dp, accv);
 }

@@ -151,6 +151,33 @@ def test_edge_cases(R):
     assert torch.isfinite(p.grad).all()
 
 
+@pytest.mark.parametrize("batched", [False, True])
+def test_clustered_points_take_the_overflow_path(R, batched):
+    """More than 16 candidates per 64x16 super tile: the warp-tile kernels hand those tiles to the overflow kernels."""
+    gen = torch.Generator().manual_seed(11)
+    n, ts, sigma = 120, [200, 136], 25.0
+    pts = torch.cat([0.45 + 0.1 * torch.rand(90, 2, generator=gen), torch.rand(30, 2, generator=gen)])   # 90 points in a 20x14 texel patch
+    wS, wO = torch.randn(ts[1], ts[0], generator=gen), torch.randn(ts[1], ts[0], generator=gen)
+    if batched:
+        p = pts.unsqueeze(0).repeat(3, 1, 1).cuda().requires_grad_(True)
+        s, o = R.splat_reduce(p, sigma, ts)
+        ((s * wS.cuda()).sum() + (o * wO.cuda()).sum()).backward()
+        s, o, grad = s[2], o[2], p.grad[1]
+    else:
+        p = pts.cuda().requires_grad_(True)
+        s, o = R.splat_reduce(p, sigma, ts)
+        ((s * wS.cuda()).sum() + (o * wO.cuda()).sum()).backward()
+        grad = p.grad
+    close(s, O.baked_sum(pts, sigma, ts))
+    close(o, O.baked_softor(pts, sigma, ts), atol=2e-6)
+    ana = O.splat_grad_analytic(pts, sigma, ts, wS, wO, 4, 5)
+    close(grad, ana, rtol=1e-4, atol=1e-4 * ana.abs().max().item())
+    # without the saved soft-OR output (first pass rebuilds the product)
+    plan = R._SplatPlan(pts.cuda(), 1, sigma, ts[0], ts[1], 4, 5)
+    d = plan.backward(pts.cuda(), wS.cuda().unsqueeze(0).contiguous(), wO.cuda().unsqueeze(0).contiguous(), False)
+    close(d[0], ana, rtol=1e-4, atol=1e-4 * ana.abs().max().item())
+
+
 def test_batched_and_shared_patterns(R):
     gen = torch.Generator().manual_seed(9)
     B, n, ts, sigma = 5, 40, [96, 72], 16.0
