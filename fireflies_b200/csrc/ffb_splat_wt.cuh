@@ -38,11 +38,17 @@
 constexpr int WT_S = 4;                   // vertically adjacent super tiles per warp
 constexpr int WT_CTA = 256;               // 8 warps x 4 super tiles (64 x 16 texels each) = 64 x 512 texels
 constexpr int WT_WARPS = WT_CTA / 32;
+#ifndef FFB_FFS_LOOP
+#define FFB_FFS_LOOP 1                    // 1: walk a tile's candidate mask with ffs (two XU-pipe ops per candidate); 0: test bit k of the mask for k < n
+#endif
+#ifndef FFB_BWD_SKIP
+#define FFB_BWD_SKIP 0                    // backward: skip 16x4 row groups outside a candidate's row span (measured slower: the branches cost more than the skipped MUFUs)
+#endif
 #ifndef FFB_FWD_MINB
 #define FFB_FWD_MINB 4                    // resident CTAs per SM the register allocation aims for
 #endif
 #ifndef FFB_BWD_MINB
-#define FFB_BWD_MINB 2
+#define FFB_BWD_MINB 3
 #endif
 
 struct WtConsts {
@@ -69,14 +75,18 @@ __device__ __forceinline__ float2 bc(float x) { return make_float2(x, x); }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 
 // Per-warp staging: candidate records and the (candidate, row pair) tables of the warp's 16 rows.
-template <bool TABB, bool ACC = false>
+// TABB: 0 = no second table, 1 = dy only (float2), 2 = dy + soft-OR row mask (float4).  ACC: backward partial-sum parking.
+// TIN: backward staging buffers for the upstream tile (cp.async targets).  NRAW: record buffers (2 = double buffered).
+template <int TABB, bool ACC = false, bool TIN = false, int NRAW = 2>
 struct WarpStage {
-    float4 cand[WCH];                     // p0, f0, point index (bits), -
+    float4 cand[WCH];                     // p0, f0, point index (bits), row-group mask (bits)
     float2 prow[WCH];                     // p1, f1
     float4 tabA[WCH][WT / 2];             // dy^2 (2 rows), sum row mask (2 rows)
-    float4 tabB[TABB ? WCH : 1][WT / 2];  // dy (2 rows), soft-OR row mask (2 rows)
-    uint4 raw[2][2 * WCH];                // candidate records as fetched by cp.async, double buffered across super tiles
+    float4 tabB4[TABB == 2 ? WCH : 1][WT / 2];   // dy (2 rows), soft-OR row mask (2 rows)
+    float2 tabB2[TABB == 1 ? WCH : 1][WT / 2];   // dy (2 rows)
+    uint4 raw[NRAW][2 * WCH];             // candidate records as fetched by cp.async
     float acc[ACC ? WCH : 1][33];         // backward: per-lane d/dP partial sums (lanes 0-15: d/dp0, 16-31: d/dp1), row padded
+    float tin[TIN ? 2 : 1][TIN ? WT : 1][TIN ? 24 : 4];   // backward: upstream soft-OR gradient / saved output tile, rows padded to 24 (bank-conflict free)
 };
 
 // Which staged candidates touch which 16x16 tile: warp-uniform ballots, 16 bits per tile.
@@ -125,16 +135,31 @@ __device__ __forceinline__ EntryRegs take_entry(const uint4* raw, int n, int lan
     return e;
 }
 
-template <bool TABB, bool ACC>
-__device__ __forceinline__ WtMasks stage_regs(WarpStage<TABB, ACC>& s, const EntryRegs& e, int n, int c0, const float r0f,
+template <typename Stage>
+struct StageTraits;
+template <int TABB, bool ACC, bool TIN, int NRAW>
+struct StageTraits<WarpStage<TABB, ACC, TIN, NRAW>> {
+    static constexpr int tabb = TABB;
+    static constexpr bool acc = ACC;
+};
+
+template <typename Stage>
+__device__ __forceinline__ WtMasks stage_regs(Stage& s, const EntryRegs& e, int n, int c0, const float r0f,
                                               const WtConsts& fc, int lane) {
+    constexpr int TABB = StageTraits<Stage>::tabb;
+    constexpr bool ACC = StageTraits<Stage>::acc;
     __syncwarp();                         // previous chunk fully consumed
     bool ta[4] = {false, false, false, false};
     if (lane < n) {
-        const int clo = (int)(e.b.y & 0xffff) - c0, chi = (int)(e.b.y >> 16) - c0;  // column span relative to the super tile
+        const int clo = (int)(e.b.y & 0xffff) - c0, chi = (int)(e.b.y >> 16) - c0;  // spans relative to the super tile
+        const int r0 = (int)r0f, rlo = (int)(e.b.x & 0xffff) - r0, rhi = (int)(e.b.x >> 16) - r0;
+        unsigned gm = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ta[i] = clo < WT * i + WT && chi > WT * i;
-        s.cand[lane] = make_float4(e.a.x, e.a.z, __uint_as_float(e.b.z), 0.f);
+        for (int i = 0; i < 4; ++i) {
+            ta[i] = clo < WT * i + WT && chi > WT * i;
+            if (rlo < 4 * i + 4 && rhi > 4 * i) gm |= 1u << i;
+        }
+        s.cand[lane] = make_float4(e.a.x, e.a.z, __uint_as_float(e.b.z), __uint_as_float(gm));
         s.prow[lane] = make_float2(e.a.y, e.a.w);
     }
     if (ACC) {
@@ -152,7 +177,8 @@ __device__ __forceinline__ WtMasks stage_regs(WarpStage<TABB, ACC>& s, const Ent
         const float da = ra - pf.x, db = rb - pf.x;
         const float ea = ra - pf.y, eb = rb - pf.y;
         s.tabA[k][p] = make_float4(__fmul_rn(da, da), __fmul_rn(db, db), cheb_mask(ea, fc.thr_s), cheb_mask(eb, fc.thr_s));
-        if (TABB) s.tabB[k][p] = make_float4(da, db, cheb_mask(ea, fc.thr_o), cheb_mask(eb, fc.thr_o));
+        if (TABB == 2) s.tabB4[k][p] = make_float4(da, db, cheb_mask(ea, fc.thr_o), cheb_mask(eb, fc.thr_o));
+        if (TABB == 1) s.tabB2[k][p] = make_float2(da, db);
     }
     __syncwarp();
     return m;
@@ -275,11 +301,16 @@ __device__ __forceinline__ void prod_group(float2& acc_p, float2 g, bool pco, fl
 
 // sum and/or soft-OR product of one 16x16 tile over the staged candidates that touch it (bit k of tm: candidate k)
 template <bool SUM, bool SOFTOR, bool MASK_O, typename Stage>
-__device__ __forceinline__ void accumulate_tile(const Stage& st, unsigned tm, float cf, int h, const WtConsts& fc,
+__device__ __forceinline__ void accumulate_tile(const Stage& st, unsigned tm, int n, float cf, int h, const WtConsts& fc,
                                                 float2 (&acc_s)[4], float2 (&acc_p)[4]) {
+#if FFB_FFS_LOOP
     while (tm) {                                                                      // warp-uniform
         const int k = __ffs(tm) - 1;
         tm &= tm - 1;
+#else
+    for (int k = 0; k < n; ++k) {
+        if (!((tm >> k) & 1u)) continue;                                              // warp-uniform
+#endif
         const float2 cd = *reinterpret_cast<const float2*>(&st.cand[k]);
         const float dx = cf - cd.x;
         const float dx2 = __fmul_rn(dx, dx);
@@ -295,7 +326,7 @@ __device__ __forceinline__ void accumulate_tile(const Stage& st, unsigned tm, fl
             if (SUM) { if (pcs) acc_s[i] = __ffma2_rn(g, make_float2(A.z, A.w), acc_s[i]); }
             if (SOFTOR) {
                 float2 mo = bc(1.f);
-                if (MASK_O) { const float4 Bq = st.tabB[k][2 * i + h]; mo = make_float2(Bq.z, Bq.w); }
+                if (MASK_O) { const float4 Bq = st.tabB4[k][2 * i + h]; mo = make_float2(Bq.z, Bq.w); }
                 prod_group<MASK_O>(acc_p[i], g, pco, mo);
             }
         }
@@ -347,10 +378,11 @@ __device__ __forceinline__ bool strip_init(Strip& s, const RasterParams& q) {
 
 template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O>
 __global__ void __launch_bounds__(WT_CTA, FFB_FWD_MINB) splat_fwd_wt(RasterParams q, WtConsts fc) {
-    __shared__ WarpStage<MASK_O> stage[WT_WARPS];
+    typedef WarpStage<MASK_O ? 2 : 0> Stage;
+    __shared__ Stage stage[WT_WARPS];
     Strip sp;
     if (!strip_init(sp, q)) return;                        // whole warp; no block-level barriers below
-    WarpStage<MASK_O>& st = stage[threadIdx.x >> 5];
+    Stage& st = stage[threadIdx.x >> 5];
     const Entry* entries = q.entries + (size_t)sp.bin * q.cap;
     WtCoord w;
     w.b = sp.b; w.c0 = sp.c0; w.lc = sp.lane & 15; w.h = sp.lane >> 4;
@@ -376,7 +408,7 @@ __global__ void __launch_bounds__(WT_CTA, FFB_FWD_MINB) splat_fwd_wt(RasterParam
                 float2 acc_s[4], acc_p[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { acc_s[i] = bc(0.f); acc_p[i] = bc(1.f); }
-                accumulate_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mk, j), (float)(ct + w.lc), w.h, fc, acc_s, acc_p);
+                accumulate_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mk, j), n, (float)(ct + w.lc), w.h, fc, acc_s, acc_p);
                 store_tile<SUM, SOFTOR, SUM_T>(q, w, tp, j, acc_s, acc_p);      // every texel of the tile is written exactly once
             }
         }
@@ -391,23 +423,36 @@ __global__ void __launch_bounds__(WT_CTA, FFB_FWD_MINB) splat_fwd_wt(RasterParam
 // Each (candidate, tile) partial is folded once across the half warps (lanes 0-15 then hold d/dp0 parts, lanes 16-31
 // d/dp1 parts) and parked in shared memory; flush_warp sums a candidate's 16 parts in one lane, all candidates at once.
 template <bool SUM, bool SOFTOR, bool MASK_O, typename Stage>
-__device__ __forceinline__ void weigh_tile(Stage& st, unsigned tm, float cf, int h, int lane, const WtConsts& fc,
+__device__ __forceinline__ void weigh_tile(Stage& st, unsigned tm, int n, float cf, int h, int lane, const WtConsts& fc,
                                            const float2 (&gs)[4], const float2 (&gp)[4]) {
+#if FFB_FFS_LOOP
     while (tm) {
         const int k = __ffs(tm) - 1;
         tm &= tm - 1;
+#else
+    for (int k = 0; k < n; ++k) {
+        if (!((tm >> k) & 1u)) continue;
+#endif
+#if FFB_BWD_SKIP
+        const float4 cd = st.cand[k];
+        const unsigned gm = __float_as_uint(cd.w);
+#else
         const float2 cd = *reinterpret_cast<const float2*>(&st.cand[k]);
+        const unsigned gm = 15u;
+#endif
         const float dx = cf - cd.x;
         const float dx2 = __fmul_rn(dx, dx);
         const float ec = fabsf(cf - cd.y);
         const bool pcs = ec <= fc.hs, pco = ec <= fc.ho;
         const float4* tA = &st.tabA[k][h];
-        const float4* tB = &st.tabB[k][h];
         float2 a0 = bc(0.f), a1 = bc(0.f);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+            if (FFB_BWD_SKIP && !(gm & (1u << i))) continue;                          // warp-uniform
             const float4 A = tA[2 * i];
-            const float4 Bq = tB[2 * i];
+            float4 Bq;
+            if (MASK_O) Bq = st.tabB4[k][2 * i + h];
+            else { const float2 dy = st.tabB2[k][2 * i + h]; Bq = make_float4(dy.x, dy.y, 1.f, 1.f); }
             const float2 d2 = __fadd2_rn(bc(dx2), make_float2(A.x, A.y));
             const float2 t = __fmul2_rn(__fmul2_rn(d2, d2), bc(fc.K2));
             const float2 g = make_float2(ex2_approx(t.x), ex2_approx(t.y));
@@ -482,9 +527,34 @@ __device__ __forceinline__ void unpack_tile_in(const TileIn& in, int h, float2 (
     }
 }
 
+// asynchronous copy of one natural-layout 16x16 tile into a padded shared buffer (interior tiles with 16-byte aligned
+// rows), or a guarded synchronous fill with the same layout otherwise
+__device__ __forceinline__ void stage_tile_async(float (&buf)[WT][24], const float* __restrict__ src, const RasterParams& q,
+                                                 const WtCoord& w, int ct, int lane) {
+    const bool interior = w.r0 + WT <= q.ts1 && ct + WT <= q.ts0;
+    const float* org = src + ((size_t)w.b * q.ts1 + w.r0) * q.ts0 + ct;
+    if (interior && (q.ts0 & 3) == 0 && (reinterpret_cast<size_t>(src) & 15) == 0) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int row = (lane >> 2) + 8 * t, ch = (lane & 3) * 4;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&buf[row][ch]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(org + (size_t)row * q.ts0 + ch) : "memory");
+        }
+    } else {
+        const int c = ct + w.lc, rb = 2 * w.h;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int r = rb + 4 * i + j;
+                buf[r][w.lc] = (c < q.ts0 && w.r0 + r < q.ts1) ? __ldg(org + (size_t)r * q.ts0 + w.lc) : 0.f;
+            }
+    }
+}
+
 template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O, bool SAVED>
 __global__ void __launch_bounds__(WT_CTA, FFB_BWD_MINB) splat_bwd_wt(RasterParams q, WtConsts fc) {
-    typedef WarpStage<true, true> Stage;
+    typedef WarpStage<MASK_O ? 2 : 1, true, true, 1> Stage;
     extern __shared__ __align__(16) unsigned char wt_smem[];
     Strip sp;
     if (!strip_init(sp, q)) return;
@@ -497,35 +567,68 @@ __global__ void __launch_bounds__(WT_CTA, FFB_BWD_MINB) splat_bwd_wt(RasterParam
     float* dp = q.d_pts + (size_t)sp.b * q.N * 2 + w.h;
     int n = __shfl_sync(0xffffffffu, sp.tv, 1) - __shfl_sync(0xffffffffu, sp.tv, 0);
     prefetch_entries(st.raw[0], entries + __shfl_sync(0xffffffffu, sp.tv, 0), n <= WCH ? n : 0, sp.lane);
-    TileIn in;
-    bool have = false;                                     // `in` holds tile 0 of the current super tile
+    float sraw[8];                                          // upstream sum gradient of the tile in flight (registers)
+    bool have = false;                                      // tile 0 of the current super tile is already in flight
+
+    // puts one tile's upstream values in flight: soft-OR gradient (+ saved output) through cp.async, sum gradient in registers
+    auto issue = [&](const WtCoord& wc, int j) {
+        const int ct = wc.c0 + WT * j;
+        if (SOFTOR) {
+            stage_tile_async(st.tin[0], q.g_softor, q, wc, ct, sp.lane);
+            if (SAVED) stage_tile_async(st.tin[1], q.saved_softor, q, wc, ct, sp.lane);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (SUM) {
+            const TilePtr tp = tile_ptr(q, wc);
+            const bool interior = wc.r0 + WT <= q.ts1 && ct + WT <= q.ts0;
+            if (SUM_T) load_run(q.g_sum + tp.tr + (size_t)(WT * j) * q.ts1, q, wc, ct + wc.lc, interior, sraw);
+            else load_natural(q.g_sum + tp.nat + WT * j, q, wc, ct + wc.lc, interior, sraw);
+        }
+    };
 
     for (int s = 0; s < sp.nst; ++s) {
-        const EntryRegs e = take_entry(st.raw[s & 1], n <= WCH ? n : 0, sp.lane);
+        const EntryRegs e = take_entry(st.raw[0], n <= WCH ? n : 0, sp.lane);
+        __syncwarp();                                       // every lane holds its record: the buffer may be refilled
         int nn = 0;
         if (s + 1 < sp.nst) {
             const int nb = __shfl_sync(0xffffffffu, sp.tv, 2 * s + 2);
             nn = __shfl_sync(0xffffffffu, sp.tv, 2 * s + 3) - nb;
-            prefetch_entries(st.raw[(s + 1) & 1], entries + nb, nn <= WCH ? nn : 0, sp.lane);
+            prefetch_entries(st.raw[0], entries + nb, nn <= WCH ? nn : 0, sp.lane);
         }
         const bool next_live = nn > 0 && nn <= WCH;
         if (n > 0 && n <= WCH) {                           // empty: nothing to do; larger lists: overflow kernel
             w.r0 = (sp.sty0 + s) * WT;
-            const TilePtr tp = tile_ptr(q, w);
-            if (!have) load_tile_in<SUM, SOFTOR, SUM_T, SAVED>(in, q, w, tp, 0);      // in flight while the candidates are staged
+            if (!have) issue(w, 0);
             const WtMasks mk = stage_regs(st, e, n, w.c0, (float)w.r0, fc, sp.lane);
             for (int j = 0; j < 4; ++j) {
                 const int ct = w.c0 + WT * j;
                 if (ct >= q.ts0) break;
+                // upstream gradients of this lane's 8 texels: gs = gS, gp = gO (* prod when the forward's output is at hand)
                 float2 gs[4], gp[4];
-                unpack_tile_in<SUM, SOFTOR, SUM_T, SAVED>(in, w.h, gs, gp);
-                // prefetch the next tile (of this super tile, or tile 0 of the next one)
+                if (SUM) {
+                    float v[8];
+                    if (SUM_T) run_to_rows(sraw, v, w.h);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) gs[i] = SUM_T ? make_float2(v[2 * i], v[2 * i + 1]) : make_float2(sraw[2 * i], sraw[2 * i + 1]);
+                }
+                if (SOFTOR) {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = 4 * i + 2 * w.h;
+                        gp[i] = make_float2(st.tin[0][r][w.lc], st.tin[0][r + 1][w.lc]);
+                        if (SAVED) gp[i] = __fmul2_rn(gp[i], make_float2(1.f - st.tin[1][r][w.lc], 1.f - st.tin[1][r + 1][w.lc]));
+                    }
+                    __syncwarp();                           // buffers consumed: the next tile may land
+                }
+                // next tile (of this super tile, or tile 0 of the next one) in flight while this one is computed
                 if (j < 3 && ct + WT < q.ts0) {
-                    load_tile_in<SUM, SOFTOR, SUM_T, SAVED>(in, q, w, tp, j + 1);
+                    issue(w, j + 1);
                 } else if (next_live) {
                     WtCoord wn = w;
                     wn.r0 = w.r0 + WT;
-                    load_tile_in<SUM, SOFTOR, SUM_T, SAVED>(in, q, wn, tile_ptr(q, wn), 0);
+                    issue(wn, 0);
                 }
                 const unsigned tm = tile_mask(mk, j);
                 const float cf = (float)(ct + w.lc);
@@ -533,11 +636,11 @@ __global__ void __launch_bounds__(WT_CTA, FFB_BWD_MINB) splat_bwd_wt(RasterParam
                     float2 prod[4], unused[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) prod[i] = bc(1.f);
-                    accumulate_tile<false, true, MASK_O>(st, tm, cf, w.h, fc, unused, prod);
+                    accumulate_tile<false, true, MASK_O>(st, tm, n, cf, w.h, fc, unused, prod);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) gp[i] = __fmul2_rn(gp[i], prod[i]);
                 }
-                weigh_tile<SUM, SOFTOR, MASK_O>(st, tm, cf, w.h, sp.lane, fc, gs, gp);
+                weigh_tile<SUM, SOFTOR, MASK_O>(st, tm, n, cf, w.h, sp.lane, fc, gs, gp);
             }
             flush_warp(st, n, w.h, w.lc, kh, dp);
             have = next_live;
@@ -574,8 +677,9 @@ __device__ __forceinline__ bool ovf_item(const RasterParams& q, const OvfParams&
 
 template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O>
 __global__ void __launch_bounds__(WT_CTA) splat_fwd_ovf(RasterParams q, WtConsts fc, OvfParams o) {
-    __shared__ WarpStage<MASK_O> stage[WT_WARPS];
-    WarpStage<MASK_O>& st = stage[threadIdx.x >> 5];
+    typedef WarpStage<MASK_O ? 2 : 0> Stage;
+    __shared__ Stage stage[WT_WARPS];
+    Stage& st = stage[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const long long nwarps = (long long)gridDim.x * WT_WARPS;
     for (long long it = (long long)blockIdx.x * WT_WARPS + (threadIdx.x >> 5);; it += nwarps) {
@@ -595,7 +699,7 @@ __global__ void __launch_bounds__(WT_CTA) splat_fwd_ovf(RasterParams q, WtConsts
             for (int base = beg; base < end; base += WCH) {
                 const int n = min(WCH, end - base);
                 const WtMasks mk = stage_regs(st, load_entry(entries, base, n, lane), n, w.c0, (float)w.r0, fc, lane);
-                accumulate_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mk, j), (float)(ct + w.lc), w.h, fc, acc_s, acc_p);
+                accumulate_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mk, j), n, (float)(ct + w.lc), w.h, fc, acc_s, acc_p);
             }
             store_tile<SUM, SOFTOR, SUM_T>(q, w, tp, j, acc_s, acc_p);
         }
@@ -604,7 +708,7 @@ __global__ void __launch_bounds__(WT_CTA) splat_fwd_ovf(RasterParams q, WtConsts
 
 template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O, bool SAVED>
 __global__ void __launch_bounds__(WT_CTA) splat_bwd_ovf(RasterParams q, WtConsts fc, OvfParams o) {
-    typedef WarpStage<true, true> Stage;
+    typedef WarpStage<MASK_O ? 2 : 1, true, false, 1> Stage;
     extern __shared__ __align__(16) unsigned char wt_smem[];
     Stage& st = reinterpret_cast<Stage*>(wt_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -635,7 +739,7 @@ __global__ void __launch_bounds__(WT_CTA) splat_bwd_ovf(RasterParams q, WtConsts
                 for (int base = beg; base < end; base += WCH) {
                     const int n = min(WCH, end - base);
                     const WtMasks mk = stage_regs(st, load_entry(entries, base, n, lane), n, w.c0, (float)w.r0, fc, lane);
-                    accumulate_tile<false, true, MASK_O>(st, tile_mask(mk, j), cf, w.h, fc, unused, prod);
+                    accumulate_tile<false, true, MASK_O>(st, tile_mask(mk, j), n, cf, w.h, fc, unused, prod);
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) gp[i] = __fmul2_rn(gp[i], prod[i]);
@@ -643,7 +747,7 @@ __global__ void __launch_bounds__(WT_CTA) splat_bwd_ovf(RasterParams q, WtConsts
             for (int base = beg; base < end; base += WCH) {
                 const int n = min(WCH, end - base);
                 const WtMasks mk = stage_regs(st, load_entry(entries, base, n, lane), n, w.c0, (float)w.r0, fc, lane);
-                weigh_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mk, j), cf, w.h, lane, fc, gs, gp);
+                weigh_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mk, j), n, cf, w.h, lane, fc, gs, gp);
                 flush_warp(st, n, w.h, w.lc, kh, dp);
             }
         }
