@@ -6,12 +6,17 @@
 //   fireflies/postprocessing/white_noise.py:16-20  WhiteNoise.post_process
 //   fireflies/postprocessing/base.py:10-14, postprocessor.py:14-19  (gates are drawn by the caller)
 //
-// HBM-bound stencil: each CTA produces a 128x32 output tile.  The input tile + halo is fetched by ONE
-// TMA tensor load (cp.async.bulk.tensor.3d) into shared memory -- out-of-image halo cells arrive as zeros
-// and are never read: the reflect border (kornia border_type="reflect", no edge repeat) is an index remap
-// onto in-tile cells.  (Measured on B200: the innermost TMA start coordinate must be a multiple of 16 bytes --
-// x = -1 raises 'illegal instruction', x = -4 works, any y works -- so the left halo is padded to 4 texels.)  Horizontal pass smem->smem, vertical pass smem->registers, noise/clip in registers,
-// 128-bit coalesced stores.  Traffic: 4 B read (+ halo re-reads served by L2) + 4 B written per texel.
+// HBM-bound stencil.  Production kernel (blur_sw_kernel, the kernel sizes the reference uses: 3, 5, 11): each CTA
+// produces a 128-column tile, 8 or 16 rows per warp.  The input tile + halo is fetched by ONE TMA tensor load
+// (cp.async.bulk.tensor.3d) into shared memory; out-of-image halo cells arrive as zeros and edge tiles patch them
+// with the reflected in-tile cells (kornia border_type="reflect", no edge repeat), so the inner loops carry no
+// index arithmetic.  (Measured on B200: the innermost TMA start coordinate must be a multiple of 16 bytes --
+// x = -1 raises 'illegal instruction', x = -4 works, any y works -- so the left halo is padded to 4 texels.)
+// A lane owns 4 columns: per input row it reads aligned 128-bit words, forms the 4 horizontal sums with
+// compile-time taps, pushes them into a register sliding window of KY rows and emits one output row
+// (vertical taps, noise / clip in registers, one 128-bit store).  No intermediate shared-memory pass.
+// Traffic: 4 B read (+ halo re-reads served by L2) + 4 B written per texel.
+// Other odd kernel sizes up to 15 take the generic kernel (blur_kernel: smem->smem horizontal, smem->register vertical).
 #include <cuda.h>
 
 #include "ffb_common.cuh"
@@ -48,10 +53,12 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint64_t frame, uint32_t 
     Philox::gen(seed, quad, 0x4E015E00u, (uint32_t)frame, (uint32_t)(frame >> 32), r);
     const float u0 = ((float)(r[0] >> 8) + 1.0f) * (1.0f / 16777216.0f), u1 = Philox::u01(r[1]);
     const float u2 = ((float)(r[2] >> 8) + 1.0f) * (1.0f / 16777216.0f), u3 = Philox::u01(r[3]);
-    const float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
+    // Box-Muller on the special-function unit: lg2, rsqrt, sin, cos (absolute error ~1e-6: statistical parity only)
+    const float xa = -1.3862943611198906f * __log2f(u0), xb = -1.3862943611198906f * __log2f(u2);   // -2 ln u
+    const float ra = xa * rsqrtf(fmaxf(xa, 1e-30f)), rb = xb * rsqrtf(fmaxf(xb, 1e-30f));
     float sa, ca, sb, cb;
-    sincospif(2.0f * u1, &sa, &ca);
-    sincospif(2.0f * u3, &sb, &cb);
+    __sincosf(6.283185307179586f * u1, &sa, &ca);
+    __sincosf(6.283185307179586f * u3, &sb, &cb);
     z[0] = ra * ca; z[1] = ra * sa; z[2] = rb * cb; z[3] = rb * sb;
 }
 
@@ -196,26 +203,163 @@ __global__ void __launch_bounds__(THREADS) blur_kernel(const __grid_constant__ C
     }
 }
 
+
+// ---- sliding-window blur ----------------------------------------------------------------------------------------------
+constexpr int SW_TW = 128;                 // tile width: 32 lanes x 4 columns
+template <int K> struct SwCfg {
+    static constexpr int H = K / 2;                      // taps each side
+    static constexpr int PADL = (H + 3) & ~3;            // left / right halo rounded to 4 texels (TMA alignment, aligned LDS.128)
+    static constexpr int NQ = PADL / 4;                  // extra 128-bit words each side
+    static constexpr int RW = K <= 5 ? 8 : 16;           // output rows per warp
+    static constexpr int TH = 8 * RW;                    // tile height (8 warps)
+    static constexpr int BOXW = SW_TW + 2 * PADL;
+    static constexpr int BOXH = TH + K - 1;
+};
+
+template <int KX, int KY>
+__global__ void __launch_bounds__(THREADS) blur_sw_kernel(const __grid_constant__ CUtensorMap tmap, const PostParams q) {
+    typedef SwCfg<KX> CX;
+    typedef SwCfg<KY> CY;
+    constexpr int BOXW = CX::BOXW, BOXH = CY::BOXH, TH2 = CY::TH, RW = CY::RW;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* in_s = reinterpret_cast<float*>(smem_raw);                  // [BOXH][BOXW]
+    __shared__ __align__(8) uint64_t bar;
+    const int tiles_x = (q.W + SW_TW - 1) / SW_TW;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x, b = blockIdx.y;
+    const int x0 = tx * SW_TW, y0 = ty * TH2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool do_blur = q.gates ? q.gates[b * 2] != 0 : true;
+    const bool do_noise = q.noise && (q.gates ? q.gates[b * 2 + 1] != 0 : true);
+
+    if (!do_blur) {      // gate off: copy (PostProcessor copies once) [+ noise]
+        for (int i = tid; i < (SW_TW / 4) * TH2; i += THREADS) {
+            const int y = y0 + i / (SW_TW / 4), x = x0 + (i % (SW_TW / 4)) * 4;
+            if (y >= q.H || x >= q.W) continue;
+            float v[4];
+            const float4 a = __ldg(reinterpret_cast<const float4*>(q.img + ((size_t)b * q.H + y) * q.W + x));   // W % 4 == 0 on this path
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            if (do_noise) noise_clip4(q, b, y, x, v);
+            store4(q, b, y, x, v);
+        }
+        return;
+    }
+
+    // ---- stage input tile + halo (one TMA load), patch the reflect border on edge tiles ----
+    const int gx0 = x0 - CX::PADL, gy0 = y0 - CY::H;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, (uint32_t)(BOXW * BOXH * sizeof(float)));
+        tma_load_3d(in_s, &tmap, &bar, gx0, gy0, b);
+    }
+    mbar_wait(&bar, 0);
+    if (gx0 < 0 || gy0 < 0 || gx0 + BOXW > q.W || gy0 + BOXH > q.H) {
+        for (int i = tid; i < BOXW * BOXH; i += THREADS) {
+            const int ly = i / BOXW, lx = i - ly * BOXW;
+            const int gy = gy0 + ly, gx = gx0 + lx;
+            if (gy < 0 || gy >= q.H || gx < 0 || gx >= q.W) {
+                // rows / columns beyond the far image edge by more than the halo are never used: clamp keeps the index in the box
+                const int sy = min(max(reflect(gy, q.H) - gy0, 0), BOXH - 1), sx = min(max(reflect(gx, q.W) - gx0, 0), BOXW - 1);
+                const int ry = reflect(gy, q.H), rx = reflect(gx, q.W);
+                const bool ok = ry >= gy0 && ry < gy0 + BOXH && rx >= gx0 && rx < gx0 + BOXW && ry >= 0 && ry < q.H && rx >= 0 && rx < q.W;
+                in_s[i] = ok ? in_s[sy * BOXW + sx] : 0.f;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- per lane: 4 columns, sliding window over the rows of this warp ----
+    float wx[KX], wy[KY];
+#pragma unroll
+    for (int t = 0; t < KX; ++t) wx[t] = q.wx[t];
+#pragma unroll
+    for (int t = 0; t < KY; ++t) wy[t] = q.wy[t];
+    const int x = x0 + 4 * lane;
+    const float* colp = in_s + 4 * lane;                     // first 128-bit word of this lane's window (PADL texels left of its columns)
+    float win[KY][4];
+#pragma unroll
+    for (int rr = 0; rr < RW + KY - 1; ++rr) {
+        const float* rowp = colp + (warp * RW + rr) * BOXW;
+        float v[4 * (1 + 2 * CX::NQ)];
+#pragma unroll
+        for (int w4 = 0; w4 < 1 + 2 * CX::NQ; ++w4) {
+            const float4 a = *reinterpret_cast<const float4*>(rowp + 4 * w4);
+            v[4 * w4] = a.x; v[4 * w4 + 1] = a.y; v[4 * w4 + 2] = a.z; v[4 * w4 + 3] = a.w;
+        }
+        float hsum[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < KX; ++t) acc = fmaf(wx[t], v[CX::PADL - CX::H + j + t], acc);
+            hsum[j] = acc;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) win[rr % KY][j] = hsum[j];
+        if (rr >= KY - 1) {
+            const int y = y0 + warp * RW + rr - (KY - 1);
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < KY; ++t)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = fmaf(wy[t], win[(rr - (KY - 1) + t) % KY][j], o[j]);
+            if (y < q.H && x < q.W) {
+                if (do_noise) noise_clip4(q, b, y, x, o);
+                store4(q, b, y, x, o);
+            }
+        }
+    }
+}
+
+template <int KX, int KY>
+static int launch_blur_sw(const CUtensorMap& tmap, const PostParams& q, cudaStream_t st) {
+    typedef SwCfg<KX> CX;
+    typedef SwCfg<KY> CY;
+    const size_t smem = (size_t)CX::BOXW * CY::BOXH * sizeof(float);
+    const unsigned tiles = (unsigned)(((q.W + SW_TW - 1) / SW_TW) * ((q.H + CY::TH - 1) / CY::TH));
+    if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(blur_sw_kernel<KX, KY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    blur_sw_kernel<KX, KY><<<dim3(tiles, q.B), THREADS, smem, st>>>(tmap, q);
+    FFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // no blur stage configured: pure streaming copy / noise / clip
 __global__ void __launch_bounds__(THREADS) pointwise_kernel(const PostParams q) {
     const size_t quads_per_row = (size_t)(q.W + 3) / 4;
     const size_t total = quads_per_row * q.H * q.B;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int b = (int)(i / (quads_per_row * q.H));
-        const size_t rem = i - (size_t)b * quads_per_row * q.H;
-        const int y = (int)(rem / quads_per_row), x = (int)(rem - (size_t)y * quads_per_row) * 4;
-        const bool do_noise = q.noise && (q.gates ? q.gates[b * 2 + 1] != 0 : true);
-        float v[4];
-        const float* s = q.img + ((size_t)b * q.H + y) * q.W + x;
-        if (x + 4 <= q.W && (q.W & 3) == 0) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(s));
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-        } else {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const bool vec = (q.W & 3) == 0;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+        float v[2][4];
+        int bb[2], yy[2], xx[2];
+        bool live[2];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = x + k < q.W ? __ldg(s + k) : 0.f;
+        for (int u = 0; u < 2; ++u) {                       // both loads in flight before any arithmetic
+            const size_t i = i0 + u * stride;
+            live[u] = i < total;
+            const size_t ii = live[u] ? i : 0;
+            bb[u] = (int)(ii / (quads_per_row * q.H));
+            const size_t rem = ii - (size_t)bb[u] * quads_per_row * q.H;
+            yy[u] = (int)(rem / quads_per_row); xx[u] = (int)(rem - (size_t)yy[u] * quads_per_row) * 4;
+            const float* s = q.img + ((size_t)bb[u] * q.H + yy[u]) * q.W + xx[u];
+            if (vec) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(s));
+                v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[u][k] = xx[u] + k < q.W ? __ldg(s + k) : 0.f;
+            }
         }
-        if (do_noise) noise_clip4(q, b, y, x, v);
-        store4(q, b, y, x, v);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!live[u]) continue;
+            const bool do_noise = q.noise && (q.gates ? q.gates[bb[u] * 2 + 1] != 0 : true);
+            if (do_noise) noise_clip4(q, bb[u], yy[u], xx[u], v[u]);
+            store4(q, bb[u], yy[u], xx[u], v[u]);
+        }
     }
 }
 
@@ -303,6 +447,22 @@ extern "C" int ffb_postprocess(const ffb_post_desc* d, const float* img, const u
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) use_tma = false;
+        }
+    }
+    if (use_tma && q.kx == q.ky && (q.kx == 3 || q.kx == 5 || q.kx == 11) && d->W >= 16 && d->H >= 16) {
+        // production path: sliding-window kernel; its TMA box differs from the generic kernel's
+        CUtensorMap tm2;
+        memset(&tm2, 0, sizeof(tm2));
+        const int padl = (q.hx + 3) & ~3, rw = q.kx <= 5 ? 8 : 16;
+        cuuint64_t gdim[3] = {(cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+        cuuint64_t gstr[2] = {(cuuint64_t)d->W * 4, (cuuint64_t)d->W * d->H * 4};
+        cuuint32_t box[3] = {(cuuint32_t)(SW_TW + 2 * padl), (cuuint32_t)(8 * rw + q.ky - 1), 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if (get_encode()(&tm2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(img), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+            if (q.kx == 3) return launch_blur_sw<3, 3>(tm2, q, st);
+            if (q.kx == 5) return launch_blur_sw<5, 5>(tm2, q, st);
+            return launch_blur_sw<11, 11>(tm2, q, st);
         }
     }
     if (use_tma) {
