@@ -648,6 +648,7 @@ static WtConsts wt_consts(const ffb_splat_desc* d, const Plan& p) {
     fc.hs = (float)p.H_s + 0.5f;
     fc.ho = (float)p.H_o + 0.5f;
     fc.c1 = 1.00000011920928955078125f;      // 1 + 2^-23
+    fc.disc2 = (float)((double)d->sigma * sqrt(20.723265836946414));      // (d2 / sigma)^2 = ln(1e9)
     return fc;
 }
 // main kernel over the strip grid, then the overflow kernel over its (normally empty) list

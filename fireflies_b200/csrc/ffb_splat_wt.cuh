@@ -44,6 +44,9 @@ constexpr int WT_WARPS = WT_CTA / 32;
 #ifndef FFB_BWD_SKIP
 #define FFB_BWD_SKIP 0                    // backward: skip 16x4 row groups outside a candidate's row span (measured slower: the branches cost more than the skipped MUFUs)
 #endif
+#ifndef FFB_BWD_DISC
+#define FFB_BWD_DISC 1                    // backward: drop (candidate, tile) pairs whose nearest texel is beyond the radius where g < 1e-9
+#endif
 #ifndef FFB_FWD_MINB
 #define FFB_FWD_MINB 4                    // resident CTAs per SM the register allocation aims for
 #endif
@@ -56,6 +59,7 @@ struct WtConsts {
     float thr_s, thr_o;                   // 4*H + 2 for the sum / soft-OR row masks
     float hs, ho;                         // H + 0.5 for the column predicates
     float c1;                             // 1 + 2^-23: keeps 1 - g away from 0 in the backward quotient
+    float disc2;                          // squared radius beyond which g < 1e-9 (backward tile culling)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -158,6 +162,18 @@ __device__ __forceinline__ WtMasks stage_regs(Stage& s, const EntryRegs& e, int 
         for (int i = 0; i < 4; ++i) {
             ta[i] = clo < WT * i + WT && chi > WT * i;
             if (rlo < 4 * i + 4 && rhi > 4 * i) gm |= 1u << i;
+        }
+        if (ACC && FFB_BWD_DISC) {
+            // backward only: a tile whose nearest texel centre has g < 1e-9 contributes nothing measurable to d/dP (weights
+            // g * d2 * (c - P)); corner tiles of the square window go.  The forward keeps the reference's square footprint.
+            const float ry = fmaxf(fmaxf(r0f - e.a.y, e.a.y - (r0f + (float)(WT - 1))), 0.f);
+            const float ry2 = ry * ry;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float xl = (float)(c0 + WT * i);
+                const float rx = fmaxf(fmaxf(xl - e.a.x, e.a.x - (xl + (float)(WT - 1))), 0.f);
+                ta[i] = ta[i] && fmaf(rx, rx, ry2) <= fc.disc2;
+            }
         }
         s.cand[lane] = make_float4(e.a.x, e.a.z, __uint_as_float(e.b.z), __uint_as_float(gm));
         s.prow[lane] = make_float2(e.a.y, e.a.w);
