@@ -654,12 +654,13 @@ static WtConsts wt_consts(const ffb_splat_desc* d, const Plan& p) {
 // main kernel over the strip grid, then the overflow kernel over its (normally empty) list
 template <typename K, typename KO>
 static int launch_wt(K kernel, KO overflow, const RasterParams& q, const WtConsts& fc, const OvfParams& o, int B, cudaStream_t st,
-                     size_t smem = 0, size_t smem_ovf = 0) {
-    const unsigned gy = (unsigned)((q.tgy + WT_WARPS * WT_S - 1) / (WT_WARPS * WT_S));
+                     int cta = WT_CTA, size_t smem = 0, size_t smem_ovf = 0) {
+    const int warps = cta / 32;
+    const unsigned gy = (unsigned)((q.tgy + warps * WT_S - 1) / (warps * WT_S));
     if (B > 65535 || gy > 65535) return fail_arg(FFB_E_LIMIT, "splat: B or the tile rows exceed the grid limit (65535)");
     if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (smem_ovf > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(overflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ovf));
-    kernel<<<dim3((unsigned)q.tgx, gy, (unsigned)B), WT_CTA, smem, st>>>(q, fc);
+    kernel<<<dim3((unsigned)q.tgx, gy, (unsigned)B), cta, smem, st>>>(q, fc);
     FFB_CUDA(cudaGetLastError());
     overflow<<<kNumSMs, WT_CTA, smem_ovf, st>>>(q, fc, o);
     FFB_CUDA(cudaGetLastError());
@@ -904,8 +905,8 @@ extern "C" int ffb_splat_bwd(const ffb_splat_desc* d, const float* pts, const vo
         const int B = d->B;
         const OvfParams ov = {q.ovf, q.ovf + 1, B};
         q.saved_softor = g_softor ? saved_softor : nullptr;
-#define FFB_BWD1(S, O, T, M, V) launch_wt(splat_bwd_wt<S, O, T, M, V>, splat_bwd_ovf<S, O, T, M, V>, q, fc, ov, B, st, \
-                                          sizeof(WarpStage<M ? 2 : 1, true, true, 1>) * WT_WARPS, sizeof(WarpStage<M ? 2 : 1, true, false, 1>) * WT_WARPS)
+#define FFB_BWD1(S, O, T, M, V) launch_wt(splat_bwd_wt<S, O, T, M, V>, splat_bwd_ovf<S, O, T, M, V>, q, fc, ov, B, st, WB_CTA, \
+                                          sizeof(WarpStage<M ? 2 : 1, true, true, 1>) * WB_WARPS, sizeof(WarpStage<M ? 2 : 1, true, false, 1>) * WT_WARPS)
 #define FFB_BWD2(S, O, T, M) (q.saved_softor ? FFB_BWD1(S, O, T, M, true) : FFB_BWD1(S, O, T, M, false))
 #define FFB_BWD(S, O, T) (p.mask_o ? FFB_BWD2(S, O, T, true) : FFB_BWD2(S, O, T, false))
         if (g_sum && g_softor) return sum_transposed ? FFB_BWD(true, true, true) : FFB_BWD(true, true, false);

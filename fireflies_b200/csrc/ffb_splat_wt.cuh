@@ -36,8 +36,10 @@
 #pragma once
 
 constexpr int WT_S = 4;                   // vertically adjacent super tiles per warp
-constexpr int WT_CTA = 256;               // 8 warps x 4 super tiles (64 x 16 texels each) = 64 x 512 texels
+constexpr int WT_CTA = 256;               // forward / overflow kernels: 8 warps x 4 super tiles (64 x 16 texels each) = 64 x 512 texels
 constexpr int WT_WARPS = WT_CTA / 32;
+constexpr int WB_CTA = 128;               // backward: 4 warps per CTA (measured: finer CTA granularity, 4 % faster; the forward prefers 8)
+constexpr int WB_WARPS = WB_CTA / 32;
 #ifndef FFB_FFS_LOOP
 #define FFB_FFS_LOOP 1                    // 1: walk a tile's candidate mask with ffs (two XU-pipe ops per candidate); 0: test bit k of the mask for k < n
 #endif
@@ -51,7 +53,7 @@ constexpr int WT_WARPS = WT_CTA / 32;
 #define FFB_FWD_MINB 4                    // resident CTAs per SM the register allocation aims for
 #endif
 #ifndef FFB_BWD_MINB
-#define FFB_BWD_MINB 3
+#define FFB_BWD_MINB 6
 #endif
 
 struct WtConsts {
@@ -378,11 +380,12 @@ __device__ __forceinline__ void store_tile(const RasterParams& q, const WtCoord&
 struct Strip {
     int b, bin, c0, sty0, nst, lane, tv;
 };
+template <int WARPS>
 __device__ __forceinline__ bool strip_init(Strip& s, const RasterParams& q) {
     s.b = blockIdx.z;
     s.bin = q.shared_pattern ? 0 : s.b;
     s.lane = threadIdx.x & 31;
-    s.sty0 = (blockIdx.y * WT_WARPS + (threadIdx.x >> 5)) * WT_S;
+    s.sty0 = (blockIdx.y * WARPS + (threadIdx.x >> 5)) * WT_S;
     if (s.sty0 >= q.tgy) return false;
     s.nst = min(WT_S, q.tgy - s.sty0);
     s.c0 = blockIdx.x * (4 * WT);
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(WT_CTA, FFB_FWD_MINB) splat_fwd_wt(RasterParam
     typedef WarpStage<MASK_O ? 2 : 0> Stage;
     __shared__ Stage stage[WT_WARPS];
     Strip sp;
-    if (!strip_init(sp, q)) return;                        // whole warp; no block-level barriers below
+    if (!strip_init<WT_WARPS>(sp, q)) return;              // whole warp; no block-level barriers below
     Stage& st = stage[threadIdx.x >> 5];
     const Entry* entries = q.entries + (size_t)sp.bin * q.cap;
     WtCoord w;
@@ -569,11 +572,11 @@ __device__ __forceinline__ void stage_tile_async(float (&buf)[WT][24], const flo
 }
 
 template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O, bool SAVED>
-__global__ void __launch_bounds__(WT_CTA, FFB_BWD_MINB) splat_bwd_wt(RasterParams q, WtConsts fc) {
+__global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_wt(RasterParams q, WtConsts fc) {
     typedef WarpStage<MASK_O ? 2 : 1, true, true, 1> Stage;
     extern __shared__ __align__(16) unsigned char wt_smem[];
     Strip sp;
-    if (!strip_init(sp, q)) return;
+    if (!strip_init<WB_WARPS>(sp, q)) return;
     Stage& st = reinterpret_cast<Stage*>(wt_smem)[threadIdx.x >> 5];
     const Entry* entries = q.entries + (size_t)sp.bin * q.cap;
     WtCoord w;
