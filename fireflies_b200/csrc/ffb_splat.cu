@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include "ffb_common.cuh"
+#include "ffb_tma.cuh"
 
 namespace ffb {
 namespace splat {
@@ -649,6 +650,9 @@ static WtConsts wt_consts(const ffb_splat_desc* d, const Plan& p) {
     fc.ho = (float)p.H_o + 0.5f;
     fc.c1 = 1.00000011920928955078125f;      // 1 + 2^-23
     fc.disc2 = (float)((double)d->sigma * sqrt(20.723265836946414));      // (d2 / sigma)^2 = ln(1e9)
+    fc.near2 = (float)((double)d->sigma * sqrt(5.545177444479562));       // (d2 / sigma)^2 = ln(2^8)
+    fc.s2 = (float)(sqrt(1.4426950408889634) / (double)d->sigma);
+    fc.rs2 = (float)((double)d->sigma / sqrt(1.4426950408889634));
     return fc;
 }
 // main kernel over the strip grid, then the overflow kernel over its (normally empty) list
@@ -661,6 +665,25 @@ static int launch_wt(K kernel, KO overflow, const RasterParams& q, const WtConst
     if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (smem_ovf > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(overflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ovf));
     kernel<<<dim3((unsigned)q.tgx, gy, (unsigned)B), cta, smem, st>>>(q, fc);
+    FFB_CUDA(cudaGetLastError());
+    overflow<<<kNumSMs, WT_CTA, smem_ovf, st>>>(q, fc, o);
+    FFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// TMA-fed backward over the same strip grid (tensor maps of the upstream arrays as kernel parameters)
+struct BwdMaps {
+    CUtensorMap gs, go, sv;
+};
+template <typename K, typename KO>
+static int launch_bwd_tma(K kernel, KO overflow, const RasterParams& q, const WtConsts& fc, const OvfParams& o, int B, cudaStream_t st,
+                          const BwdMaps& m, size_t stage_bytes, size_t smem_ovf) {
+    const unsigned gy = (unsigned)((q.tgy + WB_WARPS * WT_S - 1) / (WB_WARPS * WT_S));
+    if (B > 65535 || gy > 65535) return fail_arg(FFB_E_LIMIT, "splat: B or the tile rows exceed the grid limit (65535)");
+    const size_t smem = (size_t)WB_WARPS * 3 * TMA_TILE_BYTES + 64 + stage_bytes * WB_WARPS;
+    if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem_ovf > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(overflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ovf));
+    kernel<<<dim3((unsigned)q.tgx, gy, (unsigned)B), WB_CTA, smem, st>>>(q, fc, m.gs, m.go, m.sv);
     FFB_CUDA(cudaGetLastError());
     overflow<<<kNumSMs, WT_CTA, smem_ovf, st>>>(q, fc, o);
     FFB_CUDA(cudaGetLastError());
@@ -905,6 +928,33 @@ extern "C" int ffb_splat_bwd(const ffb_splat_desc* d, const float* pts, const vo
         const int B = d->B;
         const OvfParams ov = {q.ovf, q.ovf + 1, B};
         q.saved_softor = g_softor ? saved_softor : nullptr;
+        {
+            // production path: upstream tiles through TMA (needs 16-byte aligned bases and row pitches)
+            const char* e = getenv("FFB_SPLAT_NO_TMA");
+            BwdMaps m;
+            bool ok = !(e && e[0] == '1');
+            const uint64_t t0 = (uint64_t)d->ts0, t1 = (uint64_t)d->ts1;
+            if (ok && g_softor) ok = tma::encode_f32_3d(&m.go, g_softor, t0, t1, (uint64_t)B, WT, WT, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (ok && q.saved_softor) ok = tma::encode_f32_3d(&m.sv, q.saved_softor, t0, t1, (uint64_t)B, WT, WT, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (ok && g_sum)
+                ok = sum_transposed ? tma::encode_f32_3d(&m.gs, g_sum, t1, t0, (uint64_t)B, WT, WT, CU_TENSOR_MAP_SWIZZLE_64B)
+                                    : tma::encode_f32_3d(&m.gs, g_sum, t0, t1, (uint64_t)B, WT, WT, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (ok) {
+                if (!g_softor) m.go = m.gs;                 // unused maps still have to be valid kernel parameters
+                if (!q.saved_softor) m.sv = g_softor ? m.go : m.gs;
+                if (!g_sum) m.gs = m.go;
+#define FFB_TMA1(S, O, T, M, V) launch_bwd_tma(splat_bwd_tma<S, O, T, M, V>, splat_bwd_ovf<S, O, T, M, V>, q, fc, ov, B, st, m, \
+                                               sizeof(WarpStage<M ? 2 : 1, true, false, 1>), sizeof(WarpStage<M ? 2 : 1, true, false, 1>) * WT_WARPS)
+#define FFB_TMA2(S, O, T, M) (q.saved_softor ? FFB_TMA1(S, O, T, M, true) : FFB_TMA1(S, O, T, M, false))
+#define FFB_TMA(S, O, T) (p.mask_o ? FFB_TMA2(S, O, T, true) : FFB_TMA2(S, O, T, false))
+                if (g_sum && g_softor) return sum_transposed ? FFB_TMA(true, true, true) : FFB_TMA(true, true, false);
+                if (g_sum) return sum_transposed ? FFB_TMA1(true, false, true, false, false) : FFB_TMA1(true, false, false, false, false);
+                return FFB_TMA(false, true, false);
+#undef FFB_TMA
+#undef FFB_TMA2
+#undef FFB_TMA1
+            }
+        }
 #define FFB_BWD1(S, O, T, M, V) launch_wt(splat_bwd_wt<S, O, T, M, V>, splat_bwd_ovf<S, O, T, M, V>, q, fc, ov, B, st, WB_CTA, \
                                           sizeof(WarpStage<M ? 2 : 1, true, true, 1>) * WB_WARPS, sizeof(WarpStage<M ? 2 : 1, true, false, 1>) * WT_WARPS)
 #define FFB_BWD2(S, O, T, M) (q.saved_softor ? FFB_BWD1(S, O, T, M, true) : FFB_BWD1(S, O, T, M, false))

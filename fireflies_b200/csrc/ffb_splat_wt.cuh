@@ -49,6 +49,9 @@ constexpr int WB_WARPS = WB_CTA / 32;
 #ifndef FFB_BWD_DISC
 #define FFB_BWD_DISC 1                    // backward: drop (candidate, tile) pairs whose nearest texel is beyond the radius where g < 1e-9
 #endif
+#ifndef FFB_BWD_FAR
+#define FFB_BWD_FAR 1                     // backward: tiles where every g < 2^-8 take 1/(1-g) = 1 + g + g^2 (+O(g^3) < 6e-8) on the FMA pipe instead of MUFU.RCP
+#endif
 #ifndef FFB_FWD_MINB
 #define FFB_FWD_MINB 4                    // resident CTAs per SM the register allocation aims for
 #endif
@@ -62,6 +65,8 @@ struct WtConsts {
     float hs, ho;                         // H + 0.5 for the column predicates
     float c1;                             // 1 + 2^-23: keeps 1 - g away from 0 in the backward quotient
     float disc2;                          // squared radius beyond which g < 1e-9 (backward tile culling)
+    float near2;                          // squared radius beyond which g < 2^-8 (backward: far tiles need no reciprocal)
+    float s2, rs2;                        // sqrt(-K2) and its reciprocal: the backward's tables hold d^2 * s2, so g = 2^-(d2s^2)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -97,10 +102,14 @@ struct WarpStage {
 
 // Which staged candidates touch which 16x16 tile: warp-uniform ballots, 16 bits per tile.
 struct WtMasks {
-    unsigned tb01, tb23;
+    unsigned tb01, tb23;                  // touched (and, in the backward, inside the 1e-9 disc)
+    unsigned nb01, nb23;                  // backward: near tiles (some g >= 2^-8)
 };
 __device__ __forceinline__ unsigned tile_mask(const WtMasks& mk, int j) {
     return (((j & 2) ? mk.tb23 : mk.tb01) >> (16 * (j & 1))) & 0xffffu;
+}
+__device__ __forceinline__ unsigned near_mask(const WtMasks& mk, int j) {
+    return (((j & 2) ? mk.nb23 : mk.nb01) >> (16 * (j & 1))) & 0xffffu;
 }
 
 // a lane's candidate record, as loaded (lane k holds candidate k of the chunk)
@@ -156,6 +165,7 @@ __device__ __forceinline__ WtMasks stage_regs(Stage& s, const EntryRegs& e, int 
     constexpr bool ACC = StageTraits<Stage>::acc;
     __syncwarp();                         // previous chunk fully consumed
     bool ta[4] = {false, false, false, false};
+    bool na[4] = {false, false, false, false};
     if (lane < n) {
         const int clo = (int)(e.b.y & 0xffff) - c0, chi = (int)(e.b.y >> 16) - c0;  // spans relative to the super tile
         const int r0 = (int)r0f, rlo = (int)(e.b.x & 0xffff) - r0, rhi = (int)(e.b.x >> 16) - r0;
@@ -174,7 +184,9 @@ __device__ __forceinline__ WtMasks stage_regs(Stage& s, const EntryRegs& e, int 
             for (int i = 0; i < 4; ++i) {
                 const float xl = (float)(c0 + WT * i);
                 const float rx = fmaxf(fmaxf(xl - e.a.x, e.a.x - (xl + (float)(WT - 1))), 0.f);
-                ta[i] = ta[i] && fmaf(rx, rx, ry2) <= fc.disc2;
+                const float rr = fmaf(rx, rx, ry2);
+                ta[i] = ta[i] && rr <= fc.disc2;
+                na[i] = ta[i] && (!FFB_BWD_FAR || rr < fc.near2);
             }
         }
         s.cand[lane] = make_float4(e.a.x, e.a.z, __uint_as_float(e.b.z), __uint_as_float(gm));
@@ -186,6 +198,11 @@ __device__ __forceinline__ WtMasks stage_regs(Stage& s, const EntryRegs& e, int 
     WtMasks m;
     m.tb01 = __ballot_sync(0xffffffffu, ta[0]) | (__ballot_sync(0xffffffffu, ta[1]) << 16);
     m.tb23 = __ballot_sync(0xffffffffu, ta[2]) | (__ballot_sync(0xffffffffu, ta[3]) << 16);
+    m.nb01 = m.tb01; m.nb23 = m.tb23;
+    if (ACC && FFB_BWD_DISC && FFB_BWD_FAR) {
+        m.nb01 = __ballot_sync(0xffffffffu, na[0]) | (__ballot_sync(0xffffffffu, na[1]) << 16);
+        m.nb23 = __ballot_sync(0xffffffffu, na[2]) | (__ballot_sync(0xffffffffu, na[3]) << 16);
+    }
     __syncwarp();
     const float rp = r0f + (float)(2 * (lane & 7));
     for (int t = lane; t < n * (WT / 2); t += 32) {
@@ -194,7 +211,9 @@ __device__ __forceinline__ WtMasks stage_regs(Stage& s, const EntryRegs& e, int 
         const float ra = rp, rb = rp + 1.f;
         const float da = ra - pf.x, db = rb - pf.x;
         const float ea = ra - pf.y, eb = rb - pf.y;
-        s.tabA[k][p] = make_float4(__fmul_rn(da, da), __fmul_rn(db, db), cheb_mask(ea, fc.thr_s), cheb_mask(eb, fc.thr_s));
+        // backward (ACC): squared distances pre-scaled by s2 = sqrt(-K2), so that g = 2^-(d2s * d2s) needs no multiply by K2
+        const float sc = ACC ? fc.s2 : 1.f;
+        s.tabA[k][p] = make_float4(__fmul_rn(da, da) * sc, __fmul_rn(db, db) * sc, cheb_mask(ea, fc.thr_s), cheb_mask(eb, fc.thr_s));
         if (TABB == 2) s.tabB4[k][p] = make_float4(da, db, cheb_mask(ea, fc.thr_o), cheb_mask(eb, fc.thr_o));
         if (TABB == 1) s.tabB2[k][p] = make_float2(da, db);
     }
@@ -321,6 +340,7 @@ __device__ __forceinline__ void prod_group(float2& acc_p, float2 g, bool pco, fl
 template <bool SUM, bool SOFTOR, bool MASK_O, typename Stage>
 __device__ __forceinline__ void accumulate_tile(const Stage& st, unsigned tm, int n, float cf, int h, const WtConsts& fc,
                                                 float2 (&acc_s)[4], float2 (&acc_p)[4]) {
+    constexpr bool SCALED = StageTraits<Stage>::acc;                                  // backward stages hold d^2 * s2
 #if FFB_FFS_LOOP
     while (tm) {                                                                      // warp-uniform
         const int k = __ffs(tm) - 1;
@@ -331,7 +351,7 @@ __device__ __forceinline__ void accumulate_tile(const Stage& st, unsigned tm, in
 #endif
         const float2 cd = *reinterpret_cast<const float2*>(&st.cand[k]);
         const float dx = cf - cd.x;
-        const float dx2 = __fmul_rn(dx, dx);
+        const float dx2 = SCALED ? __fmul_rn(dx, dx) * fc.s2 : __fmul_rn(dx, dx);
         const float ec = fabsf(cf - cd.y);
         const bool pcs = ec <= fc.hs, pco = ec <= fc.ho;
         const float4* tA = &st.tabA[k][h];
@@ -339,7 +359,7 @@ __device__ __forceinline__ void accumulate_tile(const Stage& st, unsigned tm, in
         for (int i = 0; i < 4; ++i) {
             const float4 A = tA[2 * i];
             const float2 d2 = __fadd2_rn(bc(dx2), make_float2(A.x, A.y));            // dc*dc + dr*dr, as the reference
-            const float2 t = __fmul2_rn(__fmul2_rn(d2, d2), bc(fc.K2));
+            const float2 t = SCALED ? __fmul2_rn(neg2(d2), d2) : __fmul2_rn(__fmul2_rn(d2, d2), bc(fc.K2));
             const float2 g = make_float2(ex2_approx(t.x), ex2_approx(t.y));
             if (SUM) { if (pcs) acc_s[i] = __ffma2_rn(g, make_float2(A.z, A.w), acc_s[i]); }
             if (SOFTOR) {
@@ -441,7 +461,8 @@ __global__ void __launch_bounds__(WT_CTA, FFB_FWD_MINB) splat_fwd_wt(RasterParam
 // quotient; the texel's weight g*d2*(c - P) vanishes there, and the bias is <= 1.2e-7 relative elsewhere.
 // Each (candidate, tile) partial is folded once across the half warps (lanes 0-15 then hold d/dp0 parts, lanes 16-31
 // d/dp1 parts) and parked in shared memory; flush_warp sums a candidate's 16 parts in one lane, all candidates at once.
-template <bool SUM, bool SOFTOR, bool MASK_O, typename Stage>
+// FARV: every g of the tile is below 2^-8: gO * prod * g / (1 - g) = gp * (g + g^2 + g^3) to 6e-8 relative, no reciprocal.
+template <bool SUM, bool SOFTOR, bool MASK_O, bool FARV, typename Stage>
 __device__ __forceinline__ void weigh_tile(Stage& st, unsigned tm, int n, float cf, int h, int lane, const WtConsts& fc,
                                            const float2 (&gs)[4], const float2 (&gp)[4]) {
 #if FFB_FFS_LOOP
@@ -460,7 +481,7 @@ __device__ __forceinline__ void weigh_tile(Stage& st, unsigned tm, int n, float 
         const unsigned gm = 15u;
 #endif
         const float dx = cf - cd.x;
-        const float dx2 = __fmul_rn(dx, dx);
+        const float dx2 = __fmul_rn(dx, dx) * fc.s2;
         const float ec = fabsf(cf - cd.y);
         const bool pcs = ec <= fc.hs, pco = ec <= fc.ho;
         const float4* tA = &st.tabA[k][h];
@@ -472,9 +493,18 @@ __device__ __forceinline__ void weigh_tile(Stage& st, unsigned tm, int n, float 
             float4 Bq;
             if (MASK_O) Bq = st.tabB4[k][2 * i + h];
             else { const float2 dy = st.tabB2[k][2 * i + h]; Bq = make_float4(dy.x, dy.y, 1.f, 1.f); }
-            const float2 d2 = __fadd2_rn(bc(dx2), make_float2(A.x, A.y));
-            const float2 t = __fmul2_rn(__fmul2_rn(d2, d2), bc(fc.K2));
+            const float2 d2 = __fadd2_rn(bc(dx2), make_float2(A.x, A.y));            // d^2 * s2
+            const float2 t = __fmul2_rn(neg2(d2), d2);
             const float2 g = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+            if (FARV && !MASK_O) {
+                float2 x = bc(0.f);
+                if (SOFTOR) x = __fmul2_rn(gp[i], __ffma2_rn(g, __ffma2_rn(g, g, g), g));
+                if (SUM) { if (pcs) x = __ffma2_rn(__fmul2_rn(gs[i], make_float2(A.z, A.w)), g, x); }
+                const float2 wgt = __fmul2_rn(x, d2);
+                a0 = __ffma2_rn(wgt, bc(dx), a0);
+                a1 = __ffma2_rn(wgt, make_float2(Bq.x, Bq.y), a1);
+                continue;
+            }
             float2 coef = bc(0.f);
             if (SOFTOR) {
                 if (MASK_O) {
@@ -582,7 +612,7 @@ __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_wt(RasterParam
     WtCoord w;
     w.b = sp.b; w.c0 = sp.c0; w.lc = sp.lane & 15; w.h = sp.lane >> 4;
     const float inv_s2 = q.rcp_sigma * q.rcp_sigma;
-    const float kh = 4.f * (w.h ? (float)q.ts1 : (float)q.ts0) * inv_s2;     // lanes 0-15 report d/dp0, lanes 16-31 d/dp1
+    const float kh = 4.f * (w.h ? (float)q.ts1 : (float)q.ts0) * inv_s2 * fc.rs2;     // lanes 0-15 report d/dp0, lanes 16-31 d/dp1; rs2 undoes the table scaling
     float* dp = q.d_pts + (size_t)sp.b * q.N * 2 + w.h;
     int n = __shfl_sync(0xffffffffu, sp.tv, 1) - __shfl_sync(0xffffffffu, sp.tv, 0);
     prefetch_entries(st.raw[0], entries + __shfl_sync(0xffffffffu, sp.tv, 0), n <= WCH ? n : 0, sp.lane);
@@ -659,7 +689,127 @@ __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_wt(RasterParam
 #pragma unroll
                     for (int i = 0; i < 4; ++i) gp[i] = __fmul2_rn(gp[i], prod[i]);
                 }
-                weigh_tile<SUM, SOFTOR, MASK_O>(st, tm, n, cf, w.h, sp.lane, fc, gs, gp);
+                const unsigned nm = near_mask(mk, j);
+                weigh_tile<SUM, SOFTOR, MASK_O, false>(st, (MASK_O || !FFB_BWD_FAR) ? tm : nm, n, cf, w.h, sp.lane, fc, gs, gp);
+                if (!MASK_O && FFB_BWD_FAR) weigh_tile<SUM, SOFTOR, MASK_O, true>(st, tm & ~nm, n, cf, w.h, sp.lane, fc, gs, gp);
+            }
+            flush_warp(st, n, w.h, w.lc, kh, dp);
+            have = next_live;
+        } else {
+            have = false;
+        }
+        n = nn;
+    }
+}
+
+// TMA-fed backward.  The ncu source view of splat_bwd_wt showed ~200 instructions of per-tile overhead around ~290 of
+// splat arithmetic: at an 80-register budget the compiler re-derives block / lane coordinates and the 64-bit addresses
+// of three arrays for every 16x16 tile.  Here the address generation belongs to the TMA unit: lane 0 issues one
+// cp.async.bulk.tensor box {16, 16, 1} per upstream array and tile (coordinates (column, row, sample); texels beyond
+// the texture arrive as zeros, so there is no edge path), completion is an mbarrier transaction count, and every lane
+// reads its 8 texels per array from fixed shared-memory offsets.  The transposed sum gradient ([ts0, ts1]) uses the
+// 64-byte swizzle so that a lane's (column, row pair) reads are conflict free; no shuffles are needed any more.
+// One 3 KB buffer set per warp: a tile's values move to registers first, then the next tile's boxes are requested and
+// land while this tile is computed.
+constexpr int TMA_TILE_BYTES = WT * WT * 4;
+template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O, bool SAVED>
+__global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_tma(RasterParams q, WtConsts fc, const __grid_constant__ CUtensorMap tm_gs,
+                                                                      const __grid_constant__ CUtensorMap tm_go,
+                                                                      const __grid_constant__ CUtensorMap tm_sv) {
+    typedef WarpStage<MASK_O ? 2 : 1, true, false, 1> Stage;
+    extern __shared__ __align__(1024) unsigned char wt_smem_tma[];
+    Strip sp;
+    if (!strip_init<WB_WARPS>(sp, q)) return;
+    const int wid = threadIdx.x >> 5;
+    unsigned char* tin = wt_smem_tma + wid * (3 * TMA_TILE_BYTES);               // [go | saved | gs], 1 KB each, 1 KB aligned
+    uint64_t* bar = reinterpret_cast<uint64_t*>(wt_smem_tma + WB_WARPS * 3 * TMA_TILE_BYTES) + wid;
+    Stage& st = reinterpret_cast<Stage*>(wt_smem_tma + WB_WARPS * 3 * TMA_TILE_BYTES + 64)[wid];
+    const Entry* entries = q.entries + (size_t)sp.bin * q.cap;
+    WtCoord w;
+    w.b = sp.b; w.c0 = sp.c0; w.lc = sp.lane & 15; w.h = sp.lane >> 4;
+    const float inv_s2 = q.rcp_sigma * q.rcp_sigma;
+    const float kh = 4.f * (w.h ? (float)q.ts1 : (float)q.ts0) * inv_s2 * fc.rs2;
+    float* dp = q.d_pts + (size_t)sp.b * q.N * 2 + w.h;
+    if (sp.lane == 0) {
+        tma::mbar_init(bar, 1);
+        tma::fence_mbar_init();
+    }
+    __syncwarp();
+    int n = __shfl_sync(0xffffffffu, sp.tv, 1) - __shfl_sync(0xffffffffu, sp.tv, 0);
+    prefetch_entries(st.raw[0], entries + __shfl_sync(0xffffffffu, sp.tv, 0), n <= WCH ? n : 0, sp.lane);
+    unsigned phase = 0;
+    bool have = false;                                      // tile 0 of the current super tile is already in flight
+    constexpr unsigned kBytes = (unsigned)TMA_TILE_BYTES * ((SOFTOR ? (SAVED ? 2 : 1) : 0) + (SUM ? 1 : 0));
+    // natural tiles: texel (row 4i + 2h + j, column lc) at float (4i + j) * 16 + nat_off
+    const float* nat = reinterpret_cast<const float*>(tin) + (2 * w.h) * WT + w.lc;
+    // transposed tile (64-byte swizzle: 16-byte chunk index ^= (column >> 1) & 3): rows 4i + 2h + {0, 1} of column lc
+    const unsigned tr_base = (unsigned)(2 * TMA_TILE_BYTES + w.lc * 64 + 8 * w.h), tr_x = (unsigned)((w.lc >> 1) & 3) << 4;
+
+    auto issue = [&](int r0, int j) {
+        if (sp.lane == 0) {
+            const int ct = w.c0 + WT * j;
+            tma::mbar_expect_tx(bar, kBytes);
+            if (SOFTOR) {
+                tma::load_3d(tin, &tm_go, bar, ct, r0, w.b);
+                if (SAVED) tma::load_3d(tin + TMA_TILE_BYTES, &tm_sv, bar, ct, r0, w.b);
+            }
+            if (SUM) {
+                if (SUM_T) tma::load_3d(tin + 2 * TMA_TILE_BYTES, &tm_gs, bar, r0, ct, w.b);
+                else tma::load_3d(tin + 2 * TMA_TILE_BYTES, &tm_gs, bar, ct, r0, w.b);
+            }
+        }
+    };
+
+    for (int s = 0; s < sp.nst; ++s) {
+        const EntryRegs e = take_entry(st.raw[0], n <= WCH ? n : 0, sp.lane);
+        __syncwarp();                                       // every lane holds its record: the buffer may be refilled
+        int nn = 0;
+        if (s + 1 < sp.nst) {
+            const int nb = __shfl_sync(0xffffffffu, sp.tv, 2 * s + 2);
+            nn = __shfl_sync(0xffffffffu, sp.tv, 2 * s + 3) - nb;
+            prefetch_entries(st.raw[0], entries + nb, nn <= WCH ? nn : 0, sp.lane);
+        }
+        const bool next_live = nn > 0 && nn <= WCH;
+        if (n > 0 && n <= WCH) {                           // empty: nothing to do; larger lists: overflow kernel
+            w.r0 = (sp.sty0 + s) * WT;
+            if (!have) issue(w.r0, 0);
+            const WtMasks mk = stage_regs(st, e, n, w.c0, (float)w.r0, fc, sp.lane);
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                float2 gs[4], gp[4];
+                tma::mbar_wait(bar, phase);
+                phase ^= 1u;
+                if (SOFTOR) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        gp[i] = make_float2(nat[(4 * i) * WT], nat[(4 * i + 1) * WT]);
+                        if (SAVED) gp[i] = __fmul2_rn(gp[i], make_float2(1.f - nat[WT * WT + (4 * i) * WT], 1.f - nat[WT * WT + (4 * i + 1) * WT]));
+                    }
+                }
+                if (SUM) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (SUM_T) gs[i] = *reinterpret_cast<const float2*>(tin + (tr_base + (tr_x ^ (unsigned)(i << 4))));
+                        else gs[i] = make_float2(nat[2 * WT * WT + (4 * i) * WT], nat[2 * WT * WT + (4 * i + 1) * WT]);
+                    }
+                }
+                __syncwarp();                               // buffers consumed: the next tile may land
+                // next tile (of this super tile, or tile 0 of the next one) in flight while this one is computed
+                if (j < 3) issue(w.r0, j + 1);
+                else if (next_live) issue(w.r0 + WT, 0);
+                const unsigned tm = tile_mask(mk, j);
+                const float cf = (float)(w.c0 + WT * j + w.lc);
+                if (SOFTOR && !SAVED) {                    // pass 1 (only without the saved output): per-texel product of (1 - g)
+                    float2 prod[4], unused[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) prod[i] = bc(1.f);
+                    accumulate_tile<false, true, MASK_O>(st, tm, n, cf, w.h, fc, unused, prod);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) gp[i] = __fmul2_rn(gp[i], prod[i]);
+                }
+                const unsigned nm = near_mask(mk, j);
+                weigh_tile<SUM, SOFTOR, MASK_O, false>(st, (MASK_O || !FFB_BWD_FAR) ? tm : nm, n, cf, w.h, sp.lane, fc, gs, gp);
+                if (!MASK_O && FFB_BWD_FAR) weigh_tile<SUM, SOFTOR, MASK_O, true>(st, tm & ~nm, n, cf, w.h, sp.lane, fc, gs, gp);
             }
             flush_warp(st, n, w.h, w.lc, kh, dp);
             have = next_live;
@@ -741,7 +891,7 @@ __global__ void __launch_bounds__(WT_CTA) splat_bwd_ovf(RasterParams q, WtConsts
         const int beg = __ldg(toff), end = __ldg(toff + 1);
         const Entry* entries = q.entries + (size_t)bin * q.cap;
         const TilePtr tp = tile_ptr(q, w);
-        const float kh = 4.f * (w.h ? (float)q.ts1 : (float)q.ts0) * inv_s2;
+        const float kh = 4.f * (w.h ? (float)q.ts1 : (float)q.ts0) * inv_s2 * fc.rs2;
         float* dp = q.d_pts + (size_t)w.b * q.N * 2 + w.h;
         for (int j = 0; j < 4; ++j) {
             const int ct = w.c0 + WT * j;
@@ -766,7 +916,7 @@ __global__ void __launch_bounds__(WT_CTA) splat_bwd_ovf(RasterParams q, WtConsts
             for (int base = beg; base < end; base += WCH) {
                 const int n = min(WCH, end - base);
                 const WtMasks mk = stage_regs(st, load_entry(entries, base, n, lane), n, w.c0, (float)w.r0, fc, lane);
-                weigh_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mk, j), n, cf, w.h, lane, fc, gs, gp);
+                weigh_tile<SUM, SOFTOR, MASK_O, false>(st, tile_mask(mk, j), n, cf, w.h, lane, fc, gs, gp);
                 flush_warp(st, n, w.h, w.lc, kh, dp);
             }
         }

@@ -24,6 +24,13 @@ tf = t(lambda: plan.forward(ptsB, True, True, True))
 S_, O_ = plan.forward(ptsB, True, True, True)
 tb = t(lambda: plan.backward(ptsB, gS, gO, True, O_))
 tb2 = t(lambda: plan.backward(ptsB, gS, gO, True))
+import os
+os.environ["FFB_SPLAT_NO_TMA"] = "1"
+tb3 = t(lambda: plan.backward(ptsB, gS, gO, True, O_))
+d_old = plan.backward(ptsB, gS, gO, True, O_)
+os.environ["FFB_SPLAT_NO_TMA"] = "0"
+d_new = plan.backward(ptsB, gS, gO, True, O_)
+print(f"bwd (saved) without TMA: {tb3:.3f} ms; max |tma - plain| = {float((d_new - d_old).abs().max()):.3e} of {float(d_old.abs().max()):.3e}")
 print(f"bwd without saved softor: {tb2:.3f} ms")
 hw = ts[0] * ts[1]
 print(f"B={B} prepare {tp:.3f} ms  fwd {tf:.3f} ms ({B*8*hw/tf/1e6:.0f} GB/s)  bwd {tb:.3f} ms ({B*8*hw/tb/1e6:.0f} GB/s)"
