@@ -671,6 +671,21 @@ static int launch_wt(K kernel, KO overflow, const RasterParams& q, const WtConst
     return 0;
 }
 
+// TMA-store forward over the strip grid (tensor maps of the outputs as kernel parameters)
+template <typename K, typename KO>
+static int launch_fwd_tma(K kernel, KO overflow, const RasterParams& q, const WtConsts& fc, const OvfParams& o, int B, cudaStream_t st,
+                          const CUtensorMap& ms, const CUtensorMap& mo, size_t stage_bytes) {
+    const unsigned gy = (unsigned)((q.tgy + WT_WARPS * WT_S - 1) / (WT_WARPS * WT_S));
+    if (B > 65535 || gy > 65535) return fail_arg(FFB_E_LIMIT, "splat: B or the tile rows exceed the grid limit (65535)");
+    const size_t smem = (size_t)WT_WARPS * (2 * TMA_TILE_BYTES + stage_bytes);
+    if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<dim3((unsigned)q.tgx, gy, (unsigned)B), WT_CTA, smem, st>>>(q, fc, ms, mo);
+    FFB_CUDA(cudaGetLastError());
+    overflow<<<kNumSMs, WT_CTA, 0, st>>>(q, fc, o);
+    FFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // TMA-fed backward over the same strip grid (tensor maps of the upstream arrays as kernel parameters)
 struct BwdMaps {
     CUtensorMap gs, go, sv;
@@ -892,6 +907,28 @@ extern "C" int ffb_splat_fwd(const ffb_splat_desc* d, const float* pts, const vo
         const WtConsts fc = wt_consts(d, p);
         const int B = d->B;
         const OvfParams ov = {q.ovf, q.ovf + 1, B};
+        {
+            // production path: finished tiles leave through TMA stores (needs 16-byte aligned bases and row pitches)
+            const char* e = getenv("FFB_SPLAT_NO_TMA");
+            CUtensorMap ms, mo;
+            bool ok = !(e && e[0] == '1');
+            const uint64_t t0 = (uint64_t)d->ts0, t1 = (uint64_t)d->ts1;
+            if (ok && out_softor) ok = tma::encode_f32_3d(&mo, out_softor, t0, t1, (uint64_t)B, WT, WT, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (ok && out_sum)
+                ok = sum_transposed ? tma::encode_f32_3d(&ms, out_sum, t1, t0, (uint64_t)B, WT, WT, CU_TENSOR_MAP_SWIZZLE_64B)
+                                    : tma::encode_f32_3d(&ms, out_sum, t0, t1, (uint64_t)B, WT, WT, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (ok) {
+                if (!out_softor) mo = ms;                   // unused maps still have to be valid kernel parameters
+                if (!out_sum) ms = mo;
+#define FFB_FT1(S, O, T, M) launch_fwd_tma(splat_fwd_tma<S, O, T, M>, splat_fwd_ovf<S, O, T, M>, q, fc, ov, B, st, ms, mo, sizeof(WarpStage<M ? 2 : 0>))
+#define FFB_FT(S, O, T) (p.mask_o ? FFB_FT1(S, O, T, true) : FFB_FT1(S, O, T, false))
+                if (out_sum && out_softor) return sum_transposed ? FFB_FT(true, true, true) : FFB_FT(true, true, false);
+                if (out_sum) return sum_transposed ? FFB_FT1(true, false, true, false) : FFB_FT1(true, false, false, false);
+                return FFB_FT(false, true, false);
+#undef FFB_FT
+#undef FFB_FT1
+            }
+        }
 #define FFB_FWD1(S, O, T, M) launch_wt(splat_fwd_wt<S, O, T, M>, splat_fwd_ovf<S, O, T, M>, q, fc, ov, B, st)
 #define FFB_FWD(S, O, T) (p.mask_o ? FFB_FWD1(S, O, T, true) : FFB_FWD1(S, O, T, false))
         if (out_sum && out_softor) return sum_transposed ? FFB_FWD(true, true, true) : FFB_FWD(true, true, false);

@@ -38,7 +38,10 @@
 constexpr int WT_S = 4;                   // vertically adjacent super tiles per warp
 constexpr int WT_CTA = 256;               // forward / overflow kernels: 8 warps x 4 super tiles (64 x 16 texels each) = 64 x 512 texels
 constexpr int WT_WARPS = WT_CTA / 32;
-constexpr int WB_CTA = 128;               // backward: 4 warps per CTA (measured: finer CTA granularity, 4 % faster; the forward prefers 8)
+#ifndef FFB_WB_CTA
+#define FFB_WB_CTA 128
+#endif
+constexpr int WB_CTA = FFB_WB_CTA;        // backward: 4 warps per CTA (measured: finer CTA granularity, 4 % faster; the forward prefers 8)
 constexpr int WB_WARPS = WB_CTA / 32;
 #ifndef FFB_FFS_LOOP
 #define FFB_FFS_LOOP 1                    // 1: walk a tile's candidate mask with ffs (two XU-pipe ops per candidate); 0: test bit k of the mask for k < n
@@ -56,8 +59,10 @@ constexpr int WB_WARPS = WB_CTA / 32;
 #define FFB_FWD_MINB 4                    // resident CTAs per SM the register allocation aims for
 #endif
 #ifndef FFB_BWD_MINB
-#define FFB_BWD_MINB 6
+#define FFB_BWD_MINB (768 / FFB_WB_CTA)   // 24 warps per SM
 #endif
+
+constexpr int TMA_TILE_BYTES = WT * WT * 4;   // one 16x16 fp32 tile as a TMA box
 
 struct WtConsts {
     float K2;                             // -log2(e) / sigma^2
@@ -455,6 +460,78 @@ __global__ void __launch_bounds__(WT_CTA, FFB_FWD_MINB) splat_fwd_wt(RasterParam
     }
 }
 
+// TMA-store forward.  Same arithmetic as splat_fwd_wt; a finished 16x16 tile is parked in the warp's shared-memory
+// buffers (soft-OR in natural order, the sum either natural or, for the [ts0, ts1] layout, as [column][row] with the
+// 64-byte swizzle so that a lane's row-pair writes are conflict free) and leaves as one cp.async.bulk.tensor store
+// per output: no per-lane addresses, no edge path (the TMA unit clips boxes at the texture border).  In splat_fwd_wt
+// the stores and their address arithmetic were 130 of the ~340 instructions per tile.
+template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O>
+__global__ void __launch_bounds__(WT_CTA, FFB_FWD_MINB) splat_fwd_tma(RasterParams q, WtConsts fc, const __grid_constant__ CUtensorMap tm_s,
+                                                                      const __grid_constant__ CUtensorMap tm_o) {
+    typedef WarpStage<MASK_O ? 2 : 0> Stage;
+    extern __shared__ __align__(1024) unsigned char wt_smem_ftma[];
+    Strip sp;
+    if (!strip_init<WT_WARPS>(sp, q)) return;              // whole warp; no block-level barriers below
+    const int wid = threadIdx.x >> 5;
+    unsigned char* tout = wt_smem_ftma + wid * (2 * TMA_TILE_BYTES);         // [softor | sum], 1 KB each, 1 KB aligned
+    Stage& st = reinterpret_cast<Stage*>(wt_smem_ftma + WT_WARPS * 2 * TMA_TILE_BYTES)[wid];
+    const Entry* entries = q.entries + (size_t)sp.bin * q.cap;
+    WtCoord w;
+    w.b = sp.b; w.c0 = sp.c0; w.lc = sp.lane & 15; w.h = sp.lane >> 4;
+    float* nat = reinterpret_cast<float*>(tout) + (2 * w.h) * WT + w.lc;
+    const unsigned tr_base = (unsigned)(TMA_TILE_BYTES + w.lc * 64 + 8 * w.h), tr_x = (unsigned)((w.lc >> 1) & 3) << 4;
+    int n = __shfl_sync(0xffffffffu, sp.tv, 1) - __shfl_sync(0xffffffffu, sp.tv, 0);
+    prefetch_entries(st.raw[0], entries + __shfl_sync(0xffffffffu, sp.tv, 0), n <= WCH ? n : 0, sp.lane);
+
+    for (int s = 0; s < sp.nst; ++s) {
+        const EntryRegs e = take_entry(st.raw[s & 1], n <= WCH ? n : 0, sp.lane);
+        int nn = 0;
+        if (s + 1 < sp.nst) {
+            const int nb = __shfl_sync(0xffffffffu, sp.tv, 2 * s + 2);
+            nn = __shfl_sync(0xffffffffu, sp.tv, 2 * s + 3) - nb;
+            prefetch_entries(st.raw[(s + 1) & 1], entries + nb, nn <= WCH ? nn : 0, sp.lane);
+        }
+        if (n <= WCH) {                                    // larger lists belong to the overflow kernel
+            w.r0 = (sp.sty0 + s) * WT;
+            const WtMasks mk = stage_regs(st, e, n, w.c0, (float)w.r0, fc, sp.lane);
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                const int ct = w.c0 + WT * j;
+                if (ct >= q.ts0) break;
+                float2 acc_s[4], acc_p[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { acc_s[i] = bc(0.f); acc_p[i] = bc(1.f); }
+                accumulate_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mk, j), n, (float)(ct + w.lc), w.h, fc, acc_s, acc_p);
+                if (sp.lane == 0) tma::store_wait_read<0>();              // the previous tile's boxes have left the buffers
+                __syncwarp();
+                if (SOFTOR) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { nat[(4 * i) * WT] = 1.f - acc_p[i].x; nat[(4 * i + 1) * WT] = 1.f - acc_p[i].y; }
+                }
+                if (SUM) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (SUM_T) *reinterpret_cast<float2*>(tout + (tr_base + (tr_x ^ (unsigned)(i << 4)))) = acc_s[i];
+                        else { nat[WT * WT + (4 * i) * WT] = acc_s[i].x; nat[WT * WT + (4 * i + 1) * WT] = acc_s[i].y; }
+                    }
+                }
+                tma::fence_async_smem();
+                __syncwarp();
+                if (sp.lane == 0) {
+                    if (SOFTOR) tma::store_3d(&tm_o, tout, ct, w.r0, w.b);
+                    if (SUM) {
+                        if (SUM_T) tma::store_3d(&tm_s, tout + TMA_TILE_BYTES, w.r0, ct, w.b);
+                        else tma::store_3d(&tm_s, tout + TMA_TILE_BYTES, ct, w.r0, w.b);
+                    }
+                    tma::store_commit();
+                }
+            }
+        }
+        n = nn;
+    }
+    if (sp.lane == 0) tma::store_wait_read<0>();           // shared memory must outlive the last boxes
+}
+
 // Backward.  dL/dg = gS * m_s + gO * m_o * prod / (1 - g) per (texel, point); dg/dP = 4 g d2 (c - P) / sigma^2.
 // SAVED: the forward's soft-OR output is available, prod = 1 - O; otherwise a first pass rebuilds prod.
 // 1 - g is evaluated as (1 + 2^-23) - g so that a point sitting on a texel centre (g = 1) gives a finite
@@ -711,7 +788,6 @@ __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_wt(RasterParam
 // 64-byte swizzle so that a lane's (column, row pair) reads are conflict free; no shuffles are needed any more.
 // One 3 KB buffer set per warp: a tile's values move to registers first, then the next tile's boxes are requested and
 // land while this tile is computed.
-constexpr int TMA_TILE_BYTES = WT * WT * 4;
 template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O, bool SAVED>
 __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_tma(RasterParams q, WtConsts fc, const __grid_constant__ CUtensorMap tm_gs,
                                                                       const __grid_constant__ CUtensorMap tm_go,

@@ -26,6 +26,9 @@ tb = t(lambda: plan.backward(ptsB, gS, gO, True, O_))
 tb2 = t(lambda: plan.backward(ptsB, gS, gO, True))
 import os
 os.environ["FFB_SPLAT_NO_TMA"] = "1"
+tf3 = t(lambda: plan.forward(ptsB, True, True, True))
+S3, O3 = plan.forward(ptsB, True, True, True)
+print(f"fwd without TMA: {tf3:.3f} ms; tma == plain: sum {bool(torch.equal(S3, S_))} softor {bool(torch.equal(O3, O_))}")
 tb3 = t(lambda: plan.backward(ptsB, gS, gO, True, O_))
 d_old = plan.backward(ptsB, gS, gO, True, O_)
 os.environ["FFB_SPLAT_NO_TMA"] = "0"
