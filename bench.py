@@ -277,12 +277,14 @@ def main_ours(args):
     alg = {"fwd": B * (8 * hw + 8 * N_POINTS), "bwd": B * (8 * hw + 16 * N_POINTS), "randomize": B * 24 * V_MESH}
     dom = max(("fwd", "bwd"), key=lambda p: ph_ms[p])
     traffic = None
+    kname = {"fwd": "splat_fwd_tma", "bwd": "splat_bwd_tma"}[dom]
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.isfile(tpath):
-        traffic = json.load(open(tpath)).get({"fwd": "splat_fwd_wt", "bwd": "splat_bwd_wt"}[dom])
+    if os.path.isfile(tpath):                   # DRAM bytes per sample from the committed ncu --set full capture, scaled to this launch
+        per_sample = json.load(open(tpath)).get("per_sample_bytes", {}).get(kname)
+        traffic = per_sample * B if per_sample else None
     ach = alg[dom] / (ph_ms[dom] * 1e-3) / 1e9
     step_bytes = B * (16 * hw + 16 * N_POINTS + 24 * V_MESH)
-    roofline = {"bound": "hbm", "kernel": f"splat_{dom}_wt", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
                 "whole_step": {"achieved": step_bytes / (ms_step * 1e-3) / 1e9, "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
                                "algorithmic_bytes_per_step": step_bytes},

@@ -15,7 +15,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > "$OUT/ncu_launch_bench.log" 2>&1
 tail -2 "$OUT/ncu_launch_bench.log"
 echo "== ncu full (splat kernels)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:splat_ -s 6 -c 2 -f -o "$OUT/prof_splat" \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:splat_(fwd|bwd)_(tma|wt)" -s 4 -c 2 -f -o "$OUT/prof_splat" \
     python bench.py --batch 64 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > "$OUT/ncu_full_bench.log" 2>&1
 tail -2 "$OUT/ncu_full_bench.log"
 ls -la "$OUT"

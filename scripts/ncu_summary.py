@@ -18,6 +18,8 @@ for r in rows[2:]:
     for w in WANT:
         if w in ix:
             print(f"  {w:70s} {r[ix[w]]:>16s} {units[ix[w]]}")
-    rd, wr, t = float(r[ix["dram__bytes_read.sum"]]), float(r[ix["dram__bytes_write.sum"]]), float(r[ix["gpu__time_duration.sum"]])
-    ur, ut = units[ix["dram__bytes_read.sum"]], units[ix["gpu__time_duration.sum"]]
-    print(f"  traffic (read+write) = {rd + wr:.4f} {ur} per launch, duration {t} {ut} (under ncu: cold cache, serialised)")
+    SC = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    rd = float(r[ix["dram__bytes_read.sum"]]) * SC[units[ix["dram__bytes_read.sum"]]]
+    wr = float(r[ix["dram__bytes_write.sum"]]) * SC[units[ix["dram__bytes_write.sum"]]]
+    t, ut = float(r[ix["gpu__time_duration.sum"]]), units[ix["gpu__time_duration.sum"]]
+    print(f"  traffic (read+write) = {(rd + wr) / 1e9:.4f} Gbyte per launch, duration {t} {ut} (under ncu: cold cache, serialised)")
