@@ -58,6 +58,7 @@ SIGNATURES = {
     "ffb_splat_prepare": (C.c_int, [C.POINTER(SplatDesc), _P, _P, C.c_size_t, _P, _P]),
     "ffb_splat_fwd": (C.c_int, [C.POINTER(SplatDesc), _P, _P, _P, C.c_int, _P, _P]),
     "ffb_splat_bwd": (C.c_int, [C.POINTER(SplatDesc), _P, _P, _P, C.c_int, _P, _P, _P, _P]),
+    "ffb_splat_bwd_l1": (C.c_int, [C.POINTER(SplatDesc), _P, _P, _P, C.c_int, _P, _P, _P, _P]),
     "ffb_reduce_over_samples": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
     "ffb_splat_dense_fwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P]),
     "ffb_splat_dense_bwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P]),
@@ -92,6 +93,9 @@ def lib() -> C.CDLL:
             fn.restype, fn.argtypes = res, args
         _lib = h
     return _lib
+
+
+E_UNSUPPORTED = -4     # FFB_E_UNSUPPORTED: a fused path does not cover this case; the caller uses the unfused calls
 
 
 def check(rc: int, what: str) -> None:

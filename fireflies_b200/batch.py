@@ -235,7 +235,7 @@ class PatternStep:
 
     def __init__(self, n_points: int, texture_size, sigma: float, batch: int, scene_batch: Optional[SceneBatch] = None,
                  num_std_sum: int = 4, num_std_softor: int = 5, sum_transposed: bool = True, per_sample_points: bool = True,
-                 device="cuda", process_group=None):
+                 device="cuda", process_group=None, fuse_loss: bool = True):
         self.N, self.B = int(n_points), int(batch)
         self.ts0, self.ts1 = R._ts(texture_size)
         self.sigma = float(sigma)
@@ -244,6 +244,7 @@ class PatternStep:
         self.per_sample = per_sample_points
         self.device = torch.device(device)
         self.pg = process_group
+        self.fuse_loss = bool(fuse_loss)      # False: loss and texture gradients through ffb_l1_loss_fwd_bwd, then the plain backward
         self.pts_dev = torch.empty((self.B if per_sample_points else 1, self.N, 2), dtype=torch.float32, device=self.device)
         self.last = None
 
@@ -265,16 +266,22 @@ class PatternStep:
         plan = R._SplatPlan(pts, self.B, self.sigma, self.ts0, self.ts1, self.ns, self.no)
         s, o = plan.forward(pts, True, True, self.sum_t)
         loss = None
+        d = None
         if upstream is None:
             # rasterization.py:589-599: L1(softored, summed) -- the reference compares against the transposed sum as-is
-            loss = torch.empty(self.B, dtype=torch.float32, device=self.device)
-            gs, go = torch.empty_like(s), torch.empty_like(o)
-            nat.check(nat.lib().ffb_l1_loss_fwd_bwd(o.data_ptr(), s.data_ptr(), 0, self.B, self.ts0, self.ts1, loss.data_ptr(),
-                                                    go.data_ptr(), gs.data_ptr(), nat.stream()), "ffb_l1_loss_fwd_bwd")
-            nat.count(2)
+            fused = plan.backward_l1(pts, s, o, self.sum_t) if self.fuse_loss else None
+            if fused is not None:
+                loss, d = fused
+            else:
+                loss = torch.empty(self.B, dtype=torch.float32, device=self.device)
+                gs, go = torch.empty_like(s), torch.empty_like(o)
+                nat.check(nat.lib().ffb_l1_loss_fwd_bwd(o.data_ptr(), s.data_ptr(), 0, self.B, self.ts0, self.ts1, loss.data_ptr(),
+                                                        go.data_ptr(), gs.data_ptr(), nat.stream()), "ffb_l1_loss_fwd_bwd")
+                nat.count(2)
         else:
             gs, go = upstream
-        d = plan.backward(pts, gs, go, self.sum_t, o)
+        if d is None:
+            d = plan.backward(pts, gs, go, self.sum_t, o)
         dp = R.reduce_over_samples(d) if self.B > 1 else d[0]
         self._allreduce(dp)
         self.last = (s, o, res)

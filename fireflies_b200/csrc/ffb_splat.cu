@@ -396,6 +396,8 @@ struct RasterParams {
     float* out_sum; float* out_softor;            // forward
     const float* g_sum; const float* g_softor;    // backward
     float* d_pts;
+    float* loss;              // fused L1 backward: per-sample mean |softor - sum| (accumulated)
+    float loss_inv;           // 1 / (ts0 * ts1)
 };
 
 __device__ __forceinline__ bool in_win(int v, uint32_t w) { return v >= (int)(w & 0xffff) && v < (int)(w >> 16); }
@@ -688,17 +690,17 @@ static int launch_fwd_tma(K kernel, KO overflow, const RasterParams& q, const Wt
 
 // TMA-fed backward over the same strip grid (tensor maps of the upstream arrays as kernel parameters)
 struct BwdMaps {
-    CUtensorMap gs, go, sv;
+    CUtensorMap gs, go, sv, ot;
 };
 template <typename K, typename KO>
 static int launch_bwd_tma(K kernel, KO overflow, const RasterParams& q, const WtConsts& fc, const OvfParams& o, int B, cudaStream_t st,
-                          const BwdMaps& m, size_t stage_bytes, size_t smem_ovf) {
+                          const BwdMaps& m, size_t stage_bytes, size_t smem_ovf, int nbuf = 3) {
     const unsigned gy = (unsigned)((q.tgy + WB_WARPS * WT_S - 1) / (WB_WARPS * WT_S));
     if (B > 65535 || gy > 65535) return fail_arg(FFB_E_LIMIT, "splat: B or the tile rows exceed the grid limit (65535)");
-    const size_t smem = (size_t)WB_WARPS * 3 * TMA_TILE_BYTES + 64 + stage_bytes * WB_WARPS;
+    const size_t smem = (size_t)WB_WARPS * nbuf * TMA_TILE_BYTES + 64 + stage_bytes * WB_WARPS;
     if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (smem_ovf > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(overflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ovf));
-    kernel<<<dim3((unsigned)q.tgx, gy, (unsigned)B), WB_CTA, smem, st>>>(q, fc, m.gs, m.go, m.sv);
+    kernel<<<dim3((unsigned)q.tgx, gy, (unsigned)B), WB_CTA, smem, st>>>(q, fc, m.gs, m.go, m.sv, m.ot);
     FFB_CUDA(cudaGetLastError());
     overflow<<<kNumSMs, WT_CTA, smem_ovf, st>>>(q, fc, o);
     FFB_CUDA(cudaGetLastError());
@@ -728,6 +730,7 @@ static void fill_raster(const ffb_splat_desc* d, const Plan& p, const void* ws, 
     q.N = d->N; q.ts0 = d->ts0; q.ts1 = d->ts1; q.tgx = p.tgx; q.tgy = p.tgy; q.T = p.T; q.cap = p.cap;
     q.sigma = d->sigma; q.rcp_sigma = 1.0f / d->sigma;
     q.out_sum = nullptr; q.out_softor = nullptr; q.g_sum = nullptr; q.g_softor = nullptr; q.d_pts = nullptr;
+    q.loss = nullptr; q.loss_inv = 0.f;
 }
 
 // ---- dense API-compat kernels -----------------------------------------------------------------------
@@ -980,6 +983,7 @@ extern "C" int ffb_splat_bwd(const ffb_splat_desc* d, const float* pts, const vo
                 if (!g_softor) m.go = m.gs;                 // unused maps still have to be valid kernel parameters
                 if (!q.saved_softor) m.sv = g_softor ? m.go : m.gs;
                 if (!g_sum) m.gs = m.go;
+                m.ot = m.go;
 #define FFB_TMA1(S, O, T, M, V) launch_bwd_tma(splat_bwd_tma<S, O, T, M, V>, splat_bwd_ovf<S, O, T, M, V>, q, fc, ov, B, st, m, \
                                                sizeof(WarpStage<M ? 2 : 1, true, false, 1>), sizeof(WarpStage<M ? 2 : 1, true, false, 1>) * WT_WARPS)
 #define FFB_TMA2(S, O, T, M) (q.saved_softor ? FFB_TMA1(S, O, T, M, true) : FFB_TMA1(S, O, T, M, false))
@@ -1010,6 +1014,46 @@ extern "C" int ffb_splat_bwd(const ffb_splat_desc* d, const float* pts, const vo
         return sum_transposed ? launch_raster(splat_bwd_kernel<true, false, true>, q, d->B, st)
                               : launch_raster(splat_bwd_kernel<true, false, false>, q, d->B, st);
     return launch_raster(splat_bwd_kernel<false, true, false>, q, d->B, st, gsm);
+}
+
+extern "C" int ffb_splat_bwd_l1(const ffb_splat_desc* d, const float* pts, const void* workspace,
+                                const float* out_sum, int sum_transposed, const float* out_softor,
+                                float* loss_out, float* d_pts, void* stream) {
+    (void)pts;
+    Plan p;
+    if (int rc = make_plan(d, &p)) return rc;
+    if (!workspace || !d_pts || !out_sum || !out_softor || !loss_out) return fail_arg(FFB_E_ARG, "splat_bwd_l1: null pointer");
+    if (sum_transposed && d->ts0 != d->ts1)
+        return fail_arg(FFB_E_ARG, "splat_bwd_l1: softor [ts1,ts0] and a transposed sum [ts0,ts1] only pair elementwise on square textures");
+    if (!p.fast || p.mask_o) return fail_arg(FFB_E_UNSUPPORTED, "splat_bwd_l1: needs the warp-tile path (texture larger than the footprints, exact soft-OR window)");
+    RasterParams q;
+    fill_raster(d, p, workspace, q);
+    q.g_sum = out_sum; q.g_softor = out_softor; q.saved_softor = out_softor; q.d_pts = d_pts;
+    q.loss = loss_out; q.loss_inv = 1.0f / ((float)d->ts0 * (float)d->ts1);
+    cudaStream_t st = as_stream(stream);
+    const int B = d->B;
+    BwdMaps m;
+    const uint64_t t0 = (uint64_t)d->ts0, t1 = (uint64_t)d->ts1;
+    bool ok = tma::encode_f32_3d(&m.go, out_softor, t0, t1, (uint64_t)B, WT, WT, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (ok) ok = sum_transposed ? tma::encode_f32_3d(&m.sv, out_sum, t1, t0, (uint64_t)B, WT, WT, CU_TENSOR_MAP_SWIZZLE_NONE)
+                                : tma::encode_f32_3d(&m.sv, out_sum, t0, t1, (uint64_t)B, WT, WT, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (ok && sum_transposed) {
+        ok = tma::encode_f32_3d(&m.gs, out_sum, t1, t0, (uint64_t)B, WT, WT, CU_TENSOR_MAP_SWIZZLE_64B) &&
+             tma::encode_f32_3d(&m.ot, out_softor, t0, t1, (uint64_t)B, WT, WT, CU_TENSOR_MAP_SWIZZLE_64B);
+    } else if (ok) {
+        m.gs = m.sv; m.ot = m.go;
+    }
+    if (!ok) return fail_arg(FFB_E_UNSUPPORTED, "splat_bwd_l1: textures must be 16-byte aligned with sides that are multiples of 4 (TMA)");
+    FFB_CUDA(cudaMemsetAsync(d_pts, 0, (size_t)B * d->N * 2 * sizeof(float), st));
+    FFB_CUDA(cudaMemsetAsync(loss_out, 0, (size_t)B * sizeof(float), st));
+    const WtConsts fc = wt_consts(d, p);
+    const OvfParams ov = {q.ovf, q.ovf + 1, B};
+    const size_t stage = sizeof(WarpStage<1, true, false, 1>);
+    if (sum_transposed)
+        return launch_bwd_tma(splat_bwd_tma<true, true, true, false, true, true>, splat_bwd_ovf<true, true, true, false, true, true>, q, fc, ov,
+                              B, st, m, stage, stage * WT_WARPS, 4);
+    return launch_bwd_tma(splat_bwd_tma<true, true, false, false, true, true>, splat_bwd_ovf<true, true, false, false, true, true>, q, fc, ov,
+                          B, st, m, stage, stage * WT_WARPS, 3);
 }
 
 extern "C" int ffb_reduce_over_samples(const float* in, int32_t B, int64_t row_elems, float* out, void* stream) {

@@ -788,18 +788,27 @@ __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_wt(RasterParam
 // 64-byte swizzle so that a lane's (column, row pair) reads are conflict free; no shuffles are needed any more.
 // One 3 KB buffer set per warp: a tile's values move to registers first, then the next tile's boxes are requested and
 // land while this tile is computed.
-template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O, bool SAVED>
+//
+// LOSS: the upstream gradients are those of mean|softor - sum| (torch.nn.L1Loss on the two reductions as stored,
+// rasterization.py:589-599) and are formed here from the forward's outputs instead of being read: tm_go / tm_sv are
+// the soft-OR / sum outputs at the tile's own index, and -- when the sum is stored transposed ([ts0, ts1], square
+// textures) -- tm_gs / tm_ot the sum / soft-OR outputs at the mirrored index, which is where this tile's sum texels
+// meet their partners.  Every tile of the strip is visited (the loss needs all texels); super tiles without a
+// usable candidate list only contribute to the loss.
+template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O, bool SAVED, bool LOSS = false>
 __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_tma(RasterParams q, WtConsts fc, const __grid_constant__ CUtensorMap tm_gs,
                                                                       const __grid_constant__ CUtensorMap tm_go,
-                                                                      const __grid_constant__ CUtensorMap tm_sv) {
+                                                                      const __grid_constant__ CUtensorMap tm_sv,
+                                                                      const __grid_constant__ CUtensorMap tm_ot) {
     typedef WarpStage<MASK_O ? 2 : 1, true, false, 1> Stage;
+    constexpr int NBUF = (LOSS && SUM_T) ? 4 : 3;
     extern __shared__ __align__(1024) unsigned char wt_smem_tma[];
     Strip sp;
     if (!strip_init<WB_WARPS>(sp, q)) return;
     const int wid = threadIdx.x >> 5;
-    unsigned char* tin = wt_smem_tma + wid * (3 * TMA_TILE_BYTES);               // [go | saved | gs], 1 KB each, 1 KB aligned
-    uint64_t* bar = reinterpret_cast<uint64_t*>(wt_smem_tma + WB_WARPS * 3 * TMA_TILE_BYTES) + wid;
-    Stage& st = reinterpret_cast<Stage*>(wt_smem_tma + WB_WARPS * 3 * TMA_TILE_BYTES + 64)[wid];
+    unsigned char* tin = wt_smem_tma + wid * (NBUF * TMA_TILE_BYTES);            // [go | saved | gs | (LOSS) ot], 1 KB each, 1 KB aligned
+    uint64_t* bar = reinterpret_cast<uint64_t*>(wt_smem_tma + WB_WARPS * NBUF * TMA_TILE_BYTES) + wid;
+    Stage& st = reinterpret_cast<Stage*>(wt_smem_tma + WB_WARPS * NBUF * TMA_TILE_BYTES + 64)[wid];
     const Entry* entries = q.entries + (size_t)sp.bin * q.cap;
     WtCoord w;
     w.b = sp.b; w.c0 = sp.c0; w.lc = sp.lane & 15; w.h = sp.lane >> 4;
@@ -815,7 +824,8 @@ __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_tma(RasterPara
     prefetch_entries(st.raw[0], entries + __shfl_sync(0xffffffffu, sp.tv, 0), n <= WCH ? n : 0, sp.lane);
     unsigned phase = 0;
     bool have = false;                                      // tile 0 of the current super tile is already in flight
-    constexpr unsigned kBytes = (unsigned)TMA_TILE_BYTES * ((SOFTOR ? (SAVED ? 2 : 1) : 0) + (SUM ? 1 : 0));
+    constexpr unsigned kBytes = (unsigned)TMA_TILE_BYTES * (LOSS ? (SUM_T ? 4 : 2) : ((SOFTOR ? (SAVED ? 2 : 1) : 0) + (SUM ? 1 : 0)));
+    float lacc = 0.f;                                       // LOSS: this lane's share of sum |softor - sum|
     // natural tiles: texel (row 4i + 2h + j, column lc) at float (4i + j) * 16 + nat_off
     const float* nat = reinterpret_cast<const float*>(tin) + (2 * w.h) * WT + w.lc;
     // transposed tile (64-byte swizzle: 16-byte chunk index ^= (column >> 1) & 3): rows 4i + 2h + {0, 1} of column lc
@@ -825,6 +835,15 @@ __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_tma(RasterPara
         if (sp.lane == 0) {
             const int ct = w.c0 + WT * j;
             tma::mbar_expect_tx(bar, kBytes);
+            if (LOSS) {
+                tma::load_3d(tin, &tm_go, bar, ct, r0, w.b);
+                tma::load_3d(tin + TMA_TILE_BYTES, &tm_sv, bar, ct, r0, w.b);
+                if (SUM_T) {
+                    tma::load_3d(tin + 2 * TMA_TILE_BYTES, &tm_gs, bar, r0, ct, w.b);
+                    tma::load_3d(tin + 3 * TMA_TILE_BYTES, &tm_ot, bar, r0, ct, w.b);
+                }
+                return;
+            }
             if (SOFTOR) {
                 tma::load_3d(tin, &tm_go, bar, ct, r0, w.b);
                 if (SAVED) tma::load_3d(tin + TMA_TILE_BYTES, &tm_sv, bar, ct, r0, w.b);
@@ -835,6 +854,7 @@ __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_tma(RasterPara
             }
         }
     };
+    auto sgn = [&](float d) { return d > 0.f ? q.loss_inv : (d < 0.f ? -q.loss_inv : 0.f); };
 
     for (int s = 0; s < sp.nst; ++s) {
         const EntryRegs e = take_entry(st.raw[0], n <= WCH ? n : 0, sp.lane);
@@ -845,24 +865,44 @@ __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_tma(RasterPara
             nn = __shfl_sync(0xffffffffu, sp.tv, 2 * s + 3) - nb;
             prefetch_entries(st.raw[0], entries + nb, nn <= WCH ? nn : 0, sp.lane);
         }
-        const bool next_live = nn > 0 && nn <= WCH;
-        if (n > 0 && n <= WCH) {                           // empty: nothing to do; larger lists: overflow kernel
+        const bool next_live = LOSS ? (s + 1 < sp.nst) : (nn > 0 && nn <= WCH);
+        const bool grad = n > 0 && n <= WCH;               // empty: no gradient work; larger lists: overflow kernel
+        if (LOSS || grad) {
             w.r0 = (sp.sty0 + s) * WT;
             if (!have) issue(w.r0, 0);
-            const WtMasks mk = stage_regs(st, e, n, w.c0, (float)w.r0, fc, sp.lane);
+            WtMasks mk;
+            mk.tb01 = mk.tb23 = mk.nb01 = mk.nb23 = 0u;
+            if (grad) mk = stage_regs(st, e, n, w.c0, (float)w.r0, fc, sp.lane);
 #pragma unroll 1
             for (int j = 0; j < 4; ++j) {
                 float2 gs[4], gp[4];
                 tma::mbar_wait(bar, phase);
                 phase ^= 1u;
-                if (SOFTOR) {
+                if (LOSS) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 o = make_float2(nat[(4 * i) * WT], nat[(4 * i + 1) * WT]);
+                        const float2 sm = make_float2(nat[WT * WT + (4 * i) * WT], nat[WT * WT + (4 * i + 1) * WT]);
+                        const float dx_ = o.x - sm.x, dy_ = o.y - sm.y;
+                        lacc += fabsf(dx_) + fabsf(dy_);
+                        const float2 sg = make_float2(sgn(dx_), sgn(dy_));
+                        gp[i] = __fmul2_rn(sg, make_float2(1.f - o.x, 1.f - o.y));
+                        if (SUM_T) {
+                            const float2 st_ = *reinterpret_cast<const float2*>(tin + (tr_base + (tr_x ^ (unsigned)(i << 4))));
+                            const float2 ot_ = *reinterpret_cast<const float2*>(tin + TMA_TILE_BYTES + (tr_base + (tr_x ^ (unsigned)(i << 4))));
+                            gs[i] = make_float2(-sgn(ot_.x - st_.x), -sgn(ot_.y - st_.y));
+                        } else {
+                            gs[i] = neg2(sg);
+                        }
+                    }
+                } else if (SOFTOR) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         gp[i] = make_float2(nat[(4 * i) * WT], nat[(4 * i + 1) * WT]);
                         if (SAVED) gp[i] = __fmul2_rn(gp[i], make_float2(1.f - nat[WT * WT + (4 * i) * WT], 1.f - nat[WT * WT + (4 * i + 1) * WT]));
                     }
                 }
-                if (SUM) {
+                if (SUM && !LOSS) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         if (SUM_T) gs[i] = *reinterpret_cast<const float2*>(tin + (tr_base + (tr_x ^ (unsigned)(i << 4))));
@@ -873,6 +913,7 @@ __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_tma(RasterPara
                 // next tile (of this super tile, or tile 0 of the next one) in flight while this one is computed
                 if (j < 3) issue(w.r0, j + 1);
                 else if (next_live) issue(w.r0 + WT, 0);
+                if (LOSS && !grad) continue;
                 const unsigned tm = tile_mask(mk, j);
                 const float cf = (float)(w.c0 + WT * j + w.lc);
                 if (SOFTOR && !SAVED) {                    // pass 1 (only without the saved output): per-texel product of (1 - g)
@@ -887,12 +928,16 @@ __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_tma(RasterPara
                 weigh_tile<SUM, SOFTOR, MASK_O, false>(st, (MASK_O || !FFB_BWD_FAR) ? tm : nm, n, cf, w.h, sp.lane, fc, gs, gp);
                 if (!MASK_O && FFB_BWD_FAR) weigh_tile<SUM, SOFTOR, MASK_O, true>(st, tm & ~nm, n, cf, w.h, sp.lane, fc, gs, gp);
             }
-            flush_warp(st, n, w.h, w.lc, kh, dp);
+            if (grad) flush_warp(st, n, w.h, w.lc, kh, dp);
             have = next_live;
         } else {
             have = false;
         }
         n = nn;
+    }
+    if (LOSS) {
+        lacc = warp_sum(lacc);
+        if (sp.lane == 0) atomicAdd(q.loss + sp.b, lacc * q.loss_inv);
     }
 }
 
@@ -951,7 +996,7 @@ __global__ void __launch_bounds__(WT_CTA) splat_fwd_ovf(RasterParams q, WtConsts
     }
 }
 
-template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O, bool SAVED>
+template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O, bool SAVED, bool LOSS = false>
 __global__ void __launch_bounds__(WT_CTA) splat_bwd_ovf(RasterParams q, WtConsts fc, OvfParams o) {
     typedef WarpStage<MASK_O ? 2 : 1, true, false, 1> Stage;
     extern __shared__ __align__(16) unsigned char wt_smem[];
@@ -974,9 +1019,32 @@ __global__ void __launch_bounds__(WT_CTA) splat_bwd_ovf(RasterParams q, WtConsts
             if (ct >= q.ts0) break;
             const float cf = (float)(ct + w.lc);
             TileIn in;
-            load_tile_in<SUM, SOFTOR, SUM_T, SAVED>(in, q, w, tp, j);
             float2 gs[4], gp[4];
-            unpack_tile_in<SUM, SOFTOR, SUM_T, SAVED>(in, w.h, gs, gp);
+            if (LOSS) {
+                // gradients of mean|softor - sum| from the forward's outputs (g_softor = softor, g_sum = sum as stored); the loss
+                // value itself is accumulated by the main kernel, which visits every tile
+                const int c = ct + w.lc;
+                const bool interior = w.r0 + WT <= q.ts1 && ct + WT <= q.ts0;
+                float sn[8], srun[8], orun[8];
+                load_natural(q.g_softor + tp.nat + WT * j, q, w, c, interior, in.o);
+                load_natural(q.g_sum + tp.nat + WT * j, q, w, c, interior, sn);
+                auto sgn = [&](float d) { return d > 0.f ? q.loss_inv : (d < 0.f ? -q.loss_inv : 0.f); };
+                if (SUM_T) {
+                    load_run(q.g_sum + tp.tr + (size_t)(WT * j) * q.ts1, q, w, c, interior, srun);
+                    load_run(q.g_softor + tp.tr + (size_t)(WT * j) * q.ts1, q, w, c, interior, orun);
+                    run_to_rows(srun, in.s, w.h);
+                    run_to_rows(orun, in.sv, w.h);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 sg = make_float2(sgn(in.o[2 * i] - sn[2 * i]), sgn(in.o[2 * i + 1] - sn[2 * i + 1]));
+                    gp[i] = __fmul2_rn(sg, make_float2(1.f - in.o[2 * i], 1.f - in.o[2 * i + 1]));
+                    gs[i] = SUM_T ? make_float2(-sgn(in.sv[2 * i] - in.s[2 * i]), -sgn(in.sv[2 * i + 1] - in.s[2 * i + 1])) : neg2(sg);
+                }
+            } else {
+                load_tile_in<SUM, SOFTOR, SUM_T, SAVED>(in, q, w, tp, j);
+                unpack_tile_in<SUM, SOFTOR, SUM_T, SAVED>(in, w.h, gs, gp);
+            }
             if (SOFTOR && !SAVED) {
                 float2 prod[4], unused[4];
 #pragma unroll

@@ -98,6 +98,23 @@ class _SplatPlan:
         return d_pts
 
 
+    def backward_l1(self, points, out_sum, out_softor, sum_transposed: bool):
+        """Fused ``L1Loss(softor, sum).backward()`` (rasterization.py:589-599): returns ``(loss [B], d_pts [B,N,2])`` or
+        ``None`` when the fused kernel does not cover the case (the caller then runs the loss and the backward
+        separately)."""
+        if sum_transposed and self.ts0 != self.ts1:
+            return None
+        d_pts = torch.empty((self.B, self.N, 2), dtype=torch.float32, device=points.device)
+        loss = torch.empty(self.B, dtype=torch.float32, device=points.device)
+        rc = nat.lib().ffb_splat_bwd_l1(C.byref(self.desc), points.data_ptr(), self.ws.data_ptr(), out_sum.data_ptr(),
+                                        int(sum_transposed), out_softor.data_ptr(), loss.data_ptr(), d_pts.data_ptr(), nat.stream())
+        if rc == nat.E_UNSUPPORTED:
+            return None
+        nat.check(rc, "ffb_splat_bwd_l1")
+        nat.count(3)      # two memsets + kernel
+        return loss, d_pts
+
+
 def reduce_over_samples(x: torch.Tensor) -> torch.Tensor:
     """``x.sum(0)`` in a fixed order (deterministic): folds per-sample pattern gradients."""
     x = nat.require_cuda(x, torch.float32, "x")

@@ -44,6 +44,7 @@ extern "C" {
 #define FFB_E_ARG      (-1)   /* invalid argument (null pointer, non-positive size, ...)   */
 #define FFB_E_WORKSPACE (-2)  /* workspace too small                                       */
 #define FFB_E_LIMIT    (-3)   /* size beyond a compiled limit (see message)                */
+#define FFB_E_UNSUPPORTED (-4) /* the fused path does not cover this case; use the unfused calls */
 
 FFB_API int         ffb_version(void);
 FFB_API const char* ffb_last_error_string(void);
@@ -96,6 +97,22 @@ FFB_API int ffb_splat_fwd(const ffb_splat_desc* d, const float* pts, const void*
 FFB_API int ffb_splat_bwd(const ffb_splat_desc* d, const float* pts, const void* workspace,
                   const float* g_sum, int sum_transposed, const float* g_softor, const float* saved_softor,
                   float* d_pts, void* stream);
+
+/* Fused backward of the only optimisation loop the reference ships (test_point_reg,
+ * fireflies/graphics/rasterization.py:586-607: `loss = L1Loss(softored, summed); loss.backward()`):
+ * per-sample loss = mean |out_softor - out_sum| over the two textures AS STORED (same memory index), and
+ * d loss / d pts, in one pass over the forward's outputs -- the texture gradients are formed in registers
+ * instead of being written by ffb_l1_loss_fwd_bwd and read back by ffb_splat_bwd.
+ *   out_sum, out_softor  what ffb_splat_fwd wrote for these points (both required)
+ *   sum_transposed       layout of out_sum as in ffb_splat_fwd; with 1 the textures must be square
+ *                        (the reference pairs softor[ts1,ts0] with baked_sum_2's [ts0,ts1] elementwise)
+ *   loss_out f32 [B] and d_pts f32 [B,N,2] are OVERWRITTEN.
+ * Returns FFB_E_UNSUPPORTED when the textures cannot be described to the TMA unit (base not 16-byte
+ * aligned, sides not multiples of 4) or the descriptor needs the general kernels; callers then use
+ * ffb_l1_loss_fwd_bwd + ffb_splat_bwd. */
+FFB_API int ffb_splat_bwd_l1(const ffb_splat_desc* d, const float* pts, const void* workspace,
+                     const float* out_sum, int sum_transposed, const float* out_softor,
+                     float* loss_out, float* d_pts, void* stream);
 
 /* sum over the sample axis: out[N*2] = sum_b in[b, N*2]  (fixed order -> deterministic);
  * used to fold per-sample pattern gradients before the allreduce. */

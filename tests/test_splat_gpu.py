@@ -230,3 +230,56 @@ def test_full_size_properties(R):
     R.splat_reduce(p, 100.0, ts, reduce=("sum",))[0].sum().backward()
     inner = ((pts > 0.05) & (pts < 0.95)).all(1)
     assert p.grad[inner].abs().max() < 2e-2      # vs O(1e3) individual terms: sub-pixel sampling ripple only
+
+
+# ---- fused L1(softor, sum) backward (ffb_splat_bwd_l1; rasterization.py:586-607 test_point_reg) ---------------------
+def _l1_case(R, pts, sigma, ts, sum_t):
+    """(loss, d_pts) of the fused kernel, of the unfused ABI path and of the oracle's autograd for per-sample points."""
+    import ctypes as C
+    from fireflies_b200 import _native as nat
+    B, N = pts.shape[0], pts.shape[1]
+    plan = R._SplatPlan(pts, B, sigma, ts[0], ts[1], 4, 5)
+    s, o = plan.forward(pts, True, True, sum_t)
+    fused = plan.backward_l1(pts, s, o, sum_t)
+    assert fused is not None, "fused L1 backward refused a case it should cover"
+    loss_f, d_f = fused
+    loss_u = torch.empty(B, device="cuda")
+    gs, go = torch.empty_like(s), torch.empty_like(o)
+    nat.check(nat.lib().ffb_l1_loss_fwd_bwd(o.data_ptr(), s.data_ptr(), 0, B, ts[0], ts[1], loss_u.data_ptr(), go.data_ptr(),
+                                            gs.data_ptr(), nat.stream()), "l1")
+    d_u = plan.backward(pts, gs, go, sum_t, o)
+    loss_o, d_o = [], []
+    for b in range(B):
+        p = pts[b].cpu().clone().requires_grad_(True)
+        S = O.baked_sum(p, sigma, ts, transposed=sum_t)
+        So = O.baked_softor(p, sigma, ts)
+        l = O.l1_loss(So, S)
+        l.backward()
+        loss_o.append(l.detach()); d_o.append(p.grad)
+    return (loss_f, d_f), (loss_u, d_u), (torch.stack(loss_o), torch.stack(d_o))
+
+
+@pytest.mark.parametrize("ts,sum_t,N,sigma,cluster", [([256, 256], True, 300, 36.0, False), ([320, 192], False, 200, 36.0, False),
+                                                       ([256, 256], True, 120, 100.0, True), ([260, 260], True, 150, 25.0, False)])
+def test_fused_l1_backward(R, ts, sum_t, N, sigma, cluster):
+    gen = torch.Generator().manual_seed(11)
+    B = 3
+    pts = torch.rand(B, N, 2, generator=gen) * 0.9 + 0.05
+    if cluster:                                             # long candidate lists: the overflow kernels take those super tiles
+        pts = 0.45 + 0.1 * torch.rand(B, N, 2, generator=gen)
+    pts = pts.cuda()
+    (lf, df), (lu, du), (lo, do) = _l1_case(R, pts, sigma, ts, sum_t)
+    close(lf, lu, rtol=2e-6, atol=0)                        # same textures, same signs: only the summation order differs
+    close(df, du, rtol=1e-4, atol=1e-5 * float(du.abs().max()))
+    close(lf, lo, rtol=1e-5, atol=1e-9)
+    close(df, do, rtol=1e-4, atol=1e-4 * float(do.abs().max()))
+
+
+def test_fused_l1_refuses_what_it_cannot_pair(R):
+    pts = (torch.rand(2, 50, 2, generator=torch.Generator().manual_seed(1)) * 0.8 + 0.1).cuda()
+    plan = R._SplatPlan(pts, 2, 36.0, 256, 192, 4, 5)
+    s, o = plan.forward(pts, True, True, True)
+    assert plan.backward_l1(pts, s, o, True) is None        # [192,256] vs [256,192]: no elementwise pairing
+    plan = R._SplatPlan(pts, 2, 36.0, 254, 254, 4, 5)       # sides not multiples of 4: no TMA description
+    s, o = plan.forward(pts, True, True, True)
+    assert plan.backward_l1(pts, s, o, True) is None
