@@ -247,6 +247,7 @@ class PatternStep:
         self.fuse_loss = bool(fuse_loss)      # False: loss and texture gradients through ffb_l1_loss_fwd_bwd, then the plain backward
         self.pts_dev = torch.empty((self.B if per_sample_points else 1, self.N, 2), dtype=torch.float32, device=self.device)
         self.last = None
+        self._side: Optional[torch.cuda.Stream] = None
 
     def _allreduce(self, t: torch.Tensor) -> None:
         from .parallel import allreduce_sum_
@@ -256,7 +257,16 @@ class PatternStep:
                          sample0: Optional[int] = None):
         """points: ``[N,2]`` or ``[B,N,2]`` (device, or pinned host -> copied inside).  Returns
         ``(loss [B] or None, dpoints [N,2] summed over the B samples and all ranks, BatchResult or None)``."""
-        res = self.scene_batch.randomize(self.B, sample0=sample0) if self.scene_batch is not None else None
+        # the scene randomisation (HBM-bound vertex transform) does not depend on the pattern: it runs on a side stream
+        # next to the latency-bound binning kernel and joins before the fold
+        res = None
+        if self.scene_batch is not None:
+            cur = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                res = self.scene_batch.randomize(self.B, sample0=sample0)
         if points.dim() == 2:
             self.pts_dev.copy_(points.unsqueeze(0).expand_as(self.pts_dev) if self.per_sample else points.unsqueeze(0),
                                non_blocking=True)
@@ -283,6 +293,12 @@ class PatternStep:
         if d is None:
             d = plan.backward(pts, gs, go, self.sum_t, o)
         dp = R.reduce_over_samples(d) if self.B > 1 else d[0]
+        if res is not None:
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(self._side)
+            for t in (res.world, res.sampled, res.vertices):      # produced on the side stream, consumed by the caller on this one
+                if t is not None:
+                    t.record_stream(cur)
         self._allreduce(dp)
         self.last = (s, o, res)
         return loss, dp, res

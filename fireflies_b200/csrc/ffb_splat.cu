@@ -652,6 +652,7 @@ static WtConsts wt_consts(const ffb_splat_desc* d, const Plan& p) {
     fc.ho = (float)p.H_o + 0.5f;
     fc.c1 = 1.00000011920928955078125f;      // 1 + 2^-23
     fc.disc2 = (float)((double)d->sigma * sqrt(20.723265836946414));      // (d2 / sigma)^2 = ln(1e9)
+    fc.disc2_f = (float)((double)d->sigma * sqrt(17.5) * 1.02);           // same margin as the exact soft-OR no-op radius h_o (make_plan)
     fc.near2 = (float)((double)d->sigma * sqrt(5.545177444479562));       // (d2 / sigma)^2 = ln(2^8)
     fc.s2 = (float)(sqrt(1.4426950408889634) / (double)d->sigma);
     fc.rs2 = (float)((double)d->sigma / sqrt(1.4426950408889634));
@@ -677,11 +678,11 @@ static int launch_wt(K kernel, KO overflow, const RasterParams& q, const WtConst
 template <typename K, typename KO>
 static int launch_fwd_tma(K kernel, KO overflow, const RasterParams& q, const WtConsts& fc, const OvfParams& o, int B, cudaStream_t st,
                           const CUtensorMap& ms, const CUtensorMap& mo, size_t stage_bytes) {
-    const unsigned gy = (unsigned)((q.tgy + WT_WARPS * WT_S - 1) / (WT_WARPS * WT_S));
+    const unsigned gy = (unsigned)((q.tgy + WF_WARPS * WT_S - 1) / (WF_WARPS * WT_S));
     if (B > 65535 || gy > 65535) return fail_arg(FFB_E_LIMIT, "splat: B or the tile rows exceed the grid limit (65535)");
-    const size_t smem = (size_t)WT_WARPS * (2 * TMA_TILE_BYTES + stage_bytes);
+    const size_t smem = (size_t)WF_WARPS * (2 * TMA_TILE_BYTES + stage_bytes);
     if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<dim3((unsigned)q.tgx, gy, (unsigned)B), WT_CTA, smem, st>>>(q, fc, ms, mo);
+    kernel<<<dim3((unsigned)q.tgx, gy, (unsigned)B), WF_CTA, smem, st>>>(q, fc, ms, mo);
     FFB_CUDA(cudaGetLastError());
     overflow<<<kNumSMs, WT_CTA, 0, st>>>(q, fc, o);
     FFB_CUDA(cudaGetLastError());

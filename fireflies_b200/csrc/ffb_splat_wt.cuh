@@ -38,10 +38,18 @@
 constexpr int WT_S = 4;                   // vertically adjacent super tiles per warp
 constexpr int WT_CTA = 256;               // forward / overflow kernels: 8 warps x 4 super tiles (64 x 16 texels each) = 64 x 512 texels
 constexpr int WT_WARPS = WT_CTA / 32;
-#ifndef FFB_WB_CTA
-#define FFB_WB_CTA 128
+#ifndef FFB_WF_CTA
+#define FFB_WF_CTA 256
 #endif
-constexpr int WB_CTA = FFB_WB_CTA;        // backward: 4 warps per CTA (measured: finer CTA granularity, 4 % faster; the forward prefers 8)
+constexpr int WF_CTA = FFB_WF_CTA;        // TMA-store forward
+constexpr int WF_WARPS = WF_CTA / 32;
+#ifndef FFB_WF_MINB
+#define FFB_WF_MINB (1024 / FFB_WF_CTA)   // 32 warps per SM at 64 registers
+#endif
+#ifndef FFB_WB_CTA
+#define FFB_WB_CTA 32
+#endif
+constexpr int WB_CTA = FFB_WB_CTA;        // backward: one warp per CTA (measured 0.67 ms vs 0.70 ms at 64 / 128 threads: a strip's slot frees the moment it ends; the forward prefers 8 warps)
 constexpr int WB_WARPS = WB_CTA / 32;
 #ifndef FFB_FFS_LOOP
 #define FFB_FFS_LOOP 1                    // 1: walk a tile's candidate mask with ffs (two XU-pipe ops per candidate); 0: test bit k of the mask for k < n
@@ -52,6 +60,9 @@ constexpr int WB_WARPS = WB_CTA / 32;
 #ifndef FFB_BWD_DISC
 #define FFB_BWD_DISC 1                    // backward: drop (candidate, tile) pairs whose nearest texel is beyond the radius where g < 1e-9
 #endif
+#ifndef FFB_FWD_DISC
+#define FFB_FWD_DISC 1                    // forward: drop (candidate, tile) pairs whose nearest texel is beyond the radius where g <= 2^-25
+#endif
 #ifndef FFB_BWD_FAR
 #define FFB_BWD_FAR 1                     // backward: tiles where every g < 2^-8 take 1/(1-g) = 1 + g + g^2 (+O(g^3) < 6e-8) on the FMA pipe instead of MUFU.RCP
 #endif
@@ -59,7 +70,7 @@ constexpr int WB_WARPS = WB_CTA / 32;
 #define FFB_FWD_MINB 4                    // resident CTAs per SM the register allocation aims for
 #endif
 #ifndef FFB_BWD_MINB
-#define FFB_BWD_MINB (768 / FFB_WB_CTA)   // 24 warps per SM
+#define FFB_BWD_MINB (FFB_WB_CTA == 32 ? 22 : 768 / FFB_WB_CTA)   // 22-24 warps per SM: what 80 registers and ~10 KB of shared memory per warp allow
 #endif
 
 constexpr int TMA_TILE_BYTES = WT * WT * 4;   // one 16x16 fp32 tile as a TMA box
@@ -70,6 +81,7 @@ struct WtConsts {
     float hs, ho;                         // H + 0.5 for the column predicates
     float c1;                             // 1 + 2^-23: keeps 1 - g away from 0 in the backward quotient
     float disc2;                          // squared radius beyond which g < 1e-9 (backward tile culling)
+    float disc2_f;                        // squared radius beyond which g <= 2^-25 (forward tile culling: 1 - g == 1 exactly)
     float near2;                          // squared radius beyond which g < 2^-8 (backward: far tiles need no reciprocal)
     float s2, rs2;                        // sqrt(-K2) and its reciprocal: the backward's tables hold d^2 * s2, so g = 2^-(d2s^2)
 };
@@ -180,9 +192,11 @@ __device__ __forceinline__ WtMasks stage_regs(Stage& s, const EntryRegs& e, int 
             ta[i] = clo < WT * i + WT && chi > WT * i;
             if (rlo < 4 * i + 4 && rhi > 4 * i) gm |= 1u << i;
         }
-        if (ACC && FFB_BWD_DISC) {
-            // backward only: a tile whose nearest texel centre has g < 1e-9 contributes nothing measurable to d/dP (weights
-            // g * d2 * (c - P)); corner tiles of the square window go.  The forward keeps the reference's square footprint.
+        if (ACC ? FFB_BWD_DISC : FFB_FWD_DISC) {
+            // backward: a tile whose nearest texel centre has g < 1e-9 contributes nothing measurable to d/dP (weights
+            // g * d2 * (c - P)); corner tiles of the square window go.  Forward: the radius is where g <= 2^-25, i.e. where
+            // the soft-OR factor 1 - g is exactly 1 and a sum term is below 3e-8 (half an ulp of a texel value of 0.5; the
+            // reference's own dense and baked sums differ by 2.4e-7).
             const float ry = fmaxf(fmaxf(r0f - e.a.y, e.a.y - (r0f + (float)(WT - 1))), 0.f);
             const float ry2 = ry * ry;
 #pragma unroll
@@ -190,7 +204,7 @@ __device__ __forceinline__ WtMasks stage_regs(Stage& s, const EntryRegs& e, int 
                 const float xl = (float)(c0 + WT * i);
                 const float rx = fmaxf(fmaxf(xl - e.a.x, e.a.x - (xl + (float)(WT - 1))), 0.f);
                 const float rr = fmaf(rx, rx, ry2);
-                ta[i] = ta[i] && rr <= fc.disc2;
+                ta[i] = ta[i] && rr <= (ACC ? fc.disc2 : fc.disc2_f);
                 na[i] = ta[i] && (!FFB_BWD_FAR || rr < fc.near2);
             }
         }
@@ -466,15 +480,15 @@ __global__ void __launch_bounds__(WT_CTA, FFB_FWD_MINB) splat_fwd_wt(RasterParam
 // per output: no per-lane addresses, no edge path (the TMA unit clips boxes at the texture border).  In splat_fwd_wt
 // the stores and their address arithmetic were 130 of the ~340 instructions per tile.
 template <bool SUM, bool SOFTOR, bool SUM_T, bool MASK_O>
-__global__ void __launch_bounds__(WT_CTA, FFB_FWD_MINB) splat_fwd_tma(RasterParams q, WtConsts fc, const __grid_constant__ CUtensorMap tm_s,
+__global__ void __launch_bounds__(WF_CTA, FFB_WF_MINB) splat_fwd_tma(RasterParams q, WtConsts fc, const __grid_constant__ CUtensorMap tm_s,
                                                                       const __grid_constant__ CUtensorMap tm_o) {
     typedef WarpStage<MASK_O ? 2 : 0> Stage;
     extern __shared__ __align__(1024) unsigned char wt_smem_ftma[];
     Strip sp;
-    if (!strip_init<WT_WARPS>(sp, q)) return;              // whole warp; no block-level barriers below
+    if (!strip_init<WF_WARPS>(sp, q)) return;              // whole warp; no block-level barriers below
     const int wid = threadIdx.x >> 5;
     unsigned char* tout = wt_smem_ftma + wid * (2 * TMA_TILE_BYTES);         // [softor | sum], 1 KB each, 1 KB aligned
-    Stage& st = reinterpret_cast<Stage*>(wt_smem_ftma + WT_WARPS * 2 * TMA_TILE_BYTES)[wid];
+    Stage& st = reinterpret_cast<Stage*>(wt_smem_ftma + WF_WARPS * 2 * TMA_TILE_BYTES)[wid];
     const Entry* entries = q.entries + (size_t)sp.bin * q.cap;
     WtCoord w;
     w.b = sp.b; w.c0 = sp.c0; w.lc = sp.lane & 15; w.h = sp.lane >> 4;
