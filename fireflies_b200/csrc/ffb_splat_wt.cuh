@@ -60,6 +60,9 @@ constexpr int WB_WARPS = WB_CTA / 32;
 #ifndef FFB_BWD_DISC
 #define FFB_BWD_DISC 1                    // backward: drop (candidate, tile) pairs whose nearest texel is beyond the radius where g < 1e-9
 #endif
+#ifndef FFB_BWD_STAGED
+#define FFB_BWD_STAGED 1                  // backward inner loop staged over the four row groups (MUFU latencies overlap)
+#endif
 #ifndef FFB_FWD_DISC
 #define FFB_FWD_DISC 1                    // forward: drop (candidate, tile) pairs whose nearest texel is beyond the radius where g <= 2^-25
 #endif
@@ -89,6 +92,18 @@ struct WtConsts {
 __device__ __forceinline__ float ex2_approx(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// volatile twins: ptxas keeps volatile asm statements in source order, which is how the staged backward loop pins
+// "all exponentials, then all reciprocals"
+__device__ __forceinline__ float ex2_approx_v(float x) {
+    float r;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx_v(float x) {
+    float r;
+    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -577,6 +592,55 @@ __device__ __forceinline__ void weigh_tile(Stage& st, unsigned tm, int n, float 
         const bool pcs = ec <= fc.hs, pco = ec <= fc.ho;
         const float4* tA = &st.tabA[k][h];
         float2 a0 = bc(0.f), a1 = bc(0.f);
+#if FFB_BWD_STAGED
+        if (!MASK_O && !FFB_BWD_SKIP) {
+            // staged over the four row groups: all exponentials, then all reciprocals, then the FMA tail -- the special-function
+            // latencies overlap instead of being waited for group by group (the ncu source view showed ~400 stall samples on
+            // every first consumer of a MUFU result in the group-serial schedule)
+            float2 d2[4], g[4], x[4];
+            float4 A[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                A[i] = tA[2 * i];
+                d2[i] = __fadd2_rn(bc(dx2), make_float2(A[i].x, A[i].y));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 t = __fmul2_rn(neg2(d2[i]), d2[i]);
+                g[i] = make_float2(ex2_approx_v(t.x), ex2_approx_v(t.y));
+            }
+            if (FARV) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    x[i] = bc(0.f);
+                    if (SOFTOR) x[i] = __fmul2_rn(gp[i], __ffma2_rn(g[i], __ffma2_rn(g[i], g[i], g[i]), g[i]));
+                    if (SUM) { if (pcs) x[i] = __ffma2_rn(__fmul2_rn(gs[i], make_float2(A[i].z, A[i].w)), g[i], x[i]); }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    x[i] = bc(0.f);
+                    if (SOFTOR) {
+                        const float2 om = __fadd2_rn(bc(fc.c1), neg2(g[i]));
+                        x[i] = make_float2(rcp_approx_v(om.x), rcp_approx_v(om.y));
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (SOFTOR) x[i] = __fmul2_rn(gp[i], x[i]);                       // gO * prod_{m != n}(1 - g_m)
+                    if (SUM) { if (pcs) x[i] = __ffma2_rn(gs[i], make_float2(A[i].z, A[i].w), x[i]); }
+                    x[i] = __fmul2_rn(x[i], g[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 dy = st.tabB2[k][2 * i + h];
+                const float2 wgt = __fmul2_rn(x[i], d2[i]);
+                a0 = __ffma2_rn(wgt, bc(dx), a0);
+                a1 = __ffma2_rn(wgt, dy, a1);
+            }
+        } else
+#endif
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (FFB_BWD_SKIP && !(gm & (1u << i))) continue;                          // warp-uniform

@@ -35,6 +35,8 @@ os.environ["FFB_SPLAT_NO_TMA"] = "0"
 d_new = plan.backward(ptsB, gS, gO, True, O_)
 print(f"bwd (saved) without TMA: {tb3:.3f} ms; max |tma - plain| = {float((d_new - d_old).abs().max()):.3e} of {float(d_old.abs().max()):.3e}")
 print(f"bwd without saved softor: {tb2:.3f} ms")
+tl = t(lambda: plan.backward_l1(ptsB, S_, O_, True))
+print(f"fused L1 backward: {tl:.3f} ms ({B*16*ts[0]*ts[1]/tl/1e6:.0f} GB/s of 16 B/texel actual reads)")
 hw = ts[0] * ts[1]
 print(f"B={B} prepare {tp:.3f} ms  fwd {tf:.3f} ms ({B*8*hw/tf/1e6:.0f} GB/s)  bwd {tb:.3f} ms ({B*8*hw/tb/1e6:.0f} GB/s)"
       f"  fwd+bwd per sample {(tf+tb)/B*1e3:.2f} us -> {B/(tf+tb)*1e3:.0f} samples/s, roofline frac {(B*(16*hw+16*N)/((tp+tf+tb)*1e-3))/6445.6e9:.3f}")
