@@ -62,6 +62,13 @@ SIGNATURES = {
     "ffb_reduce_over_samples": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
     "ffb_splat_dense_fwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P]),
     "ffb_splat_dense_bwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P]),
+    "ffb_lines_dense_fwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P]),
+    "ffb_lines_dense_bwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P]),
+    "ffb_lines_reduce_fwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P]),
+    "ffb_lines_reduce_bwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P, _P]),
+    "ffb_depth_dense_fwd": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P]),
+    "ffb_depth_dense_bwd": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P, _P, _P]),
+    "ffb_depth_softor_fwd": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P]),
     "ffb_l1_loss_fwd_bwd": (C.c_int, [_P, _P, C.c_int, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "ffb_sample": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, _P, _P, _P]),
     "ffb_uniform_between": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),

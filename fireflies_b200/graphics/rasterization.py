@@ -299,3 +299,138 @@ def l1_loss(a: torch.Tensor, b: torch.Tensor, b_transposed: bool = False) -> tor
     transposed (``baked_sum_2``) layout -- the loss of the in-tree pattern optimisation
     (fireflies/graphics/rasterization.py:589-599).  Returns ``[B]``."""
     return _L1Fn.apply(a, b, b_transposed)
+
+
+# --------------------------------------------------------------------------------------------------
+# line and depth rasterisers (SURVEY.md 8(f) row 2)
+# --------------------------------------------------------------------------------------------------
+def _lines(lines: torch.Tensor) -> torch.Tensor:
+    lines = nat.require_cuda(lines.float().contiguous(), torch.float32, "lines")
+    if lines.dim() != 3 or lines.shape[1:] != (2, 2):
+        raise ValueError("lines must be [L, 2, 2] (start / end x X / Y)")
+    return lines
+
+
+class _LinesDenseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lines, sigma, ts0, ts1):
+        ln = _lines(lines.detach())
+        L = ln.shape[0]
+        out = torch.empty((L, ts1, ts0), dtype=torch.float32, device=ln.device)
+        nat.check(nat.lib().ffb_lines_dense_fwd(ln.data_ptr(), L, ts0, ts1, sigma, out.data_ptr(), nat.stream()), "ffb_lines_dense_fwd")
+        nat.count()
+        ctx.ln, ctx.args = ln, (sigma, ts0, ts1)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        sigma, ts0, ts1 = ctx.args
+        g = g.contiguous().float()
+        d = torch.empty_like(ctx.ln)
+        nat.check(nat.lib().ffb_lines_dense_bwd(ctx.ln.data_ptr(), ctx.ln.shape[0], ts0, ts1, sigma, g.data_ptr(), d.data_ptr(),
+                                                nat.stream()), "ffb_lines_dense_bwd")
+        nat.count(2)
+        return d, None, None, None
+
+
+class _LinesReduceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lines, sigma, ts0, ts1, want_sum, want_softor):
+        ln = _lines(lines.detach())
+        L = ln.shape[0]
+        out_s = torch.empty((ts1, ts0), dtype=torch.float32, device=ln.device) if want_sum else None
+        out_o = torch.empty((ts1, ts0), dtype=torch.float32, device=ln.device) if want_softor else None
+        nat.check(nat.lib().ffb_lines_reduce_fwd(ln.data_ptr(), L, ts0, ts1, sigma, nat.ptr(out_s), nat.ptr(out_o), nat.stream()),
+                  "ffb_lines_reduce_fwd")
+        nat.count()
+        ctx.ln, ctx.args = ln, (sigma, ts0, ts1, want_sum, want_softor)
+        empty = ln.new_empty(0)
+        outs = (out_s if want_sum else empty, out_o if want_softor else empty)
+        ctx.mark_non_differentiable(*[o for o, w in zip(outs, (want_sum, want_softor)) if not w])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_sum, g_softor):
+        sigma, ts0, ts1, want_sum, want_softor = ctx.args
+        gs = g_sum.contiguous().float() if (want_sum and g_sum is not None) else None
+        go = g_softor.contiguous().float() if (want_softor and g_softor is not None) else None
+        d = torch.zeros_like(ctx.ln)
+        if gs is not None or go is not None:
+            nat.check(nat.lib().ffb_lines_reduce_bwd(ctx.ln.data_ptr(), ctx.ln.shape[0], ts0, ts1, sigma, nat.ptr(gs), nat.ptr(go),
+                                                     d.data_ptr(), nat.stream()), "ffb_lines_reduce_bwd")
+            nat.count(2)
+        return d, None, None, None, None, None
+
+
+def rasterize_lines(lines: torch.Tensor, sigma: float, texture_size: torch.Tensor,
+                    device: torch.device = torch.device("cuda")) -> torch.Tensor:
+    """fireflies/graphics/rasterization.py:107-153 -- dense ``[L, ts[1], ts[0]]`` squared-distance transform of the
+    segments ``lines[L,2,2]``, ``exp(-(d2*d2)/(sigma*sigma))``.  Deviation: the reference scales the caller's ``lines``
+    by ``texture_size`` IN PLACE (:122-123); here ``lines`` is left untouched."""
+    _device_ok(device)
+    ts0, ts1 = _ts(texture_size)
+    return _LinesDenseFn.apply(lines, _sigma(sigma), ts0, ts1)
+
+
+def lines_reduce(lines: torch.Tensor, sigma, texture_size, reduce: Tuple[str, ...] = ("sum", "softor")):
+    """``(rasterize_lines(...).sum(0), softor(rasterize_lines(...)))`` without the ``[L,H,W]`` tensor (what
+    test_line_reg, rasterization.py:684-697, and the epipolar regulariser compute).  Entries not named in ``reduce``
+    come back as ``None``."""
+    ts0, ts1 = _ts(texture_size)
+    s, o = _LinesReduceFn.apply(lines, _sigma(sigma), ts0, ts1, "sum" in reduce, "softor" in reduce)
+    return (s if "sum" in reduce else None), (o if "softor" in reduce else None)
+
+
+class _DepthFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, depth_vals, sigma, ts0, ts1):
+        pts = _points(points.detach())
+        dv = nat.require_cuda(depth_vals.detach().float().reshape(-1).contiguous(), torch.float32, "depth_vals")
+        N = pts.shape[0]
+        if dv.numel() != N:
+            raise ValueError("depth_vals must hold one value per point")
+        out = torch.empty((N, ts1, ts0), dtype=torch.float32, device=pts.device)
+        nat.check(nat.lib().ffb_depth_dense_fwd(pts.data_ptr(), dv.data_ptr(), N, ts0, ts1, sigma, out.data_ptr(), nat.stream()),
+                  "ffb_depth_dense_fwd")
+        nat.count()
+        ctx.pts, ctx.dv, ctx.args, ctx.dshape = pts, dv, (sigma, ts0, ts1), depth_vals.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        sigma, ts0, ts1 = ctx.args
+        g = g.contiguous().float()
+        N = ctx.pts.shape[0]
+        d_pts, d_dv = torch.empty_like(ctx.pts), torch.empty_like(ctx.dv)
+        scratch = torch.empty((N, 3), dtype=torch.float32, device=g.device)
+        nat.check(nat.lib().ffb_depth_dense_bwd(ctx.pts.data_ptr(), ctx.dv.data_ptr(), N, ts0, ts1, sigma, g.data_ptr(),
+                                                scratch.data_ptr(), d_pts.data_ptr(), d_dv.data_ptr(), nat.stream()), "ffb_depth_dense_bwd")
+        nat.count(3)
+        return d_pts, d_dv.reshape(ctx.dshape), None, None, None
+
+
+def rasterize_depth(points: torch.Tensor, depth_vals: torch.Tensor, sigma: float, texture_size: torch.Tensor,
+                    device: torch.device = torch.device("cuda")) -> torch.Tensor:
+    """fireflies/graphics/rasterization.py:66-104 -- ``rasterize_points`` normalised by its per-point maximum over the
+    frame and scaled by ``depth_vals [N,1]`` -> ``[N, ts[1], ts[0]]``."""
+    _device_ok(device)
+    ts0, ts1 = _ts(texture_size)
+    return _DepthFn.apply(points, depth_vals, _sigma(sigma), ts0, ts1)
+
+
+def subsampled_point_raster(ndc_points: torch.Tensor, num_subsamples: int, sigma, sensor_size):
+    """fireflies/graphics/rasterization.py:538-549 -- per pyramid level ``i`` the soft-OR (keepdim) over the points of
+    ``rasterize_depth`` at ``sensor_size // 2**i``; one fused launch per level, no ``[N,H,W]`` tensor.  Forward only
+    (the reference uses it for the depth regulariser's target)."""
+    pts = _points(ndc_points[:, 0:2].detach())
+    dv = nat.require_cuda(ndc_points[:, 2].detach().float().contiguous(), torch.float32, "depth")
+    ss = torch.as_tensor(sensor_size).cpu()
+    out = []
+    for i in range(num_subsamples):
+        ts0, ts1 = _ts(ss // 2 ** i)
+        o = torch.empty((1, ts1, ts0), dtype=torch.float32, device=pts.device)
+        nat.check(nat.lib().ffb_depth_softor_fwd(pts.data_ptr(), dv.data_ptr(), pts.shape[0], ts0, ts1, _sigma(sigma), o.data_ptr(),
+                                                 nat.stream()), "ffb_depth_softor_fwd")
+        nat.count()
+        out.append(o)
+    return out

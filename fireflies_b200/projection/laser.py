@@ -155,8 +155,19 @@ class Laser(Camera):
         s, o = rasterization.splat_reduce(points, sigma, texture_size, num_std_sum=None, num_std_softor=None, reduce=(reduce,))
         return s if reduce == "sum" else o
 
-    def render_epipolar_lines(self, sigma: float, texture_size: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError("render_epipolar_lines (rasterize_lines) is a 'next' row of SURVEY.md section 8(f)")
+    def render_epipolar_lines(self, sigma: float, texture_size: torch.Tensor, camera_to_world: torch.Tensor = None) -> torch.Tensor:
+        """laser.py:298-325: the segments origin + [near_clip, far_clip] * ray, seen through ``camera_to_world`` (identity when
+        omitted) and ``_perspective``, rasterised with ``rasterize_lines``.  The reference reads the camera pose through an
+        attribute that does not exist (``self._fireflies.entity.Transformable.world()``, :304); the evident intent is the
+        viewing camera's world matrix, which the caller passes here."""
+        lo = self.originPerRay() + self._near_clip * self.rays()
+        hi = self.originPerRay() + self._far_clip * self.rays()
+        if camera_to_world is None:
+            camera_to_world = torch.eye(4, device=self.device)
+        w2c = camera_to_world.float().inverse()
+        hi = ffmath.transform_points(ffmath.transform_points(hi, w2c), self._perspective)[:, 0:2]
+        lo = ffmath.transform_points(ffmath.transform_points(lo, w2c), self._perspective)[:, 0:2]
+        return rasterization.rasterize_lines(torch.stack([lo, hi], dim=1), sigma, texture_size)
 
     def save(self, filepath: str):
         import yaml

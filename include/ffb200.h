@@ -125,6 +125,35 @@ FFB_API int ffb_splat_dense_fwd(const float* pts, int32_t N, int32_t ts0, int32_
 FFB_API int ffb_splat_dense_bwd(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sigma,
                         const float* g_out, float* d_pts, void* stream);
 
+/* ---- line and depth rasterisers ------------------------------------------------
+ * lines f32 [L,2,2] = (start, end) x (x, y) in units of the texture size (16-byte aligned); the squared
+ * point-to-segment distance d2 gives g = exp(-(d2*d2)/(sigma*sigma))  (rasterize_lines,
+ * fireflies/graphics/rasterization.py:107-153; the reference's in-place scaling of its argument, :122-123,
+ * is not reproduced: `lines` is read-only here).
+ *   ffb_lines_dense_fwd/bwd   the reference's dense [L,ts1,ts0] tensor and its backward (d_lines [L,2,2],
+ *                             OVERWRITTEN) -- API compatibility.
+ *   ffb_lines_reduce_fwd/bwd  sum and/or soft-OR over the lines in one pass (what test_line_reg, :684-697,
+ *                             and the epipolar regulariser reduce the dense tensor to): outputs [ts1,ts0];
+ *                             the backward takes the upstream gradients of those (NULL = not used). */
+FFB_API int ffb_lines_dense_fwd(const float* lines, int32_t L, int32_t ts0, int32_t ts1, float sigma, float* out, void* stream);
+FFB_API int ffb_lines_dense_bwd(const float* lines, int32_t L, int32_t ts0, int32_t ts1, float sigma, const float* g_out,
+                        float* d_lines, void* stream);
+FFB_API int ffb_lines_reduce_fwd(const float* lines, int32_t L, int32_t ts0, int32_t ts1, float sigma, float* out_sum,
+                         float* out_softor, void* stream);
+FFB_API int ffb_lines_reduce_bwd(const float* lines, int32_t L, int32_t ts0, int32_t ts1, float sigma, const float* g_sum,
+                         const float* g_softor, float* d_lines, void* stream);
+
+/* rasterize_depth (fireflies/graphics/rasterization.py:66-104): the dense point splat of pts [N,2] divided by
+ * its per-point maximum over the frame and scaled by depth [N] -> out [N,ts1,ts0]; its backward w.r.t. pts
+ * and depth (scratch: f32 [N,3]; d_pts [N,2] / d_depth [N] may be NULL, both OVERWRITTEN);
+ * ffb_depth_softor_fwd = one level of subsampled_point_raster (:538-549): soft-OR over the points -> [ts1,ts0]. */
+FFB_API int ffb_depth_dense_fwd(const float* pts, const float* depth, int32_t N, int32_t ts0, int32_t ts1, float sigma, float* out,
+                        void* stream);
+FFB_API int ffb_depth_dense_bwd(const float* pts, const float* depth, int32_t N, int32_t ts0, int32_t ts1, float sigma,
+                        const float* g_out, float* scratch, float* d_pts, float* d_depth, void* stream);
+FFB_API int ffb_depth_softor_fwd(const float* pts, const float* depth, int32_t N, int32_t ts0, int32_t ts1, float sigma, float* out,
+                         void* stream);
+
 /* mean |a-b| and its gradients (torch.nn.L1Loss as used by test_point_reg, rasterization.py:591-599).
  *   a is natural [B,ts1,ts0]; b is natural or transposed ([B,ts0,ts1]) per b_transposed.
  *   loss_out f32 [B] (OVERWRITTEN); g_a / g_b (may be NULL) receive d loss_b / d a, d b in the

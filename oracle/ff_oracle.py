@@ -74,6 +74,53 @@ def reduce_sum(tex: torch.Tensor, dim: int = 0) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------
+# f2: line and depth rasterisers
+# (fireflies/graphics/rasterization.py:38-104, 107-153, 538-549)
+# ----------------------------------------------------------------------------
+def rasterize_lines(lines: torch.Tensor, sigma, texture_size) -> torch.Tensor:
+    """Squared point-to-segment distance transform, ``exp(-(d2*d2)/(sigma*sigma))``, shape ``[L, ts1, ts0]``.
+
+    Follows rasterize_lines (graphics/rasterization.py:107-153) without its in-place scaling of the caller's
+    tensor (:122-123): ``lines[L,2,2]`` = (start, end) x (x, y), scaled by ``texture_size``; ``t0`` with the
+    ``finfo.eps`` guard (:142), the three boolean-masked branches (:145-149).
+    """
+    ts0, ts1 = _as_ts(texture_size)
+    scale = torch.tensor([ts0, ts1], dtype=F32)
+    a = (lines[:, 0, :].to(F32) * scale).permute(1, 0).unsqueeze(-1).unsqueeze(-1)      # [2,L,1,1]  :122,125
+    b = (lines[:, 1, :].to(F32) * scale).permute(1, 0).unsqueeze(-1).unsqueeze(-1)
+    L = lines.shape[0]
+    y, x = torch.meshgrid(torch.arange(0, ts1), torch.arange(0, ts0), indexing="ij")    # :128-132
+    xy = torch.stack([x.unsqueeze(0).repeat(L, 1, 1), y.unsqueeze(0).repeat(L, 1, 1)])  # integer grid, promoted below
+    pa = xy - a                                                                          # :140
+    pb = xy - b
+    m = b - a
+    t0 = (pa * m).sum(dim=0) / ((m * m).sum(dim=0) + torch.finfo().eps)                  # :142
+    patm = xy - (a + t0.unsqueeze(0) * m)
+    d = (t0 <= 0) * (pa * pa).sum(dim=0) + (t0 > 0) * (t0 < 1) * (patm * patm).sum(dim=0) + (t0 >= 1) * (pb * pb).sum(dim=0)
+    s = _sigma_f32(sigma)
+    return torch.exp(-(d * d) / (s * s))                                                 # :153
+
+
+def rasterize_depth(points: torch.Tensor, depth_vals: torch.Tensor, sigma, texture_size) -> torch.Tensor:
+    """rasterize_depth (graphics/rasterization.py:66-104): the dense point splat, normalised by its per-point maximum
+    over the frame (:96-99), scaled by the point's depth (:104).  ``depth_vals`` is ``[N,1]``."""
+    g = splat_dense(points, sigma, texture_size)
+    g = g / g.max(dim=2, keepdim=True)[0].max(dim=1, keepdim=True)[0]
+    return g * depth_vals.to(F32).unsqueeze(-1)
+
+
+def subsampled_point_raster(ndc_points: torch.Tensor, num_subsamples: int, sigma, sensor_size) -> List[torch.Tensor]:
+    """subsampled_point_raster (graphics/rasterization.py:538-549): soft-OR (keepdim) of rasterize_depth at
+    ``sensor_size // 2**i``."""
+    out = []
+    ss = torch.as_tensor(sensor_size)
+    for i in range(num_subsamples):
+        d = rasterize_depth(ndc_points[:, 0:2], ndc_points[:, 2:3], sigma, ss // 2 ** i)
+        out.append((1 - torch.prod(1 - d, dim=0, keepdim=True)))
+    return out
+
+
+# ----------------------------------------------------------------------------
 # a3-a5: footprint-limited ("baked") splat-reduce
 # (fireflies/graphics/rasterization.py:164-237, 240-318, 321-392, 395-472)
 # ----------------------------------------------------------------------------

@@ -270,6 +270,50 @@ def post_cases(ff):
     print("wrote postprocess")
 
 
+def line_depth_cases(ff):
+    """rasterize_lines (+ L1(softor, sum) gradient, test_line_reg rasterization.py:684-697), rasterize_depth,
+    subsampled_point_raster from the reference.  The reference scales `lines` in place (:122-123): it gets clones."""
+    R = ff.graphics.rasterization
+    out = {}
+    # KAT3 (SURVEY App. B)
+    kat = torch.tensor([[[0.2, 0.2], [0.8, 0.6]]])
+    out["kat3_lines"] = npy(kat)
+    out["kat3"] = npy(R.rasterize_lines(kat.clone(), torch.tensor([4.0]), torch.tensor([8, 6]), device=CPU))
+    g = torch.Generator().manual_seed(5)
+    lines = torch.rand(12, 2, 2, generator=g) * 1.2 - 0.1           # some end points outside [0,1]
+    lines[3, 1] = lines[3, 0]                                       # degenerate segment: the eps guard (:142)
+    ts = [96, 64]
+    out["lines"], out["lines_ts"], out["lines_sigma"] = npy(lines), np.array(ts), np.float32(10.0)
+    l = lines.clone().requires_grad_(True)
+    tex = R.rasterize_lines(l * 1.0, torch.tensor([10.0]), torch.tensor(ts), device=CPU)
+    out["lines_dense"] = npy(tex)
+    S, O = tex.sum(dim=0), R.softor(tex)
+    out["lines_sum"], out["lines_softor"] = npy(S), npy(O)
+    loss = torch.nn.L1Loss()(O, S)
+    loss.backward()
+    out["lines_l1"], out["lines_l1_grad"] = npy(loss), npy(l.grad)
+    gw = torch.Generator().manual_seed(6)
+    wS, wO = torch.randn(ts[1], ts[0], generator=gw), torch.randn(ts[1], ts[0], generator=gw)
+    l = lines.clone().requires_grad_(True)
+    tex = R.rasterize_lines(l * 1.0, torch.tensor([10.0]), torch.tensor(ts), device=CPU)
+    ((tex.sum(dim=0) * wS).sum() + (R.softor(tex) * wO).sum()).backward()
+    out["lines_wS"], out["lines_wO"], out["lines_weighted_grad"] = npy(wS), npy(wO), npy(l.grad)
+    # depth
+    pts = torch.rand(9, 3, generator=g)
+    pts[0, 0:2] = torch.tensor([1.05, 0.5])                         # outside the frame: the maximum sits on the border
+    out["depth_points"], out["depth_ts"], out["depth_sigma"] = npy(pts), np.array([40, 24]), np.float32(6.0)
+    out["depth_dense"] = npy(R.rasterize_depth(pts[:, 0:2], pts[:, 2:3], 6.0, torch.tensor([40, 24]), device=CPU))
+    sub = R.subsampled_point_raster.__wrapped__ if hasattr(R.subsampled_point_raster, "__wrapped__") else None
+    # subsampled_point_raster calls rasterize_depth with the default device (cuda): restate its four lines on CPU
+    levels = []
+    for i in range(3):
+        d = R.rasterize_depth(pts[:, 0:2], pts[:, 2:3], 6.0, torch.tensor([40, 24]) // 2 ** i, device=CPU)
+        levels.append(npy(R.softor(d, keepdim=True)))
+    for i, lv in enumerate(levels):
+        out[f"depth_level{i}"] = lv
+    np.savez_compressed(os.path.join(OUT, "lines_depth.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -289,6 +333,7 @@ def main():
     sampler_cases(ff)
     laser_cases(ff)
     post_cases(ff)
+    line_depth_cases(ff)
 
 
 if __name__ == "__main__":

@@ -237,3 +237,28 @@ def test_oracle_equals_live_reference():
         assert torch.equal(O.yaw(a32), m.getYawTransform(a32, cpu))
         assert torch.equal(O.pitch(a32), m.getPitchTransform(a32, cpu))
         assert torch.equal(O.roll(a32), m.getRollTransform(a32, cpu))
+
+
+# ---- line / depth rasterisers ---------------------------------------------------------
+def test_lines_and_depth_match_reference_fixture(golden):
+    g = golden("lines_depth")
+    T = lambda a: torch.from_numpy(np.asarray(a))  # noqa: E731
+    kat = O.rasterize_lines(T(g["kat3_lines"]), 4.0, [8, 6])
+    assert kat.shape == (1, 6, 8)
+    np.testing.assert_allclose(kat.numpy(), g["kat3"], rtol=1e-6, atol=1e-9)
+    assert abs(float(kat[0, 1, 2]) - 0.9989765286) < 1e-6 and abs(float(kat.sum()) - 27.94803810) < 1e-4
+    ts, sig = g["lines_ts"].tolist(), float(g["lines_sigma"])
+    lines = T(g["lines"]).clone().requires_grad_(True)
+    tex = O.rasterize_lines(lines, sig, ts)
+    np.testing.assert_allclose(tex.detach().numpy(), g["lines_dense"], rtol=1e-6, atol=1e-9)
+    S, So = tex.sum(dim=0), O.softor(tex)
+    np.testing.assert_allclose(S.detach().numpy(), g["lines_sum"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(So.detach().numpy(), g["lines_softor"], rtol=1e-6, atol=1e-9)
+    ((S * T(g["lines_wS"])).sum() + (So * T(g["lines_wO"])).sum()).backward()
+    ref = g["lines_weighted_grad"]
+    np.testing.assert_allclose(lines.grad.numpy(), ref, rtol=1e-4, atol=1e-5 * np.abs(ref).max())
+    pts = T(g["depth_points"])
+    d = O.rasterize_depth(pts[:, 0:2], pts[:, 2:3], float(g["depth_sigma"]), g["depth_ts"].tolist())
+    np.testing.assert_allclose(d.numpy(), g["depth_dense"], rtol=1e-6, atol=1e-9)
+    for i, lv in enumerate(O.subsampled_point_raster(pts, 3, float(g["depth_sigma"]), g["depth_ts"].tolist())):
+        np.testing.assert_allclose(lv.numpy(), g[f"depth_level{i}"], rtol=1e-6, atol=1e-9)
