@@ -36,7 +36,10 @@ constexpr int WROWS = 8;      // rows per warp
 constexpr int CTA = 256;      // 8 warps: 2 column halves x 4 row groups
 constexpr int CHUNK = 128;    // candidate records staged per pass
 constexpr int KCACHE = 6;     // cached g slots per warp in the backward (8 rows x 32 lanes each; dynamic smem)
-constexpr int PREP_CTA = 1024;
+#ifndef FFB_PREP_CTA
+#define FFB_PREP_CTA 1024
+#endif
+constexpr int PREP_CTA = FFB_PREP_CTA;
 constexpr int WT = 16;        // warp tile side of the warp-tile kernels (ffb_splat_wt.cuh)
 constexpr int WCH = 16;       // candidates a warp stages at once; longer super-tile lists go to the overflow kernels
 
@@ -354,7 +357,29 @@ __global__ void __launch_bounds__(PREP_CTA) prepare_kernel(PrepParams q) {
         // 4. order every tile's list by point index -> deterministic accumulation order
         for (int t = tid; t < nt; t += PREP_CTA) {
             const int b = cnt[t], e = min(cur[t], q.cap);
-            if (FAST) {
+            if (FAST && e - b <= WCH) {
+                // the common case: the whole list in registers (one load per element instead of one per comparison -- the
+                // per-lane scattered re-reads were the kernel's L1 wavefront budget), rank by counting, entries written in order
+                int l[WCH];
+#pragma unroll
+                for (int i = 0; i < WCH; ++i) l[i] = b + i < e ? list[b + i] : 0x7fffffff;
+                const bool bs = q.baked_s != 0;
+                const int baked = (bs || !q.baked_o) ? (int)bs : 1, half = (bs || !q.baked_o) ? q.half_s : q.half_o;
+#pragma unroll
+                for (int i = 0; i < WCH; ++i) {
+                    if (b + i < e) {
+                        int rank = 0;
+#pragma unroll
+                        for (int j = 0; j < WCH; ++j) rank += l[j] < l[i];
+                        const PointRec r = recs[l[i]];
+                        Entry en;
+                        en.p0 = r.p0; en.p1 = r.p1;
+                        en.f0 = (float)origin_axis(r.p0, baked, half); en.f1 = (float)origin_axis(r.p1, baked, half);
+                        en.ur = r.ur; en.uc = r.uc; en.idx = l[i]; en.pad = 0;
+                        entries[b + rank] = en;
+                    }
+                }
+            } else if (FAST) {
                 // rank sort straight into the entry list: independent loads, no serial chain through global memory
                 for (int i = b; i < e; ++i) {
                     const int v = list[i];
@@ -783,13 +808,30 @@ __global__ void __launch_bounds__(256) dense_bwd_kernel(const float* __restrict_
     }
 }
 
-// out[j] = sum_b in[b, j], fixed order
+// out[j] = sum_b in[b, j] in a fixed order (deterministic): 32 columns per CTA, the samples split over 8 warps (each
+// walks its contiguous share with four loads in flight), partial sums folded in warp order
 __global__ void __launch_bounds__(256) reduce_samples_kernel(const float* __restrict__ in, int B, long long row, float* __restrict__ out) {
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= row) return;
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s += in[(long long)b * row + j];
-    out[j] = s;
+    __shared__ float part[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long j = (long long)blockIdx.x * 32 + lane;
+    const int per = (B + 7) / 8, b0 = w * per, b1 = min(b0 + per, B);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (j < row) {
+        int b = b0;
+        for (; b + 3 < b1; b += 4) {
+            s0 += in[(long long)b * row + j]; s1 += in[(long long)(b + 1) * row + j];
+            s2 += in[(long long)(b + 2) * row + j]; s3 += in[(long long)(b + 3) * row + j];
+        }
+        for (; b < b1; ++b) s0 += in[(long long)b * row + j];
+    }
+    part[w][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (w == 0 && j < row) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += part[k][lane];
+        out[j] = s;
+    }
 }
 
 // mean |a - b| per sample and its gradients.  grid = (row blocks, B); each CTA handles 32x32 texels so the
@@ -1059,7 +1101,7 @@ extern "C" int ffb_splat_bwd_l1(const ffb_splat_desc* d, const float* pts, const
 
 extern "C" int ffb_reduce_over_samples(const float* in, int32_t B, int64_t row_elems, float* out, void* stream) {
     if (!in || !out || B <= 0 || row_elems <= 0) return fail_arg(FFB_E_ARG, "reduce_over_samples: bad argument");
-    const unsigned grid = (unsigned)((row_elems + 255) / 256);
+    const unsigned grid = (unsigned)((row_elems + 31) / 32);
     reduce_samples_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, B, row_elems, out);
     FFB_CUDA(cudaGetLastError());
     return 0;

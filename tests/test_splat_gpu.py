@@ -283,3 +283,12 @@ def test_fused_l1_refuses_what_it_cannot_pair(R):
     plan = R._SplatPlan(pts, 2, 36.0, 254, 254, 4, 5)       # sides not multiples of 4: no TMA description
     s, o = plan.forward(pts, True, True, True)
     assert plan.backward_l1(pts, s, o, True) is None
+
+
+@pytest.mark.parametrize("B,shape", [(1, (5, 2)), (7, (33, 2)), (37, (1000,)), (256, (4096, 2))])
+def test_reduce_over_samples(R, B, shape):
+    x = torch.randn((B,) + shape, generator=torch.Generator().manual_seed(B)).cuda()
+    out = R.reduce_over_samples(x)
+    assert out.shape == shape
+    close(out, x.double().sum(0), rtol=1e-5, atol=1e-5)
+    assert torch.equal(out, R.reduce_over_samples(x))       # fixed summation order
