@@ -360,11 +360,93 @@ __global__ void __launch_bounds__(128) clamp_fov_kernel(const float* __restrict_
     out[3 * n] = wx / nrm; out[3 * n + 1] = wy / nrm; out[3 * n + 2] = wz / nrm;
 }
 
+// Laser.randomize_laser_out_of_bounds / randomize_camera_out_of_bounds (projection/laser.py:208-249) in one launch, no host
+// sync: a ray whose NDC x or y lies outside (lo, hi) is respawned at (u0, u1, -1) un-projected through Minv; if ANY ray was
+// out of bounds all rays are renormalised, otherwise nothing is written (the reference returns before its normalise).
+// One CTA walks all rays: count and exclusive scan of the out-of-bounds flags give the k-th respawned ray row k of the
+// injected variates (the reference draws torch.rand(K, 3) for the K rays in index order); the Philox mode keys by ray.
+constexpr int RS_THREADS = 1024;
+__global__ void __launch_bounds__(RS_THREADS) respawn_kernel(float* __restrict__ rays, int N, const float* __restrict__ M,
+                                                             const float* __restrict__ ndc_in, float lo, float hi,
+                                                             const float* __restrict__ Minv, uint64_t seed, uint64_t counter,
+                                                             const float* __restrict__ variates, int* __restrict__ count_out) {
+    __shared__ int warp_cnt[32];
+    __shared__ int carry, total;
+    __shared__ float Tm[16], Ti[16];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid < 16) { Tm[tid] = M ? M[tid] : 0.f; Ti[tid] = Minv[tid]; }
+    if (tid == 0) { carry = 0; total = 0; }
+    __syncthreads();
+    // pass 1: is anything out of bounds?
+    int mine = 0;
+    for (int n = tid; n < N; n += RS_THREADS) {
+        float x, y, z;
+        if (M) xform_point(Tm, rays[3 * n], rays[3 * n + 1], rays[3 * n + 2], x, y, z);
+        else { x = ndc_in[3 * n]; y = ndc_in[3 * n + 1]; }
+        mine += (x >= hi || x <= lo || y >= hi || y <= lo) ? 1 : 0;
+    }
+    const int any = __syncthreads_count(mine);
+    if (any == 0) {
+        if (tid == 0 && count_out) *count_out = 0;
+        return;
+    }
+    // pass 2: respawn in index order, renormalise everything
+    for (int base = 0; base < N; base += RS_THREADS) {
+        const int n = base + tid;
+        bool oob = false;
+        float rx = 0.f, ry = 0.f, rz = 0.f;
+        if (n < N) {
+            rx = rays[3 * n]; ry = rays[3 * n + 1]; rz = rays[3 * n + 2];
+            float x, y, z;
+            if (M) xform_point(Tm, rx, ry, rz, x, y, z);
+            else { x = ndc_in[3 * n]; y = ndc_in[3 * n + 1]; }
+            oob = x >= hi || x <= lo || y >= hi || y <= lo;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, oob);
+        if (lane == 0) warp_cnt[w] = __popc(bal);
+        __syncthreads();
+        int before = carry;
+        for (int k = 0; k < w; ++k) before += warp_cnt[k];
+        const int row = before + __popc(bal & ((1u << lane) - 1u));
+        if (oob) {
+            float u0, u1;
+            if (variates) { u0 = variates[3 * row]; u1 = variates[3 * row + 1]; }
+            else {
+                uint32_t r[4];
+                Philox::gen(seed, (uint32_t)n, (uint32_t)counter, (uint32_t)(counter >> 32), 0x52455350u, r);
+                u0 = Philox::u01(r[0]); u1 = Philox::u01(r[1]);
+            }
+            xform_point(Ti, u0, u1, -1.0f, rx, ry, rz);
+        }
+        if (n < N) {
+            const float nrm = sqrtf(rx * rx + ry * ry + rz * rz);
+            rays[3 * n] = rx / nrm; rays[3 * n + 1] = ry / nrm; rays[3 * n + 2] = rz / nrm;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int k = 0; k < RS_THREADS / 32; ++k) t += warp_cnt[k];
+            carry += t;
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && count_out) *count_out = carry;
+}
+
 }  // namespace scene
 }  // namespace ffb
 
 using namespace ffb;
 using namespace ffb::scene;
+
+extern "C" int ffb_respawn_rays(float* rays, int32_t N, const float* M, const float* ndc, float lo, float hi, const float* Minv,
+                                uint64_t seed, uint64_t counter, const float* variates, int32_t* respawned_out, void* stream) {
+    if (!rays || !Minv || N <= 0) return fail_arg(FFB_E_ARG, "respawn_rays: bad argument");
+    if ((M == nullptr) == (ndc == nullptr)) return fail_arg(FFB_E_ARG, "respawn_rays: exactly one of M (project the rays) and ndc (given coordinates) is required");
+    respawn_kernel<<<1, RS_THREADS, 0, as_stream(stream)>>>(rays, N, M, ndc, lo, hi, Minv, seed, counter, variates, respawned_out);
+    FFB_CUDA(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int ffb_sample(ffb_sampler* samplers, int32_t S, int32_t B, int32_t mode, uint64_t seed, uint64_t sample0,
                           const float* variates, float* out, void* stream) {

@@ -98,32 +98,34 @@ class Laser(Camera):
         with torch.no_grad():
             self._rays[:] = out
 
-    def randomize_laser_out_of_bounds(self) -> None:
-        """laser.py:208-231."""
-        new_rays = self._rays.detach().clone()
-        ndc = ffmath.transform_points(new_rays, self._perspective)
-        xy = ndc[:, 0:2]
-        oob = ((xy >= 1.0) | (xy <= 0.0)).any(dim=1)
-        if int(oob.sum()) == 0:
-            return 0
-        new_pt = torch.rand((int(oob.sum()), 3), device=self.device)
-        new_pt[:, 2] = -1.0
-        new_rays[oob] = self.projectNDCPointsToWorld(new_pt)
-        with torch.no_grad():
-            self._rays[:] = self.normalize(new_rays)
+    def _respawn(self, M, ndc, lo: float, hi: float, variates) -> None:
+        """One launch, no host sync (``ffb_respawn_rays``).  New positions come from the device Philox stream keyed by
+        (torch's seed, ray index, call counter) unless ``variates`` ([K,3], the reference's ``torch.rand(K, 3)`` rows in ray
+        order) is given.  ``self.last_respawned`` (device int32) holds the number of respawned rays."""
+        rays = nat.require_cuda(self._rays.detach(), torch.float32, "rays")
+        Minv = self._M().inverse().contiguous()
+        v = None if variates is None else nat.require_cuda(variates.float().contiguous(), torch.float32, "variates")
+        if v is not None and (v.dim() != 2 or v.shape[1] != 3 or v.shape[0] < rays.shape[0]) and v.shape[0] == 0:
+            raise ValueError("variates must be [K, 3]")
+        self.last_respawned = torch.zeros(1, dtype=torch.int32, device=rays.device)
+        self._respawn_calls = getattr(self, "_respawn_calls", 0) + 1
+        nat.check(nat.lib().ffb_respawn_rays(rays.data_ptr(), rays.shape[0], nat.ptr(M), nat.ptr(ndc), float(lo), float(hi),
+                                             Minv.data_ptr(), int(torch.initial_seed()) & (2 ** 64 - 1), self._respawn_calls,
+                                             nat.ptr(v), self.last_respawned.data_ptr(), nat.stream()), "ffb_respawn_rays")
+        nat.count()
 
-    def randomize_camera_out_of_bounds(self, ndc_coords) -> None:
-        """laser.py:233-249."""
-        new_rays = self._rays.detach().clone()
-        xy = ndc_coords[:, 0:2]
-        oob = ((xy >= 1.0) | (xy <= -1.0)).any(dim=1)
-        if int(oob.sum()) == 0:
-            return 0
-        new_pt = torch.rand((int(oob.sum()), 3), device=self.device)
-        new_pt[:, 2] = -1.0
-        new_rays[oob] = self.projectNDCPointsToWorld(new_pt)
-        with torch.no_grad():
-            self._rays[:] = self.normalize(new_rays)
+    def randomize_laser_out_of_bounds(self, variates: torch.Tensor = None) -> None:
+        """laser.py:208-231: rays whose projection through ``_perspective`` leaves (0, 1)^2 are respawned uniformly in NDC
+        and all rays renormalised.  (The reference returns 0 when nothing was out of bounds, None otherwise; no caller
+        uses the value and reading it would cost a host sync: this returns None, see ``last_respawned``.)"""
+        self._respawn(self._perspective.float().contiguous(), None, 0.0, 1.0, variates)
+
+    def randomize_camera_out_of_bounds(self, ndc_coords, variates: torch.Tensor = None) -> None:
+        """laser.py:233-249: as above for camera-space coordinates supplied by the caller, bounds (-1, 1)."""
+        ndc = nat.require_cuda(ndc_coords.detach().float().contiguous(), torch.float32, "ndc_coords")
+        if ndc.shape != (self._rays.shape[0], 3):
+            raise ValueError("ndc_coords must be [N, 3]")
+        self._respawn(None, ndc, -1.0, 1.0, variates)
 
     def normalize(self, tensor: torch.Tensor) -> torch.Tensor:
         return tensor / torch.linalg.norm(tensor, dim=-1, keepdims=True)

@@ -264,6 +264,17 @@ FFB_API int ffb_rays_to_ndc(const float* rays, int32_t N, const float* M, float*
 FFB_API int ffb_clamp_to_fov(const float* rays, int32_t N, const float* M, const float* Minv, float clamp_lo, float clamp_hi,
                      float* rays_out, void* stream);
 
+/* Laser.randomize_laser_out_of_bounds (M = `_perspective`, bounds (0, 1)) and randomize_camera_out_of_bounds
+ * (ndc given, bounds (-1, 1)) -- fireflies/projection/laser.py:208-249 -- in one launch without a host sync.
+ * rays f32 [N,3] IN/OUT: a ray whose NDC x or y is >= hi or <= lo is replaced by Minv applied to (u0, u1, -1)
+ * (projectNDCPointsToWorld); if any ray was replaced ALL rays are renormalised, otherwise `rays` is untouched
+ * (the reference returns before its normalise).  Exactly one of M ([4,4], projects the rays) and ndc ([N,3],
+ * coordinates computed by the caller) is non-NULL.  u comes from `variates` ([K,3] rows consumed in ray order,
+ * the reference's torch.rand(K, 3)) or, when NULL, from Philox keyed by (seed, ray index, counter).
+ * respawned_out (device int32, nullable) receives K. */
+FFB_API int ffb_respawn_rays(float* rays, int32_t N, const float* M, const float* ndc, float lo, float hi, const float* Minv,
+                     uint64_t seed, uint64_t counter, const float* variates, int32_t* respawned_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * 4. Post-processing  (fireflies/postprocessing)
  * ------------------------------------------------------------------------------------------ */

@@ -209,6 +209,10 @@ def sampler_cases(ff):
     print("wrote samplers")
 
 
+def fireflies_transform(ff, pts, T):
+    return sys.modules["fireflies.utils.math"].transform_points(pts, T)
+
+
 def laser_cases(ff):
     import fireflies.utils.io as io
     Laser = ff.projection.Laser
@@ -231,6 +235,31 @@ def laser_cases(ff):
     tex = laser.generateTexture(10.0, torch.tensor([64, 48]))
     pts01 = (ndc[:, 0:2] * 0.5 + 0.5)
     out.update(gen_tex_sum=npy(tex.sum(0)), pts01=npy(pts01))
+    # out-of-bounds respawn (laser.py:208-249): the reference draws torch.rand(K, 3) for its K out-of-bounds rays
+    wider = Laser.generate_uniform_rays(0.17, 9, 9, device=CPU)
+    laser3 = Laser(tr, wider.clone(), K01, 60.0, 0.01, 1000.0, device=CPU)
+    xy = fireflies_transform(ff, wider, K01)[:, 0:2]
+    K_oob = int(((xy >= 1.0) | (xy <= 0.0)).any(dim=1).sum())
+    torch.manual_seed(11)
+    var = torch.rand(K_oob, 3)
+    torch.manual_seed(11)
+    laser3.randomize_laser_out_of_bounds()
+    out.update(respawn_rays=npy(wider), respawn_variates=npy(var), respawn_laser=npy(laser3._rays), respawn_k=np.int32(K_oob))
+    laser4 = Laser(tr, wide.clone(), K01, 60.0, 0.01, 1000.0, device=CPU)
+    cam_ndc = ndc2.clone()
+    cam_ndc[:, 0:2] = cam_ndc[:, 0:2] * 2.0 - 0.6
+    xy = cam_ndc[:, 0:2]
+    K_cam = int(((xy >= 1.0) | (xy <= -1.0)).any(dim=1).sum())
+    torch.manual_seed(12)
+    var2 = torch.rand(K_cam, 3)
+    torch.manual_seed(12)
+    laser4.randomize_camera_out_of_bounds(cam_ndc)
+    out.update(respawn_cam_ndc=npy(cam_ndc), respawn_cam_variates=npy(var2), respawn_cam=npy(laser4._rays), respawn_cam_k=np.int32(K_cam))
+    inside = Laser.generate_uniform_rays(0.01, 5, 5, device=CPU)       # nothing out of bounds: rays must stay untouched (not renormalised)
+    inside = inside * 1.5
+    laser5 = Laser(tr, inside.clone(), K01, 60.0, 0.01, 1000.0, device=CPU)
+    laser5.randomize_laser_out_of_bounds()
+    out.update(respawn_inside=npy(inside), respawn_inside_after=npy(laser5._rays))
     np.savez_compressed(os.path.join(OUT, "laser.npz"), **out)
     print("wrote laser")
 

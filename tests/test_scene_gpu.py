@@ -317,3 +317,35 @@ def test_animation_gather(ff):
         assert d.min() < 1e-4
         used.add(int(d.argmin()))
     assert len(used) == F
+
+
+def test_laser_out_of_bounds_respawn(ff, golden):
+    """projection/laser.py:208-249 through ffb_respawn_rays, with the reference's own torch.rand rows injected."""
+    g = golden("laser")
+    Laser = ff.projection.Laser
+    tr = ff.entity.Transformable("projector")
+    K01 = T(g["K01"]).cuda()
+    laser = Laser(tr, T(g["respawn_rays"]).cuda(), K01, 60.0, 0.01, 1000.0)
+    laser.randomize_laser_out_of_bounds(variates=T(g["respawn_variates"]).cuda())
+    assert int(laser.last_respawned) == int(g["respawn_k"]) and int(g["respawn_k"]) > 0
+    close(laser._rays, g["respawn_laser"], rtol=1e-5, atol=1e-6)
+    laser = Laser(tr, T(g["wide"]).cuda(), K01, 60.0, 0.01, 1000.0)
+    laser.randomize_camera_out_of_bounds(T(g["respawn_cam_ndc"]).cuda(), variates=T(g["respawn_cam_variates"]).cuda())
+    assert int(laser.last_respawned) == int(g["respawn_cam_k"]) and int(g["respawn_cam_k"]) > 0
+    close(laser._rays, g["respawn_cam"], rtol=1e-5, atol=1e-6)
+    inside = T(g["respawn_inside"]).cuda()
+    laser = Laser(tr, inside.clone(), K01, 60.0, 0.01, 1000.0)
+    laser.randomize_laser_out_of_bounds()
+    assert int(laser.last_respawned) == 0 and torch.equal(laser._rays, inside)      # untouched, not renormalised
+    # device Philox stream: respawned rays land inside the field of view, every ray has unit length, same seed -> same rays
+    torch.manual_seed(5)
+    a = Laser(tr, T(g["respawn_rays"]).cuda(), K01, 60.0, 0.01, 1000.0)
+    a.randomize_laser_out_of_bounds()
+    torch.manual_seed(5)
+    b = Laser(tr, T(g["respawn_rays"]).cuda(), K01, 60.0, 0.01, 1000.0)
+    b.randomize_laser_out_of_bounds()
+    assert torch.equal(a._rays, b._rays)
+    close(torch.linalg.norm(a._rays, dim=1), torch.ones(a._rays.shape[0]), rtol=1e-6, atol=1e-6)
+    ndc = ff.utils.math.transform_points(a._rays, K01)[:, 0:2]
+    flipped = ndc.clone(); flipped[:, 1] = 1.0 - flipped[:, 1]      # respawn un-projects through (K @ FLIP_Y)^-1
+    assert int(((ndc[:, 0] >= 1.0) | (ndc[:, 0] <= 0.0)).sum()) == 0
