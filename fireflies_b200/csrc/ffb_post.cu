@@ -392,11 +392,118 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+// ---- Perlin material textures ---------------------------------------------------------------
+// rand_perlin_2d_octaves (fireflies/sampling/noise_texture_lerp.py:8-62) with the lattice angles supplied by the caller
+// (the reference draws them with torch.rand on the CPU generator; the Python mirror does the same, so the stream is
+// consumed identically), then NoiseTextureLerpSampler.sample_train's min/max normalisation and colour lerp (:86-98).
+__device__ __forceinline__ float torch_lerp(float a, float b, float w) {     // ATen lerp: two-sided form
+    const float d = b - a;
+    return w < 0.5f ? __fadd_rn(a, __fmul_rn(w, d)) : __fadd_rn(b, -__fmul_rn(d, __fadd_rn(1.f, -w)));
+}
+__device__ __forceinline__ float fade5(float t) {                             // 6 t^5 - 15 t^4 + 10 t^3, term by term like the lambda
+    const float t3 = __fmul_rn(__fmul_rn(t, t), t), t4 = powf(t, 4.f), t5 = powf(t, 5.f);
+    return __fadd_rn(__fadd_rn(__fmul_rn(6.f, t5), -__fmul_rn(15.f, t4)), __fmul_rn(10.f, t3));
+}
+// order-preserving float <-> int for atomicMin / atomicMax
+__device__ __forceinline__ int f2ord(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+struct PerlinParams {
+    const float* angles;       // per octave (R0+1) x (R1+1) uniforms in [0,1), concatenated
+    int H, W, res0, res1, octaves;
+    float amp[8];              // float32(persistence^k)
+    float* noise;              // [H, W]
+    int* minmax;               // [2] ordered-int min / max
+};
+
+__global__ void __launch_bounds__(256) perlin_kernel(PerlinParams q) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < (long long)q.H * q.W;
+    float acc = 0.f;
+    if (live) {
+        const int i = (int)(t / q.W), j = (int)(t - (long long)i * q.W);
+        const float* ang = q.angles;
+        int f = 1;
+        for (int o = 0; o < q.octaves; ++o, f *= 2) {
+            const int R0 = f * q.res0, R1 = f * q.res1;
+            const int d0 = q.H / R0, d1 = q.W / R1;
+            // torch.arange(0, R, R / shape) is start + i * step in double, stored as float32; then % 1
+            const float a0 = (float)((double)i * ((double)R0 / (double)q.H)), a1 = (float)((double)j * ((double)R1 / (double)q.W));
+            const float gx = a0 - floorf(a0), gy = a1 - floorf(a1);
+            const int ci = i / d0, cj = j / d1;
+            const float TWO_PI = 6.283185307179586f;
+            float n[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int di = k & 1, dj = k >> 1;                   // n00, n10, n01, n11
+                const float th = __fmul_rn(TWO_PI, __ldg(ang + (size_t)(ci + di) * (R1 + 1) + cj + dj));
+                float sn, cs;
+                sincosf(th, &sn, &cs);
+                n[k] = __fadd_rn(__fmul_rn(gx - (float)di, cs), __fmul_rn(gy - (float)dj, sn));
+            }
+            const float t0 = fade5(gx), t1 = fade5(gy);
+            const float v = __fmul_rn(1.4142135623730951f, torch_lerp(torch_lerp(n[0], n[1], t0), torch_lerp(n[2], n[3], t0), t1));
+            acc = __fadd_rn(acc, __fmul_rn(q.amp[o], v));
+            ang += (size_t)(R0 + 1) * (R1 + 1);
+        }
+        q.noise[t] = acc;
+    }
+    float mn = live ? acc : INFINITY, mx = live ? acc : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(q.minmax, f2ord(mn));
+        atomicMax(q.minmax + 1, f2ord(mx));
+    }
+}
+
+// out[c, i, j] = lerp(color_a[c], color_b[c], (noise - min) / (max - min))
+__global__ void __launch_bounds__(256) noise_lerp_kernel(const float* __restrict__ noise, const int* __restrict__ minmax, long long n,
+                                                         const float* __restrict__ ca, const float* __restrict__ cb, float* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float mn = ord2f(minmax[0]), mx = ord2f(minmax[1]);
+    const float w = __fdiv_rn(noise[t] - mn, mx - mn);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[(size_t)c * n + t] = torch_lerp(__ldg(ca + c), __ldg(cb + c), w);
+}
+
 }  // namespace post
 }  // namespace ffb
 
 using namespace ffb;
 using namespace ffb::post;
+
+extern "C" int ffb_perlin_texture(const float* angles, int32_t H, int32_t W, int32_t res0, int32_t res1, int32_t octaves,
+                                  double persistence, const float* color_a, const float* color_b, float* noise_scratch,
+                                  int32_t* minmax_scratch, float* out, void* stream) {
+    if (!angles || !noise_scratch || !minmax_scratch || H <= 0 || W <= 0 || res0 <= 0 || res1 <= 0)
+        return fail_arg(FFB_E_ARG, "perlin_texture: bad argument");
+    if (octaves < 1 || octaves > 8) return fail_arg(FFB_E_LIMIT, "perlin_texture: 1..8 octaves");
+    if (out && (!color_a || !color_b)) return fail_arg(FFB_E_ARG, "perlin_texture: colours required with an output");
+    const int top = 1 << (octaves - 1);
+    if (H % (res0 * top) != 0 || W % (res1 * top) != 0)
+        return fail_arg(FFB_E_ARG, "perlin_texture: shape must be a multiple of res * 2^(octaves-1) (as in the reference, whose tiling fails otherwise)");
+    PerlinParams q;
+    q.angles = angles; q.H = H; q.W = W; q.res0 = res0; q.res1 = res1; q.octaves = octaves;
+    double a = 1.0;
+    for (int o = 0; o < 8; ++o) { q.amp[o] = (float)a; a *= persistence; }
+    q.noise = noise_scratch; q.minmax = minmax_scratch;
+    cudaStream_t st = as_stream(stream);
+    const int init[2] = {0x7f800000, (int)0x807fffff};       // ordered(+inf), ordered(-inf)
+    FFB_CUDA(cudaMemcpyAsync(minmax_scratch, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const long long n = (long long)H * W;
+    perlin_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q);
+    FFB_CUDA(cudaGetLastError());
+    if (out) {
+        noise_lerp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(noise_scratch, minmax_scratch, n, color_a, color_b, out);
+        FFB_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
 
 extern "C" int ffb_postprocess(const ffb_post_desc* d, const float* img, const uint8_t* gates,
                                const double* noise_injected, float* out, void* stream) {

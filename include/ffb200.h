@@ -295,6 +295,15 @@ typedef struct ffb_post_desc {
 FFB_API int ffb_postprocess(const ffb_post_desc* d, const float* img, const uint8_t* gates,
                     const double* noise_injected, float* out, void* stream);
 
+/* Perlin material texture: rand_perlin_2d_octaves + NoiseTextureLerpSampler.sample_train
+ * (fireflies/sampling/noise_texture_lerp.py:8-98).  `angles`: per octave o (frequency f = 2^o) the
+ * (f*res0+1) x (f*res1+1) uniforms in [0,1) the reference draws with torch.rand, concatenated; H, W must be
+ * multiples of res * 2^(octaves-1).  noise_scratch f32 [H,W] receives the octave sum, minmax_scratch
+ * (2 x int32) its extrema; out (nullable) f32 [3,H,W] = lerp(color_a, color_b, (noise-min)/(max-min)). */
+FFB_API int ffb_perlin_texture(const float* angles, int32_t H, int32_t W, int32_t res0, int32_t res1, int32_t octaves,
+                       double persistence, const float* color_a, const float* color_b, float* noise_scratch,
+                       int32_t* minmax_scratch, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

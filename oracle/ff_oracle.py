@@ -528,3 +528,51 @@ def post_process(img: np.ndarray, blur: Optional[dict], noise: Optional[dict], g
 def bernoulli_gates(probabilities: Sequence[float], rng: _pyrandom.Random) -> List[bool]:
     """postprocessing/base.py:10-11: one ``random.uniform(0,1) < p`` per function, in chain order."""
     return [rng.uniform(0, 1) < p for p in probabilities]
+
+
+# ----------------------------------------------------------------------------
+# f4: Perlin material textures (SURVEY 8(f) row 4)
+# (fireflies/sampling/noise_texture_lerp.py:8-98)
+# ----------------------------------------------------------------------------
+def perlin_2d(shape, res, angles01: torch.Tensor) -> torch.Tensor:
+    """rand_perlin_2d (noise_texture_lerp.py:8-50) with its ``torch.rand(res[0]+1, res[1]+1)`` draw passed in."""
+    import math
+    fade = lambda t: 6 * t ** 5 - 15 * t ** 4 + 10 * t ** 3  # noqa: E731  (:8)
+    delta = (res[0] / shape[0], res[1] / shape[1])
+    d = (shape[0] // res[0], shape[1] // res[1])
+    grid = torch.stack(torch.meshgrid(torch.arange(0, res[0], delta[0]), torch.arange(0, res[1], delta[1]), indexing="ij"), dim=-1) % 1
+    angles = 2 * math.pi * angles01
+    gradients = torch.stack((torch.cos(angles), torch.sin(angles)), dim=-1)
+
+    def tile_grads(s1, s2):
+        return gradients[s1[0]:s1[1], s2[0]:s2[1]].repeat_interleave(d[0], 0).repeat_interleave(d[1], 1)
+
+    def dot(grad, shift):
+        return (torch.stack((grid[:shape[0], :shape[1], 0] + shift[0], grid[:shape[0], :shape[1], 1] + shift[1]), dim=-1)
+                * grad[:shape[0], :shape[1]]).sum(dim=-1)
+
+    n00 = dot(tile_grads([0, -1], [0, -1]), [0, 0])
+    n10 = dot(tile_grads([1, None], [0, -1]), [-1, 0])
+    n01 = dot(tile_grads([0, -1], [1, None]), [0, -1])
+    n11 = dot(tile_grads([1, None], [1, None]), [-1, -1])
+    t = fade(grid[:shape[0], :shape[1]])
+    return math.sqrt(2) * torch.lerp(torch.lerp(n00, n10, t[..., 0]), torch.lerp(n01, n11, t[..., 0]), t[..., 1])
+
+
+def perlin_octaves(shape, res, octaves: int, persistence: float, angles: List[torch.Tensor]) -> torch.Tensor:
+    """rand_perlin_2d_octaves (noise_texture_lerp.py:53-62)."""
+    noise = torch.zeros(shape)
+    frequency, amplitude = 1, 1
+    for o in range(octaves):
+        noise += amplitude * perlin_2d(shape, (frequency * res[0], frequency * res[1]), angles[o])
+        frequency *= 2
+        amplitude *= persistence
+    return noise
+
+
+def noise_texture_lerp(noise: torch.Tensor, color_a: torch.Tensor, color_b: torch.Tensor) -> torch.Tensor:
+    """NoiseTextureLerpSampler.sample_train after the noise (noise_texture_lerp.py:86-98)."""
+    tex = (noise - noise.min()) / (noise.max() - noise.min())
+    col_a = torch.ones_like(tex).unsqueeze(0).repeat(3, 1, 1) * color_a.unsqueeze(-1).unsqueeze(-1)
+    col_b = torch.ones_like(tex).unsqueeze(0).repeat(3, 1, 1) * color_b.unsqueeze(-1).unsqueeze(-1)
+    return torch.lerp(col_a, col_b, tex.unsqueeze(0).repeat(3, 1, 1))

@@ -343,6 +343,33 @@ def line_depth_cases(ff):
     np.savez_compressed(os.path.join(OUT, "lines_depth.npz"), **out)
 
 
+def perlin_cases(ff):
+    """rand_perlin_2d_octaves and NoiseTextureLerpSampler.sample_train from the reference under a fixed seed, plus the
+    torch.rand lattice draws it consumed (re-drawn under the same seed)."""
+    import fireflies.sampling.noise_texture_lerp as NT
+    out = {}
+    for name, shape, res, octaves, pers, seed in [("a", [64, 64], (2, 2), 3, 0.5, 21), ("b", [96, 128], (4, 8), 2, 1.7, 22),
+                                                   ("c", [128, 128], (8, 8), 4, 0.3, 23)]:
+        torch.manual_seed(seed)
+        noise = NT.rand_perlin_2d_octaves(shape, res, octaves, pers)
+        torch.manual_seed(seed)
+        angles, f = [], 1
+        for _ in range(octaves):
+            angles.append(torch.rand(f * res[0] + 1, f * res[1] + 1)); f *= 2
+        out[f"{name}_noise"] = npy(noise)
+        out[f"{name}_cfg"] = np.array([shape[0], shape[1], res[0], res[1], octaves], dtype=np.int64)
+        out[f"{name}_pers"] = np.float64(pers)
+        out[f"{name}_angles"] = npy(torch.cat([a.reshape(-1) for a in angles]))
+    # the whole sampler: python `random` for (i, octaves, persistence), torch.rand for the lattice
+    ca, cb = torch.tensor([0.8, 0.14, 0.34]), torch.tensor([0.1, 0.4, 0.9])
+    smp = NT.NoiseTextureLerpSampler(ca, cb, [128, 128], device=CPU)
+    random.seed(31); torch.manual_seed(31)
+    tex = smp.sample_train()
+    out.update(sampler_tex=npy(tex), sampler_ca=npy(ca), sampler_cb=npy(cb))
+    np.savez_compressed(os.path.join(OUT, "perlin.npz"), **out)
+    print("wrote perlin")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -363,6 +390,7 @@ def main():
     laser_cases(ff)
     post_cases(ff)
     line_depth_cases(ff)
+    perlin_cases(ff)
 
 
 if __name__ == "__main__":

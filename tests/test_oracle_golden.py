@@ -262,3 +262,20 @@ def test_lines_and_depth_match_reference_fixture(golden):
     np.testing.assert_allclose(d.numpy(), g["depth_dense"], rtol=1e-6, atol=1e-9)
     for i, lv in enumerate(O.subsampled_point_raster(pts, 3, float(g["depth_sigma"]), g["depth_ts"].tolist())):
         np.testing.assert_allclose(lv.numpy(), g[f"depth_level{i}"], rtol=1e-6, atol=1e-9)
+
+
+def _perlin_angles(g, name):
+    H, W, r0, r1, oc = g[f"{name}_cfg"].tolist()
+    ang = torch.from_numpy(g[f"{name}_angles"])
+    angles, f, off = [], 1, 0
+    for _ in range(oc):
+        n = (f * r0 + 1) * (f * r1 + 1)
+        angles.append(ang[off:off + n].reshape(f * r0 + 1, f * r1 + 1)); off += n; f *= 2
+    return [H, W], (r0, r1), oc, float(g[f"{name}_pers"]), angles
+
+
+def test_perlin_matches_reference_fixture(golden):
+    g = golden("perlin")
+    for name in "abc":
+        shape, res, oc, pers, angles = _perlin_angles(g, name)
+        np.testing.assert_allclose(O.perlin_octaves(shape, res, oc, pers, angles).numpy(), g[f"{name}_noise"], rtol=1e-6, atol=1e-7)
