@@ -38,6 +38,7 @@ struct PostParams {
     const float* img;
     const uint8_t* gates;        // [B,2] or null
     const double* noise_inj;     // [B,H,W] or null
+    const float* mul;            // [B,H,W] or null: the result is multiplied texel-wise (silhouette: image x blurred mask)
     float* out;
 };
 
@@ -79,9 +80,22 @@ __device__ __forceinline__ void noise_clip4(const PostParams& q, int b, int y, i
     for (int k = 0; k < 4; ++k) v[k] = fminf(fmaxf(v[k], 0.f), 1.f);
 }
 
-__device__ __forceinline__ void store4(const PostParams& q, int b, int y, int x0, const float (&v)[4]) {
-    float* o = q.out + ((size_t)b * q.H + y) * q.W + x0;
-    if (x0 + 4 <= q.W && (q.W & 3) == 0) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+__device__ __forceinline__ void store4(const PostParams& q, int b, int y, int x0, const float (&vin)[4]) {
+    const size_t off = ((size_t)b * q.H + y) * q.W + x0;
+    float* o = q.out + off;
+    float v[4] = {vin[0], vin[1], vin[2], vin[3]};
+    const bool vec = x0 + 4 <= q.W && (q.W & 3) == 0;
+    if (q.mul) {                                             // warp-uniform
+        if (vec) {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(q.mul + off));
+            v[0] *= m.x; v[1] *= m.y; v[2] *= m.z; v[3] *= m.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (x0 + k < q.W) v[k] *= __ldg(q.mul + off + k);
+        }
+    }
+    if (vec) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
     else {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -392,6 +406,31 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+// ---- silhouette -------------------------------------------------------------------------------
+// ApplySilhouette.post_process (fireflies/postprocessing/apply_silhouette.py:17-40): a filled disc of ones per frame,
+// blurred 11x11 / sigma 5, multiplied into the image.  The disc is written analytically ((x-cx)^2 + (y-cy)^2 <= r^2; the
+// reference rasterises it with cv2.circle, which is absent here: parity with OpenCV's circle is unpinned), the blur is the
+// sliding-window kernel above and the product is its epilogue (PostParams::mul).
+__global__ void __launch_bounds__(256) disc_mask_kernel(const int* __restrict__ discs, int B, int H, int W, float* __restrict__ mask) {
+    const int b = blockIdx.y;
+    const int cx = discs[3 * b], cy = discs[3 * b + 1], r = discs[3 * b + 2];
+    const long long n4 = (long long)H * ((W + 3) / 4);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(t / ((W + 3) / 4)), x0 = (int)(t % ((W + 3) / 4)) * 4;
+        const long long dy2 = (long long)(y - cy) * (y - cy), r2 = (long long)r * r;
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = ((long long)(x0 + k - cx) * (x0 + k - cx) + dy2 <= r2) ? 1.f : 0.f;
+        float* o = mask + ((size_t)b * H + y) * W + x0;
+        if (x0 + 4 <= W && (W & 3) == 0) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (x0 + k < W) o[k] = v[k];
+        }
+    }
+}
+
 // ---- Perlin material textures ---------------------------------------------------------------
 // rand_perlin_2d_octaves (fireflies/sampling/noise_texture_lerp.py:8-62) with the lattice angles supplied by the caller
 // (the reference draws them with torch.rand on the CPU generator; the Python mirror does the same, so the stream is
@@ -505,8 +544,34 @@ extern "C" int ffb_perlin_texture(const float* angles, int32_t H, int32_t W, int
     return 0;
 }
 
+static int postprocess_impl(const ffb_post_desc* d, const float* img, const uint8_t* gates, const double* noise_injected,
+                            const float* mul, float* out, void* stream);
+
 extern "C" int ffb_postprocess(const ffb_post_desc* d, const float* img, const uint8_t* gates,
                                const double* noise_injected, float* out, void* stream) {
+    return postprocess_impl(d, img, gates, noise_injected, nullptr, out, stream);
+}
+
+extern "C" int ffb_silhouette(const float* img, const int32_t* discs, int32_t B, int32_t H, int32_t W, float* mask_scratch, float* out,
+                              void* stream) {
+    if (!img || !discs || !mask_scratch || !out || B <= 0 || H <= 0 || W <= 0) return fail_arg(FFB_E_ARG, "silhouette: bad argument");
+    if (B > 65535) return fail_arg(FFB_E_LIMIT, "silhouette: B > 65535");
+    if (mask_scratch == out || mask_scratch == img) return fail_arg(FFB_E_ARG, "silhouette: the mask scratch must not alias the frames");
+    cudaStream_t st = as_stream(stream);
+    const long long n4 = (long long)H * ((W + 3) / 4);
+    unsigned gx = (unsigned)((n4 + 255) / 256);
+    if (gx > (unsigned)kNumSMs * 8) gx = (unsigned)kNumSMs * 8;
+    disc_mask_kernel<<<dim3(gx, B), 256, 0, st>>>(discs, B, H, W, mask_scratch);
+    FFB_CUDA(cudaGetLastError());
+    ffb_post_desc d;
+    memset(&d, 0, sizeof(d));
+    d.B = B; d.H = H; d.W = W;
+    d.blur_ky = 11; d.blur_kx = 11; d.blur_sy = 5.f; d.blur_sx = 5.f;      // apply_silhouette.py:31-35
+    return postprocess_impl(&d, mask_scratch, nullptr, nullptr, img, out, stream);
+}
+
+static int postprocess_impl(const ffb_post_desc* d, const float* img, const uint8_t* gates, const double* noise_injected,
+                            const float* mul, float* out, void* stream) {
     if (!d || !img || !out) return fail_arg(FFB_E_ARG, "postprocess: null pointer");
     if (d->B <= 0 || d->H <= 0 || d->W <= 0) return fail_arg(FFB_E_ARG, "postprocess: B, H, W must be positive");
     if (d->B > 65535) return fail_arg(FFB_E_LIMIT, "postprocess: B > 65535");
@@ -515,7 +580,7 @@ extern "C" int ffb_postprocess(const ffb_post_desc* d, const float* img, const u
     memset(&q, 0, sizeof(q));
     q.B = d->B; q.H = d->H; q.W = d->W;
     q.noise = d->noise; q.mean = d->noise_mean; q.stdv = d->noise_std; q.seed = d->seed; q.frame0 = d->frame0;
-    q.img = img; q.gates = gates; q.noise_inj = noise_injected; q.out = out;
+    q.img = img; q.gates = gates; q.noise_inj = noise_injected; q.mul = mul; q.out = out;
     cudaStream_t st = as_stream(stream);
     if (!blur) {
         const size_t total = (size_t)((d->W + 3) / 4) * d->H * d->B;

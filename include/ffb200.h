@@ -295,6 +295,14 @@ typedef struct ffb_post_desc {
 FFB_API int ffb_postprocess(const ffb_post_desc* d, const float* img, const uint8_t* gates,
                     const double* noise_injected, float* out, void* stream);
 
+/* ApplySilhouette.post_process (fireflies/postprocessing/apply_silhouette.py:17-40) for B frames:
+ * out = img * blur11x11,sigma5(disc(cx, cy, r)).  discs int32 [B,3] = (cx, cy, r) per frame -- the caller's
+ * random.randint draws (:23-25).  The disc is the analytic set (x-cx)^2 + (y-cy)^2 <= r^2 (the reference
+ * rasterises it with cv2.circle: parity with OpenCV's rasteriser is unpinned).  mask_scratch f32 [B,H,W];
+ * out may alias img. */
+FFB_API int ffb_silhouette(const float* img, const int32_t* discs, int32_t B, int32_t H, int32_t W, float* mask_scratch,
+                   float* out, void* stream);
+
 /* Perlin material texture: rand_perlin_2d_octaves + NoiseTextureLerpSampler.sample_train
  * (fireflies/sampling/noise_texture_lerp.py:8-98).  `angles`: per octave o (frequency f = 2^o) the
  * (f*res0+1) x (f*res1+1) uniforms in [0,1) the reference draws with torch.rand, concatenated; H, W must be

@@ -576,3 +576,13 @@ def noise_texture_lerp(noise: torch.Tensor, color_a: torch.Tensor, color_b: torc
     col_a = torch.ones_like(tex).unsqueeze(0).repeat(3, 1, 1) * color_a.unsqueeze(-1).unsqueeze(-1)
     col_b = torch.ones_like(tex).unsqueeze(0).repeat(3, 1, 1) * color_b.unsqueeze(-1).unsqueeze(-1)
     return torch.lerp(col_a, col_b, tex.unsqueeze(0).repeat(3, 1, 1))
+
+
+def silhouette(image: torch.Tensor, cx: int, cy: int, r: int) -> torch.Tensor:
+    """ApplySilhouette.post_process (postprocessing/apply_silhouette.py:17-40) with the disc drawn analytically
+    (``(x-cx)^2 + (y-cy)^2 <= r^2``; cv2.circle is absent: parity with OpenCV's rasteriser is unpinned), blurred with the
+    restated kornia gaussian_blur2d (11,11)/(5,5) and multiplied into the image."""
+    H, W = image.shape
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    mask = (((xx - cx) ** 2 + (yy - cy) ** 2) <= r * r).to(F32)
+    return image * gaussian_blur2d(mask, (11, 11), (5.0, 5.0))

@@ -90,3 +90,24 @@ def test_batched_fused_path(P):
     assert not torch.equal(a[0], a[1])
     d = pp.post_process_batch(torch.rand(3, 100, 100, device="cuda") * 4 - 1, seed=1)
     assert d.min() >= 0 and d.max() <= 1
+
+
+def test_silhouette_batch(golden):
+    """ApplySilhouette (apply_silhouette.py:17-40): analytic disc -> 11x11 sigma-5 blur -> product, against the oracle;
+    the class draws its disc with random.randint exactly like the reference."""
+    import random
+    from fireflies_b200.postprocessing.apply_silhouette import ApplySilhouette, run_silhouette
+    gen = torch.Generator().manual_seed(8)
+    frames = torch.rand(3, 512, 384, generator=gen)
+    discs = torch.tensor([[150, 250, 200], [100, 300, 170], [380, 20, 60]], dtype=torch.int32)     # the last one crosses two borders
+    out = run_silhouette(frames.cuda(), discs.cuda())
+    for b in range(3):
+        close(out[b], O.silhouette(frames[b], *discs[b].tolist()))
+    inplace = frames.cuda().clone()
+    run_silhouette(inplace, discs.cuda(), out=inplace)
+    assert torch.equal(inplace, out)
+    random.seed(4)
+    cx, cy, r = random.randint(100, 200), random.randint(200, 300), random.randint(170, 230)
+    random.seed(4)
+    res = ApplySilhouette().post_process(frames[0].numpy())
+    close(torch.from_numpy(res), O.silhouette(frames[0], cx, cy, r))
