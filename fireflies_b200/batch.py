@@ -26,6 +26,7 @@ from .sampling.base import rehome
 
 @dataclass
 class BatchResult:
+    """B randomised scene samples on the device (see :class:`SceneBatch`)."""
     world: torch.Tensor                 # [B,E,4,4]
     sampled: torch.Tensor               # [B,S,3]
     vertices: Optional[torch.Tensor]    # [B,Vtot,3] (padded slots) or None
@@ -41,6 +42,46 @@ class BatchResult:
     def attribute(self, entity_name: str, key: str) -> torch.Tensor:
         row, dim = self.batch._attr_rows[(entity_name, key)]
         return self.sampled[:, row, :dim]
+
+    # ---- hand-off to Mitsuba (reference: Scene.update_*, scene.py:243-342) ----------------------
+    def to_host(self):
+        """ONE device->host copy (pinned, asynchronous + one event wait) of every 4x4 matrix and sampled attribute of all B
+        samples.  The reference pays a `.tolist()` / `.item()` sync per entity and attribute (scene.py:257-342)."""
+        if getattr(self, "_host", None) is None:
+            B = self.world.shape[0]
+            nw, ns = self.world[0].numel(), self.sampled[0].numel()
+            stage = torch.empty((B, nw + ns), dtype=torch.float32, device=self.world.device)
+            stage[:, :nw] = self.world.reshape(B, nw)
+            stage[:, nw:] = self.sampled.reshape(B, ns)
+            host = torch.empty((B, nw + ns), dtype=torch.float32, pin_memory=True)
+            host.copy_(stage, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            self._host = (host[:, :nw].reshape(self.world.shape).numpy(), host[:, nw:].reshape(self.sampled.shape).numpy())
+        return self._host
+
+    def write_sample(self, b: int, update: bool = True) -> None:
+        """Write scene sample ``b`` into the Mitsuba parameter map, like ``Scene.randomize()``'s update_* tail
+        (scene.py:243-342, 371-384), from the host copy made by :meth:`to_host` -- no further device syncs.  Mesh vertices
+        are handed over as slices of the device buffer (``Float32`` takes them through DLPack /
+        ``__cuda_array_interface__`` without a copy)."""
+        sb, sc = self.batch, self.batch.scene
+        params, T = sc._mitsuba_params, sc._types
+        world, sampled = self.to_host()
+        for m in sb.meshes:
+            off, n = sb._mesh_slices[m.name()]
+            params[m.name() + ".vertex_positions"] = T.Float32(self.vertices[b, off:off + n].reshape(-1))
+        for e in sb.entities:
+            if isinstance(e, Mesh) or not e.randomizable():
+                continue
+            name = e.name()
+            if name + ".to_world" in params.keys():
+                params[name + ".to_world"] = T.Transform4f(world[b, sb._entity_index[name]].tolist())
+        for (name, key), (row, dim) in sb._attr_rows.items():
+            joined = name + "." + key
+            tp = type(params[joined])
+            params[joined] = tp(float(sampled[b, row, 0])) if dim == 1 else tp(sampled[b, row, :dim].tolist())
+        if update:
+            params.update()
 
 
 class SceneBatch:

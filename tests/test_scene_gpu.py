@@ -349,3 +349,34 @@ def test_laser_out_of_bounds_respawn(ff, golden):
     ndc = ff.utils.math.transform_points(a._rays, K01)[:, 0:2]
     flipped = ndc.clone(); flipped[:, 1] = 1.0 - flipped[:, 1]      # respawn un-projects through (K @ FLIP_Y)^-1
     assert int(((ndc[:, 0] >= 1.0) | (ndc[:, 0] <= 0.0)).sum()) == 0
+
+
+def test_batched_hand_off_to_the_parameter_map(ff):
+    """BatchResult.write_sample writes sample b like Scene.randomize()'s update_* tail, from one
+    host copy of all matrices / attributes and device slices of the vertex buffer."""
+    params = fm.demo_params()
+    sc = ff.Scene(params)
+    a = sc.mesh("mesh-A")
+    a.rotate_z(-np.pi, np.pi)
+    a.translate_x(-0.2, 0.2)
+    sc._camera.translate_x(-0.15, 0.15)
+    sc.light("emit-Spot").add_vec3_sampler("intensity.value", ff.sampling.UniformScalarToVec3Sampler(0.1, 10.0))
+    sc.material("mat-Mucosa").add_float_key("brdf_0.roughness.value", 0.0, 1.0)
+    sc.train()
+    res = sc.batch(seed=9).randomize(6, sample0=0)
+    world, sampled = res.to_host()
+    assert world.shape == tuple(res.world.shape) and np.array_equal(world, res.world.cpu().numpy())
+    assert np.array_equal(sampled, res.sampled.cpu().numpy())
+    assert res.to_host()[0] is world                                   # cached: one copy per result
+    for b in (0, 5):
+        before = params.n_updates
+        res.write_sample(b)
+        assert params.n_updates == before + 1
+        out = torch.tensor(list(params["mesh-A.vertex_positions"])).reshape(-1, 3)
+        assert torch.equal(out, res.mesh_vertices("mesh-A")[b].cpu())
+        cam = params["PerspectiveCamera.to_world"].matrix.torch()[0]
+        assert torch.equal(cam, res.entity_world("PerspectiveCamera")[b].cpu())
+        inten = params["emit-Spot.intensity.value"]
+        assert list(inten) == res.attribute("emit-Spot", "intensity.value")[b].cpu().tolist()
+        rough = params["mat-Mucosa.brdf_0.roughness.value"]
+        assert float(rough) == float(res.attribute("mat-Mucosa", "brdf_0.roughness.value")[b, 0])
