@@ -60,6 +60,9 @@ constexpr int WB_WARPS = WB_CTA / 32;
 #ifndef FFB_BWD_DISC
 #define FFB_BWD_DISC 1                    // backward: drop (candidate, tile) pairs whose nearest texel is beyond the radius where g < 1e-9
 #endif
+#ifndef FFB_ACC_FOLD
+#define FFB_ACC_FOLD 0                    // backward: fold the parked partial sums once more (1 KB less shared memory per warp, one more shuffle per candidate tile)
+#endif
 #ifndef FFB_BWD_STAGED
 #define FFB_BWD_STAGED 1                  // backward inner loop staged over the four row groups (MUFU latencies overlap)
 #endif
@@ -128,7 +131,7 @@ struct WarpStage {
     float4 tabB4[TABB == 2 ? WCH : 1][WT / 2];   // dy (2 rows), soft-OR row mask (2 rows)
     float2 tabB2[TABB == 1 ? WCH : 1][WT / 2];   // dy (2 rows)
     uint4 raw[NRAW][2 * WCH];             // candidate records as fetched by cp.async
-    float acc[ACC ? WCH : 1][33];         // backward: per-lane d/dP partial sums (lanes 0-15: d/dp0, 16-31: d/dp1), row padded
+    float acc[ACC ? WCH : 1][FFB_ACC_FOLD ? 17 : 33];   // backward: parked d/dP partial sums (first half: d/dp0, second: d/dp1), row padded
     float tin[TIN ? 2 : 1][TIN ? WT : 1][TIN ? 24 : 4];   // backward: upstream soft-OR gradient / saved output tile, rows padded to 24 (bank-conflict free)
 };
 
@@ -227,7 +230,8 @@ __device__ __forceinline__ WtMasks stage_regs(Stage& s, const EntryRegs& e, int 
         s.prow[lane] = make_float2(e.a.y, e.a.w);
     }
     if (ACC) {
-        for (int k = 0; k < n; ++k) s.acc[k][lane] = 0.f;
+        if (FFB_ACC_FOLD) { if (lane < 16) for (int k = 0; k < n; ++k) s.acc[k][lane] = 0.f; }
+        else for (int k = 0; k < n; ++k) s.acc[k][lane] = 0.f;
     }
     WtMasks m;
     m.tb01 = __ballot_sync(0xffffffffu, ta[0]) | (__ballot_sync(0xffffffffu, ta[1]) << 16);
@@ -678,7 +682,13 @@ __device__ __forceinline__ void weigh_tile(Stage& st, unsigned tm, int n, float 
         }
         const float s0 = a0.x + a0.y, s1 = a1.x + a1.y;
         const float keep = h ? s1 : s0, give = h ? s0 : s1;
+#if FFB_ACC_FOLD
+        float v = keep + __shfl_xor_sync(0xffffffffu, give, 16);        // lanes 0-15: d/dp0 parts, 16-31: d/dp1 parts
+        v += __shfl_xor_sync(0xffffffffu, v, 8);                        // pairs folded: half the parking space
+        if (!(lane & 8)) st.acc[k][(lane & 7) + 8 * (lane >> 4)] += v;
+#else
         st.acc[k][lane] += keep + __shfl_xor_sync(0xffffffffu, give, 16);
+#endif
     }
 }
 
@@ -687,10 +697,11 @@ template <typename Stage>
 __device__ __forceinline__ void flush_warp(const Stage& st, int n, int h, int lc, float kh, float* __restrict__ dp) {
     __syncwarp();
     if (lc < n) {
-        const float* a = &st.acc[lc][16 * h];
+        constexpr int NP = FFB_ACC_FOLD ? 8 : 16;
+        const float* a = &st.acc[lc][NP * h];
         float x = 0.f, y = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) { x += a[j]; y += a[j + 1]; }
+        for (int j = 0; j < NP; j += 2) { x += a[j]; y += a[j + 1]; }
         const float val = (x + y) * kh;
         if (val != 0.f) atomicAdd(dp + (size_t)__float_as_int(st.cand[lc].z) * 2, val);
     }
