@@ -84,7 +84,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.005)
 
     def start(self):
         if self.nv is not None:
@@ -203,6 +203,10 @@ def main_ours(args):
         raise SystemExit("bench.py --impl ours needs a CUDA device: fireflies_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    # stdout carries exactly one JSON line: NCCL's own banner (NCCL_DEBUG=VERSION in this image) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
@@ -262,6 +266,9 @@ def main_ours(args):
     for i in range(Wm):
         one_step(i)
     barrier()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     clocks = ClockSampler(local)
     clocks.start()
     l0 = nat.launch_count
