@@ -47,37 +47,50 @@ __device__ __forceinline__ int reflect(int i, int n) {      // torch 'reflect' p
     return i >= n ? 2 * (n - 1) - i : i;
 }
 
-// 4 normal variates for 4 consecutive texels of one frame: Philox4x32-10 keyed by the seed, counter =
-// (texel quad index, global frame index); Box-Muller.  Independent of tiling, batching and rank.
-__device__ __forceinline__ void normal4(uint64_t seed, uint64_t frame, uint32_t quad, float (&z)[4]) {
+// 8 normal variates for a 4-texel quad of two consecutive rows (2 rp, 2 rp + 1) of one frame: one Philox4x32-10 call keyed by
+// the seed, counter = (row-pair quad index, global frame index); every 32-bit output feeds one Box-Muller pair (upper 16
+// bits: radius, u in (0, 1]; lower 16 bits: angle), so a call yields eight variates -- the integer rounds were two thirds
+// of the noise stage's instructions when a call served four.  The 16-bit radius caps |z| at 4.7 (P = 2.6e-6); the stream
+// has statistical parity with numpy's only.  Independent of tiling, batching and rank.
+__device__ __forceinline__ void normal8(uint64_t seed, uint64_t frame, uint32_t quadpair, float (&za)[4], float (&zb)[4]) {
     uint32_t r[4];
-    Philox::gen(seed, quad, 0x4E015E00u, (uint32_t)frame, (uint32_t)(frame >> 32), r);
-    const float u0 = ((float)(r[0] >> 8) + 1.0f) * (1.0f / 16777216.0f), u1 = Philox::u01(r[1]);
-    const float u2 = ((float)(r[2] >> 8) + 1.0f) * (1.0f / 16777216.0f), u3 = Philox::u01(r[3]);
-    // Box-Muller on the special-function unit: lg2, rsqrt, sin, cos (absolute error ~1e-6: statistical parity only)
-    const float xa = -1.3862943611198906f * __log2f(u0), xb = -1.3862943611198906f * __log2f(u2);   // -2 ln u
-    const float ra = xa * rsqrtf(fmaxf(xa, 1e-30f)), rb = xb * rsqrtf(fmaxf(xb, 1e-30f));
-    float sa, ca, sb, cb;
-    __sincosf(6.283185307179586f * u1, &sa, &ca);
-    __sincosf(6.283185307179586f * u3, &sb, &cb);
-    z[0] = ra * ca; z[1] = ra * sa; z[2] = rb * cb; z[3] = rb * sb;
+    Philox::gen(seed, quadpair, 0x4E015E00u, (uint32_t)frame, (uint32_t)(frame >> 32), r);
+    // Box-Muller on the special-function unit: lg2, rsqrt, sin, cos (absolute error ~1e-6)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float u0 = ((float)(r[k] >> 16) + 1.0f) * (1.0f / 65536.0f), u1 = (float)(r[k] & 0xffffu) * (1.0f / 65536.0f);
+        const float x2 = -1.3862943611198906f * __log2f(u0);                      // -2 ln u
+        const float rad = x2 * rsqrtf(fmaxf(x2, 1e-30f));
+        float sn, cs;
+        __sincosf(6.283185307179586f * u1, &sn, &cs);
+        if (k < 2) { za[2 * k] = rad * cs; za[2 * k + 1] = rad * sn; }          // row 2 rp
+        else { zb[2 * k - 4] = rad * cs; zb[2 * k - 3] = rad * sn; }            // row 2 rp + 1
+    }
+}
+__device__ __forceinline__ uint32_t quadpair_index(const PostParams& q, int y, int x0) {
+    return (uint32_t)((size_t)(y >> 1) * ((size_t)(q.W + 3) / 4) + (size_t)(x0 >> 2));
 }
 
-// noise + clip on up to 4 consecutive texels (x0..x0+3 of row y) -- white_noise.py:17-20
-__device__ __forceinline__ void noise_clip4(const PostParams& q, int b, int y, int x0, float (&v)[4]) {
-    const size_t base = ((size_t)b * q.H + y) * q.W + x0;
+// noise + clip on up to 4 consecutive texels (x0..x0+3 of row y) given their variates -- white_noise.py:17-20
+__device__ __forceinline__ void noise_clip4z(const PostParams& q, int b, int y, int x0, float (&v)[4], const float (&z)[4]) {
     if (q.noise_inj) {
+        const size_t base = ((size_t)b * q.H + y) * q.W + x0;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (x0 + k < q.W) v[k] = (float)((double)v[k] + q.noise_inj[base + k]);    // fp32 image += fp64 draw
     } else {
-        float z[4];
-        normal4(q.seed, q.frame0 + (uint64_t)b, (uint32_t)(((size_t)y * q.W + x0) >> 2), z);
 #pragma unroll
         for (int k = 0; k < 4; ++k) v[k] += fmaf(q.stdv, z[k], q.mean);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[k] = fminf(fmaxf(v[k], 0.f), 1.f);
+}
+// stateless form: generates the row pair's eight variates and uses this row's four
+__device__ __forceinline__ void noise_clip4(const PostParams& q, int b, int y, int x0, float (&v)[4]) {
+    float za[4] = {0.f, 0.f, 0.f, 0.f}, zb[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!q.noise_inj) normal8(q.seed, q.frame0 + (uint64_t)b, quadpair_index(q, y, x0), za, zb);
+    if (y & 1) noise_clip4z(q, b, y, x0, v, zb);
+    else noise_clip4z(q, b, y, x0, v, za);
 }
 
 __device__ __forceinline__ void store4(const PostParams& q, int b, int y, int x0, const float (&vin)[4]) {
@@ -230,8 +243,12 @@ template <int K> struct SwCfg {
     static constexpr int BOXH = TH + K - 1;
 };
 
-template <int KX, int KY>
-__global__ void __launch_bounds__(THREADS) blur_sw_kernel(const __grid_constant__ CUtensorMap tmap, const PostParams q) {
+// NOISE / MUL: the launch has a noise stage / a texel-wise multiplier; the plain blur instantiation carries neither the
+// variate registers nor the multiplier load
+template <int KX, int KY, bool NOISE, bool MUL>
+__global__ void __launch_bounds__(THREADS) blur_sw_kernel(const __grid_constant__ CUtensorMap tmap, const PostParams qin) {
+    PostParams q = qin;
+    if (!MUL) q.mul = nullptr;
     typedef SwCfg<KX> CX;
     typedef SwCfg<KY> CY;
     constexpr int BOXW = CX::BOXW, BOXH = CY::BOXH, TH2 = CY::TH, RW = CY::RW;
@@ -243,7 +260,7 @@ __global__ void __launch_bounds__(THREADS) blur_sw_kernel(const __grid_constant_
     const int x0 = tx * SW_TW, y0 = ty * TH2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool do_blur = q.gates ? q.gates[b * 2] != 0 : true;
-    const bool do_noise = q.noise && (q.gates ? q.gates[b * 2 + 1] != 0 : true);
+    const bool do_noise = NOISE && q.noise && (q.gates ? q.gates[b * 2 + 1] != 0 : true);
 
     if (!do_blur) {      // gate off: copy (PostProcessor copies once) [+ noise]
         for (int i = tid; i < (SW_TW / 4) * TH2; i += THREADS) {
@@ -294,6 +311,7 @@ __global__ void __launch_bounds__(THREADS) blur_sw_kernel(const __grid_constant_
     const int x = x0 + 4 * lane;
     const float* colp = in_s + 4 * lane;                     // first 128-bit word of this lane's window (PADL texels left of its columns)
     float win[KY][4];
+    float za[4] = {0.f, 0.f, 0.f, 0.f}, zb[4] = {0.f, 0.f, 0.f, 0.f};   // the row pair's variates: generated on even rows, zb kept for the odd row
 #pragma unroll
     for (int rr = 0; rr < RW + KY - 1; ++rr) {
         const float* rowp = colp + (warp * RW + rr) * BOXW;
@@ -321,7 +339,15 @@ __global__ void __launch_bounds__(THREADS) blur_sw_kernel(const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 4; ++j) o[j] = fmaf(wy[t], win[(rr - (KY - 1) + t) % KY][j], o[j]);
             if (y < q.H && x < q.W) {
-                if (do_noise) noise_clip4(q, b, y, x, o);
+                if (do_noise) {
+                    // y0 and warp * RW are even and KY is odd: the parity of y is the parity of rr, known at compile time
+                    if (((rr - (KY - 1)) & 1) == 0) {
+                        if (!q.noise_inj) normal8(q.seed, q.frame0 + (uint64_t)b, quadpair_index(q, y, x), za, zb);
+                        noise_clip4z(q, b, y, x, o, za);
+                    } else {
+                        noise_clip4z(q, b, y, x, o, zb);
+                    }
+                }
                 store4(q, b, y, x, o);
             }
         }
@@ -334,45 +360,58 @@ static int launch_blur_sw(const CUtensorMap& tmap, const PostParams& q, cudaStre
     typedef SwCfg<KY> CY;
     const size_t smem = (size_t)CX::BOXW * CY::BOXH * sizeof(float);
     const unsigned tiles = (unsigned)(((q.W + SW_TW - 1) / SW_TW) * ((q.H + CY::TH - 1) / CY::TH));
-    if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(blur_sw_kernel<KX, KY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    blur_sw_kernel<KX, KY><<<dim3(tiles, q.B), THREADS, smem, st>>>(tmap, q);
+    const bool noise = q.noise != 0, mul = q.mul != nullptr;
+#define FFB_SW(N, M)                                                                                                            \
+    do {                                                                                                                       \
+        if (smem > 48 * 1024)                                                                                                  \
+            FFB_CUDA(cudaFuncSetAttribute(blur_sw_kernel<KX, KY, N, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        blur_sw_kernel<KX, KY, N, M><<<dim3(tiles, q.B), THREADS, smem, st>>>(tmap, q);                                         \
+    } while (0)
+    if (noise && mul) FFB_SW(true, true);
+    else if (noise) FFB_SW(true, false);
+    else if (mul) FFB_SW(false, true);
+    else FFB_SW(false, false);
+#undef FFB_SW
     FFB_CUDA(cudaGetLastError());
     return 0;
 }
 
 // no blur stage configured: pure streaming copy / noise / clip
 __global__ void __launch_bounds__(THREADS) pointwise_kernel(const PostParams q) {
-    const size_t quads_per_row = (size_t)(q.W + 3) / 4;
-    const size_t total = quads_per_row * q.H * q.B;
+    // one item = a 4-texel quad of a row pair (rows 2 rp, 2 rp + 1): both loads in flight, one Philox call for the 8 variates
+    const size_t quads_per_row = (size_t)(q.W + 3) / 4, pairs = (size_t)(q.H + 1) / 2;
+    const size_t total = quads_per_row * pairs * q.B;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const bool vec = (q.W & 3) == 0;
-    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int b = (int)(i / (quads_per_row * pairs));
+        const size_t rem = i - (size_t)b * quads_per_row * pairs;
+        const int rp = (int)(rem / quads_per_row), x0 = (int)(rem - (size_t)rp * quads_per_row) * 4;
         float v[2][4];
-        int bb[2], yy[2], xx[2];
         bool live[2];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {                       // both loads in flight before any arithmetic
-            const size_t i = i0 + u * stride;
-            live[u] = i < total;
-            const size_t ii = live[u] ? i : 0;
-            bb[u] = (int)(ii / (quads_per_row * q.H));
-            const size_t rem = ii - (size_t)bb[u] * quads_per_row * q.H;
-            yy[u] = (int)(rem / quads_per_row); xx[u] = (int)(rem - (size_t)yy[u] * quads_per_row) * 4;
-            const float* s = q.img + ((size_t)bb[u] * q.H + yy[u]) * q.W + xx[u];
+        for (int u = 0; u < 2; ++u) {
+            const int y = 2 * rp + u;
+            live[u] = y < q.H;
+            const float* s = q.img + ((size_t)b * q.H + (live[u] ? y : 0)) * q.W + x0;
             if (vec) {
                 const float4 a = __ldg(reinterpret_cast<const float4*>(s));
                 v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[u][k] = xx[u] + k < q.W ? __ldg(s + k) : 0.f;
+                for (int k = 0; k < 4; ++k) v[u][k] = x0 + k < q.W ? __ldg(s + k) : 0.f;
             }
         }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (!live[u]) continue;
-            const bool do_noise = q.noise && (q.gates ? q.gates[bb[u] * 2 + 1] != 0 : true);
-            if (do_noise) noise_clip4(q, bb[u], yy[u], xx[u], v[u]);
-            store4(q, bb[u], yy[u], xx[u], v[u]);
+        const bool do_noise = q.noise && (q.gates ? q.gates[b * 2 + 1] != 0 : true);
+        float za[4] = {0.f, 0.f, 0.f, 0.f}, zb[4] = {0.f, 0.f, 0.f, 0.f};
+        if (do_noise && !q.noise_inj) normal8(q.seed, q.frame0 + (uint64_t)b, quadpair_index(q, 2 * rp, x0), za, zb);
+        if (live[0]) {
+            if (do_noise) noise_clip4z(q, b, 2 * rp, x0, v[0], za);
+            store4(q, b, 2 * rp, x0, v[0]);
+        }
+        if (live[1]) {
+            if (do_noise) noise_clip4z(q, b, 2 * rp + 1, x0, v[1], zb);
+            store4(q, b, 2 * rp + 1, x0, v[1]);
         }
     }
 }
@@ -583,7 +622,7 @@ static int postprocess_impl(const ffb_post_desc* d, const float* img, const uint
     q.img = img; q.gates = gates; q.noise_inj = noise_injected; q.mul = mul; q.out = out;
     cudaStream_t st = as_stream(stream);
     if (!blur) {
-        const size_t total = (size_t)((d->W + 3) / 4) * d->H * d->B;
+        const size_t total = (size_t)((d->W + 3) / 4) * ((d->H + 1) / 2) * d->B;
         size_t blocks = (total + THREADS - 1) / THREADS;
         if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
         pointwise_kernel<<<(unsigned)blocks, THREADS, 0, st>>>(q);

@@ -371,11 +371,11 @@ __global__ void __launch_bounds__(RS_THREADS) respawn_kernel(float* __restrict__
                                                              const float* __restrict__ Minv, uint64_t seed, uint64_t counter,
                                                              const float* __restrict__ variates, int* __restrict__ count_out) {
     __shared__ int warp_cnt[32];
-    __shared__ int carry, total;
+    __shared__ int carry;
     __shared__ float Tm[16], Ti[16];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid < 16) { Tm[tid] = M ? M[tid] : 0.f; Ti[tid] = Minv[tid]; }
-    if (tid == 0) { carry = 0; total = 0; }
+    if (tid == 0) carry = 0;
     __syncthreads();
     // pass 1: is anything out of bounds?
     int mine = 0;
