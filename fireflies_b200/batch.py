@@ -250,8 +250,12 @@ class SceneBatch:
                       for a in self._anim_meshes]
                 hi = [(a._animation_sampler._max_integer_train if train else a._animation_sampler._max_integer_eval) if a else 0
                       for a in self._anim_meshes]
-                amin = torch.tensor(lo, dtype=torch.int32, device=self.device)
-                amax = torch.tensor(hi, dtype=torch.int32, device=self.device)
+                key = (train, tuple(lo), tuple(hi))
+                if getattr(self, "_anim_range_key", None) != key:      # two tiny H2D copies only when the ranges change
+                    self._anim_range = (torch.tensor(lo, dtype=torch.int32, device=self.device),
+                                        torch.tensor(hi, dtype=torch.int32, device=self.device))
+                    self._anim_range_key = key
+                amin, amax = self._anim_range
                 idx = torch.empty((B, M), dtype=torch.int32, device=self.device)
                 nat.check(L.ffb_sample_anim_index(amin.data_ptr(), amax.data_ptr(), self._anim_cur.data_ptr(), M, B,
                                                   nat.MODE_TRAIN if train else nat.MODE_EVAL, self.seed, int(sample0),
