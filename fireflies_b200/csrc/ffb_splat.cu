@@ -703,7 +703,7 @@ static int launch_wt(K kernel, KO overflow, const RasterParams& q, const WtConst
 template <typename K, typename KO>
 static int launch_fwd_tma(K kernel, KO overflow, const RasterParams& q, const WtConsts& fc, const OvfParams& o, int B, cudaStream_t st,
                           const CUtensorMap& ms, const CUtensorMap& mo, size_t stage_bytes) {
-    const unsigned gy = (unsigned)((q.tgy + WF_WARPS * WT_S - 1) / (WF_WARPS * WT_S));
+    const unsigned gy = (unsigned)((q.tgy + WF_WARPS * WF_S - 1) / (WF_WARPS * WF_S));
     if (B > 65535 || gy > 65535) return fail_arg(FFB_E_LIMIT, "splat: B or the tile rows exceed the grid limit (65535)");
     const size_t smem = (size_t)WF_WARPS * (2 * TMA_TILE_BYTES + stage_bytes);
     if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

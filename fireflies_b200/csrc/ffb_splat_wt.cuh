@@ -35,13 +35,22 @@
 //     this file, which walk the binning kernel's overflow list with the same device functions in chunks of 16.
 #pragma once
 
-constexpr int WT_S = 4;                   // vertically adjacent super tiles per warp
+#ifndef FFB_WT_S
+#define FFB_WT_S 1                        // backward: 0.624 / 0.658 / 0.654 / 0.651 ms per 64 samples at 1 / 2 / 3 / 4 (locality of the CTAs in flight beats the
+#endif                                    // cross-super-tile prefetch a longer strip allows)
+constexpr int WT_S = FFB_WT_S;            // vertically adjacent super tiles per warp (<= 16: one lane pair per super tile holds its list bounds)
+#ifndef FFB_WF_S
+#define FFB_WF_S 1
+#endif
+constexpr int WF_S = FFB_WF_S;            // ... in the TMA-store forward.  Measured per 64 samples (256-thread CTAs): 0.422 / 0.419 / 0.475 / 0.541 /
+                                          // 0.587 ms at 1 / 2 / 4 / 8 / 16: with short strips the CTAs in flight (scheduled column block first) write a
+                                          // narrow band of texture rows at any time, and DRAM sees whole rows complete together
 constexpr int WT_CTA = 256;               // forward / overflow kernels: 8 warps x 4 super tiles (64 x 16 texels each) = 64 x 512 texels
 constexpr int WT_WARPS = WT_CTA / 32;
 #ifndef FFB_WF_CTA
-#define FFB_WF_CTA 256
+#define FFB_WF_CTA 64
 #endif
-constexpr int WF_CTA = FFB_WF_CTA;        // TMA-store forward
+constexpr int WF_CTA = FFB_WF_CTA;        // TMA-store forward (measured at one super tile per warp: 0.386 / 0.379 / 0.378 ms at 128 / 64 / 32 threads)
 constexpr int WF_WARPS = WF_CTA / 32;
 #ifndef FFB_WF_MINB
 #define FFB_WF_MINB (1024 / FFB_WF_CTA)   // 32 warps per SM at 64 registers
@@ -438,14 +447,14 @@ __device__ __forceinline__ void store_tile(const RasterParams& q, const WtCoord&
 struct Strip {
     int b, bin, c0, sty0, nst, lane, tv;
 };
-template <int WARPS>
+template <int WARPS, int S = WT_S>
 __device__ __forceinline__ bool strip_init(Strip& s, const RasterParams& q) {
     s.b = blockIdx.z;
     s.bin = q.shared_pattern ? 0 : s.b;
     s.lane = threadIdx.x & 31;
-    s.sty0 = (blockIdx.y * WARPS + (threadIdx.x >> 5)) * WT_S;
+    s.sty0 = (blockIdx.y * WARPS + (threadIdx.x >> 5)) * S;
     if (s.sty0 >= q.tgy) return false;
-    s.nst = min(WT_S, q.tgy - s.sty0);
+    s.nst = min(S, q.tgy - s.sty0);
     s.c0 = blockIdx.x * (4 * WT);
     const int* toff = q.tile_off + (size_t)s.bin * (q.T + 1) + (size_t)s.sty0 * q.tgx + blockIdx.x;
     s.tv = 0;
@@ -504,7 +513,7 @@ __global__ void __launch_bounds__(WF_CTA, FFB_WF_MINB) splat_fwd_tma(RasterParam
     typedef WarpStage<MASK_O ? 2 : 0> Stage;
     extern __shared__ __align__(1024) unsigned char wt_smem_ftma[];
     Strip sp;
-    if (!strip_init<WF_WARPS>(sp, q)) return;              // whole warp; no block-level barriers below
+    if (!strip_init<WF_WARPS, WF_S>(sp, q)) return;        // whole warp; no block-level barriers below
     const int wid = threadIdx.x >> 5;
     unsigned char* tout = wt_smem_ftma + wid * (2 * TMA_TILE_BYTES);         // [softor | sum], 1 KB each, 1 KB aligned
     Stage& st = reinterpret_cast<Stage*>(wt_smem_ftma + WF_WARPS * 2 * TMA_TILE_BYTES)[wid];
