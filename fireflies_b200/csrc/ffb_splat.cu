@@ -421,6 +421,7 @@ struct RasterParams {
     float* out_sum; float* out_softor;            // forward
     const float* g_sum; const float* g_softor;    // backward
     float* d_pts;
+    int eager;                // backward: request a super tile's first upstream boxes before its candidate list is known (dense patterns)
     float* loss;              // fused L1 backward: per-sample mean |softor - sum| (accumulated)
     float loss_inv;           // 1 / (ts0 * ts1)
 };
@@ -757,6 +758,13 @@ static void fill_raster(const ffb_splat_desc* d, const Plan& p, const void* ws, 
     q.sigma = d->sigma; q.rcp_sigma = 1.0f / d->sigma;
     q.out_sum = nullptr; q.out_softor = nullptr; q.g_sum = nullptr; q.g_softor = nullptr; q.d_pts = nullptr;
     q.loss = nullptr; q.loss_inv = 0.f;
+    {
+        // expected candidates per 64x16 super tile for points spread over the texture: above ~2 nearly every super tile has work
+        const double wwin = 2.0 * (p.H_s > p.H_o ? p.H_s : p.H_o) + 1.0;
+        const double per_tile = (double)d->N * (wwin + 4 * WT - 1) * (wwin + WT - 1) / ((double)d->ts0 * (double)d->ts1);
+        const char* e = getenv("FFB_SPLAT_EAGER");
+        q.eager = e ? (e[0] == '1') : (per_tile >= 2.0);
+    }
 }
 
 // ---- dense API-compat kernels -----------------------------------------------------------------------

@@ -39,6 +39,9 @@
 #define FFB_WT_S 1                        // backward: 0.624 / 0.658 / 0.654 / 0.651 ms per 64 samples at 1 / 2 / 3 / 4 (locality of the CTAs in flight beats the
 #endif                                    // cross-super-tile prefetch a longer strip allows)
 constexpr int WT_S = FFB_WT_S;            // vertically adjacent super tiles per warp (<= 16: one lane pair per super tile holds its list bounds)
+#ifndef FFB_RASTER_G
+#define FFB_RASTER_G 1
+#endif
 #ifndef FFB_WF_S
 #define FFB_WF_S 1
 #endif
@@ -445,18 +448,29 @@ __device__ __forceinline__ void store_tile(const RasterParams& q, const WtCoord&
 
 // The strip of super tiles a warp owns, and its list offsets (one load for the whole strip).
 struct Strip {
-    int b, bin, c0, sty0, nst, lane, tv;
+    int b, bin, c0, sty0, nst, lane, tv, bx;
 };
 template <int WARPS, int S = WT_S>
 __device__ __forceinline__ bool strip_init(Strip& s, const RasterParams& q) {
     s.b = blockIdx.z;
+    // CTA rasterisation: the hardware issues CTAs with blockIdx.x fastest; FFB_RASTER_G > 1 walks bands of G CTA rows
+    // column block by column block instead (G vertically adjacent CTAs, then the next column block)
+    int bx = blockIdx.x, by = blockIdx.y;
+    if (FFB_RASTER_G > 1) {
+        const int lin = blockIdx.y * gridDim.x + blockIdx.x, per = FFB_RASTER_G * gridDim.x;
+        const int band = lin / per, r = lin - band * per;
+        const int g = min(FFB_RASTER_G, (int)gridDim.y - band * FFB_RASTER_G);
+        by = band * FFB_RASTER_G + r % g;
+        bx = r / g;
+    }
     s.bin = q.shared_pattern ? 0 : s.b;
     s.lane = threadIdx.x & 31;
-    s.sty0 = (blockIdx.y * WARPS + (threadIdx.x >> 5)) * S;
+    s.sty0 = (by * WARPS + (threadIdx.x >> 5)) * S;
     if (s.sty0 >= q.tgy) return false;
     s.nst = min(S, q.tgy - s.sty0);
-    s.c0 = blockIdx.x * (4 * WT);
-    const int* toff = q.tile_off + (size_t)s.bin * (q.T + 1) + (size_t)s.sty0 * q.tgx + blockIdx.x;
+    s.c0 = bx * (4 * WT);
+    s.bx = bx;
+    const int* toff = q.tile_off + (size_t)s.bin * (q.T + 1) + (size_t)s.sty0 * q.tgx + bx;
     s.tv = 0;
     if (s.lane < 2 * s.nst) s.tv = __ldg(toff + (s.lane >> 1) * q.tgx + (s.lane & 1));   // lane 2k: begin, lane 2k+1: end of super tile k
     return true;
@@ -918,8 +932,6 @@ __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_tma(RasterPara
         tma::fence_mbar_init();
     }
     __syncwarp();
-    int n = __shfl_sync(0xffffffffu, sp.tv, 1) - __shfl_sync(0xffffffffu, sp.tv, 0);
-    prefetch_entries(st.raw[0], entries + __shfl_sync(0xffffffffu, sp.tv, 0), n <= WCH ? n : 0, sp.lane);
     unsigned phase = 0;
     bool have = false;                                      // tile 0 of the current super tile is already in flight
     constexpr unsigned kBytes = (unsigned)TMA_TILE_BYTES * (LOSS ? (SUM_T ? 4 : 2) : ((SOFTOR ? (SAVED ? 2 : 1) : 0) + (SUM ? 1 : 0)));
@@ -953,6 +965,14 @@ __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_tma(RasterPara
         }
     };
     auto sgn = [&](float d) { return d > 0.f ? q.loss_inv : (d < 0.f ? -q.loss_inv : 0.f); };
+    // dense patterns (or the loss mode, which visits every tile): the first tile's boxes are requested before the list bounds and
+    // the candidate records arrive -- three dependent memory latencies at the head of a warp's life become one
+    if (LOSS || q.eager) {
+        issue(sp.sty0 * WT, 0);
+        have = true;
+    }
+    int n = __shfl_sync(0xffffffffu, sp.tv, 1) - __shfl_sync(0xffffffffu, sp.tv, 0);
+    prefetch_entries(st.raw[0], entries + __shfl_sync(0xffffffffu, sp.tv, 0), n <= WCH ? n : 0, sp.lane);
 
     for (int s = 0; s < sp.nst; ++s) {
         const EntryRegs e = take_entry(st.raw[0], n <= WCH ? n : 0, sp.lane);
@@ -1029,6 +1049,10 @@ __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_tma(RasterPara
             if (grad) flush_warp(st, n, w.h, w.lc, kh, dp);
             have = next_live;
         } else {
+            if (have) {                                     // requested eagerly, not needed: let the boxes land before the buffers go away
+                tma::mbar_wait(bar, phase);
+                phase ^= 1u;
+            }
             have = false;
         }
         n = nn;

@@ -35,6 +35,12 @@ os.environ["FFB_SPLAT_NO_TMA"] = "0"
 d_new = plan.backward(ptsB, gS, gO, True, O_)
 print(f"bwd (saved) without TMA: {tb3:.3f} ms; max |tma - plain| = {float((d_new - d_old).abs().max()):.3e} of {float(d_old.abs().max()):.3e}")
 print(f"bwd without saved softor: {tb2:.3f} ms")
+os.environ["FFB_SPLAT_EAGER"] = "0"
+tb4 = t(lambda: plan.backward(ptsB, gS, gO, True, O_))
+os.environ["FFB_SPLAT_EAGER"] = "1"
+tb5 = t(lambda: plan.backward(ptsB, gS, gO, True, O_))
+del os.environ["FFB_SPLAT_EAGER"]
+print(f"bwd eager off {tb4:.3f} ms, on {tb5:.3f} ms")
 tl = t(lambda: plan.backward_l1(ptsB, S_, O_, True))
 print(f"fused L1 backward: {tl:.3f} ms ({B*16*ts[0]*ts[1]/tl/1e6:.0f} GB/s of 16 B/texel actual reads)")
 hw = ts[0] * ts[1]
