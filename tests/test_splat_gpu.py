@@ -292,3 +292,33 @@ def test_reduce_over_samples(R, B, shape):
     assert out.shape == shape
     close(out, x.double().sum(0), rtol=1e-5, atol=1e-5)
     assert torch.equal(out, R.reduce_over_samples(x))       # fixed summation order
+
+
+def test_tma_and_plain_kernels_agree(R, monkeypatch):
+    """The TMA-fed / TMA-stored kernels are the production path; textures the TMA unit cannot describe (sides not
+    multiples of 4) and FFB_SPLAT_NO_TMA=1 take the plain-load / plain-store kernels.  Same arithmetic: forward bit for bit."""
+    gen = torch.Generator().manual_seed(21)
+    pts = (torch.rand(3, 400, 2, generator=gen) * 0.96 + 0.02).cuda()
+    ts, sigma = [320, 272], 49.0
+    gS, gO = torch.randn(3, ts[0], ts[1], generator=gen).cuda(), torch.randn(3, ts[1], ts[0], generator=gen).cuda()
+    plan = R._SplatPlan(pts, 3, sigma, ts[0], ts[1], 4, 5)
+    s1, o1 = plan.forward(pts, True, True, True)
+    d1 = plan.backward(pts, gS, gO, True, o1)
+    monkeypatch.setenv("FFB_SPLAT_NO_TMA", "1")
+    s2, o2 = plan.forward(pts, True, True, True)
+    d2 = plan.backward(pts, gS, gO, True, o1)
+    monkeypatch.delenv("FFB_SPLAT_NO_TMA")
+    assert torch.equal(s1, s2) and torch.equal(o1, o2)
+    close(d1, d2, rtol=1e-5, atol=1e-5 * float(d2.abs().max()))
+    # odd sides: no tensor map possible, the plain kernels run on their own; checked against the oracle
+    pts1 = pts[0, :60].contiguous()
+    ts_odd = [101, 75]
+    s, o = R.splat_reduce(pts1, 16.0, ts_odd)
+    close(s, O.baked_sum(pts1.cpu(), 16.0, ts_odd)); close(o, O.baked_softor(pts1.cpu(), 16.0, ts_odd))
+    p = pts1.clone().requires_grad_(True)
+    w = torch.randn(ts_odd[1], ts_odd[0], generator=gen).cuda()
+    s, o = R.splat_reduce(p, 16.0, ts_odd)
+    ((s * w).sum() + (o * w).sum()).backward()
+    po = pts1.cpu().clone().requires_grad_(True)
+    ((O.baked_sum(po, 16.0, ts_odd) * w.cpu()).sum() + (O.baked_softor(po, 16.0, ts_odd) * w.cpu()).sum()).backward()
+    close(p.grad, po.grad, rtol=1e-4, atol=1e-4 * float(po.grad.abs().max()))
