@@ -309,6 +309,29 @@ def main_ours(args):
                 "kernels_ms": ph_ms,
                 "kernels_gbs": {p: alg[p] / (ph_ms[p] * 1e-3) / 1e9 for p in alg}}
 
+    # ---- optimisation mode, reported separately: one pattern shared by all scenes of the step ----
+    # The B textures are then one texture and the backward is linear in the upstream gradients: fold them over the samples
+    # (streaming read), one forward, one backward.  NOT the headline: `value` keeps per-sample textures.
+    shared = None
+    if not args.no_e2e:
+        step_sh = ff.PatternStep(N_POINTS, TS, SIGMA, B, scene_batch=sb, per_sample_points=False, device=device)
+        for i in range(2):
+            step_sh.forward_backward(pattern, upstream=(gS, gO), sample0=i * B * world + first)
+        barrier()
+        s0, s1 = ev(), ev()
+        s0.record()
+        for i in range(K):
+            step_sh.forward_backward(pattern, upstream=(gS, gO), sample0=(2 + i) * B * world + first)
+        s1.record()
+        barrier()
+        sh_ms = max_over_ranks(s0.elapsed_time(s1), device) / K
+        sh_bytes = B * (8 * hw + 24 * V_MESH)                    # both upstream gradients read once + the vertex transform
+        shared = {"value": B * world / (sh_ms * 1e-3), "unit": UNIT, "ms_per_step": sh_ms,
+                  "achieved_GBs": sh_bytes / (sh_ms * 1e-3) / 1e9, "frac_of_peak": sh_bytes / (sh_ms * 1e-3) / 1e9 / peak,
+                  "note": "PatternStep(per_sample_points=False): upstream gradients folded over the samples, one forward + one backward; "
+                          "a separate mode, not the headline metric"}
+        del step_sh
+
     # ---- e2e: public API with host buffers ----
     e2e = None
     if not args.no_e2e:
@@ -341,7 +364,8 @@ def main_ours(args):
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config(B, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "config": config(B, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "shared_pattern_mode": shared,
+            "gpu_launches": launches,
             "clocks": clk}))
     if world > 1:
         dist.destroy_process_group()

@@ -291,6 +291,7 @@ class PatternStep:
         self.pg = process_group
         self.fuse_loss = bool(fuse_loss)      # False: loss and texture gradients through ffb_l1_loss_fwd_bwd, then the plain backward
         self.pts_dev = torch.empty((self.B if per_sample_points else 1, self.N, 2), dtype=torch.float32, device=self.device)
+        # per_sample_points=False: one pattern for all scenes of the step -> see _shared_pattern
         self._pat_dev = torch.empty((self.N, 2), dtype=torch.float32, device=self.device)
         self.last = None
         self._side: Optional[torch.cuda.Stream] = None
@@ -322,7 +323,10 @@ class PatternStep:
                 self.pts_dev.copy_(points.unsqueeze(0), non_blocking=True)
         else:
             self.pts_dev.copy_(points, non_blocking=True)
-        pts = self.pts_dev if self.per_sample else self.pts_dev[0]
+        if not self.per_sample:
+            loss, dp, s, o = self._shared_pattern(self.pts_dev[0], upstream)
+            return self._finish(loss, dp, s, o, res)
+        pts = self.pts_dev
         plan = R._SplatPlan(pts, self.B, self.sigma, self.ts0, self.ts1, self.ns, self.no)
         s, o = plan.forward(pts, True, True, self.sum_t)
         loss = None
@@ -343,6 +347,9 @@ class PatternStep:
         if d is None:
             d = plan.backward(pts, gs, go, self.sum_t, o)
         dp = R.reduce_over_samples(d) if self.B > 1 else d[0]
+        return self._finish(loss, dp, s, o, res)
+
+    def _finish(self, loss, dp, s, o, res):
         if res is not None:
             cur = torch.cuda.current_stream()
             cur.wait_stream(self._side)
@@ -352,6 +359,32 @@ class PatternStep:
         self._allreduce(dp)
         self.last = (s, o, res)
         return loss, dp, res
+
+    def _shared_pattern(self, pts: torch.Tensor, upstream):
+        """One pattern for all B scenes of the step (``per_sample_points=False``: what data-parallel pattern optimisation
+        does -- the scenes differ, the projector texture does not).  The B textures are one texture, and the backward is
+        linear in the upstream texture gradients, so they are folded over the samples first (a streaming read of
+        2 x B textures) and ONE splat backward runs on the folded gradients: the per-sample splat work disappears, the
+        step is bounded by reading the upstream gradients once."""
+        plan = R._SplatPlan(pts, 1, self.sigma, self.ts0, self.ts1, self.ns, self.no)
+        s, o = plan.forward(pts, True, True, self.sum_t)                    # [1, ...]: the texture every scene is rendered with
+        if upstream is None:
+            fused = plan.backward_l1(pts, s, o, self.sum_t) if self.fuse_loss else None
+            if fused is not None:
+                loss1, d = fused
+            else:
+                loss1 = torch.empty(1, dtype=torch.float32, device=self.device)
+                gs, go = torch.empty_like(s), torch.empty_like(o)
+                nat.check(nat.lib().ffb_l1_loss_fwd_bwd(o.data_ptr(), s.data_ptr(), 0, 1, self.ts0, self.ts1, loss1.data_ptr(),
+                                                        go.data_ptr(), gs.data_ptr(), nat.stream()), "ffb_l1_loss_fwd_bwd")
+                nat.count(2)
+                d = plan.backward(pts, gs, go, self.sum_t, o)
+            return loss1.expand(self.B), d[0] * float(self.B), s.expand(self.B, -1, -1), o.expand(self.B, -1, -1)
+        gs, go = upstream
+        gs1 = R.reduce_over_samples(gs).unsqueeze(0) if gs.shape[0] > 1 else gs
+        go1 = R.reduce_over_samples(go).unsqueeze(0) if go.shape[0] > 1 else go
+        d = plan.backward(pts, gs1, go1, self.sum_t, o)
+        return None, d[0], s.expand(self.B, -1, -1), o.expand(self.B, -1, -1)
 
     def step_host(self, points_host: torch.Tensor, out_host: torch.Tensor, loss_host: torch.Tensor, sample0: Optional[int] = None):
         """End-to-end step with HOST buffers: pinned ``points_host`` [N,2] in, ``out_host`` [N,2] (gradient) and

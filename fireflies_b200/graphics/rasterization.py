@@ -118,8 +118,16 @@ class _SplatPlan:
 def reduce_over_samples(x: torch.Tensor) -> torch.Tensor:
     """``x.sum(0)`` in a fixed order (deterministic): folds per-sample pattern gradients."""
     x = nat.require_cuda(x, torch.float32, "x")
+    row = x[0].numel()
+    # texture-sized rows: fold 8 samples per level at streaming bandwidth (a CTA that walks all B planes loses to TLB reach)
+    while x.shape[0] > 8 and row >= 1 << 16 and row % 4 == 0 and x.data_ptr() % 16 == 0:
+        G = (x.shape[0] + 7) // 8
+        part = torch.empty((G,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
+        nat.check(nat.lib().ffb_reduce_sample_groups(x.data_ptr(), x.shape[0], row, part.data_ptr(), nat.stream()),
+                  "ffb_reduce_sample_groups")
+        nat.count()
+        x = part
     out = torch.empty(x.shape[1:], dtype=torch.float32, device=x.device)
-    row = out.numel()
     nat.check(nat.lib().ffb_reduce_over_samples(x.data_ptr(), x.shape[0], row, out.data_ptr(), nat.stream()),
               "ffb_reduce_over_samples")
     nat.count()

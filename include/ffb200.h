@@ -118,6 +118,12 @@ FFB_API int ffb_splat_bwd_l1(const ffb_splat_desc* d, const float* pts, const vo
  * used to fold per-sample pattern gradients before the allreduce. */
 FFB_API int ffb_reduce_over_samples(const float* in, int32_t B, int64_t row_elems, float* out, void* stream);
 
+/* One level of the same fold for texture-sized rows: out[g, :] = sum of samples 8g .. 8g+7 (fixed order), out is
+ * [ceil(B/8), row_elems].  Applied repeatedly it sums B upstream texture gradients at streaming bandwidth (the
+ * shared-pattern backward: one pattern for all scenes of a step, the backward being linear in the upstream gradients).
+ * Rows must be 16-byte aligned multiples of 4 elements (FFB_E_UNSUPPORTED otherwise). */
+FFB_API int ffb_reduce_sample_groups(const float* in, int32_t B, int64_t row_elems, float* out, void* stream);
+
 /* API-compatibility dense splat: rasterize_points (rasterization.py:7-37) -> [N,ts1,ts0],
  * and its backward given the upstream gradient of that tensor. */
 FFB_API int ffb_splat_dense_fwd(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sigma,

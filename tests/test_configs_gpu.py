@@ -143,3 +143,23 @@ def test_config4_sharded_step_equals_whole_batch(ff):
     assert torch.equal(torch.cat(verts_parts), res_w.vertices)           # randomisation independent of the split
     close(torch.cat(loss_parts), loss_w, rtol=1e-6, atol=0)              # per-sample loss: atomic accumulation order varies
     close(dp_parts[0] + dp_parts[1], dp_w, rtol=1e-4, atol=1e-4 * float(dp_w.abs().max()))
+
+
+def test_shared_pattern_step_equals_per_sample_step(ff):
+    """One pattern for all scenes of a step: the folded-gradient path (one forward, upstream gradients summed over the samples,
+    one backward) gives the per-sample path's result."""
+    N, ts, sigma, B = 500, [256, 256], 49.0, 12
+    gen = torch.Generator().manual_seed(17)
+    pattern = (torch.rand(N, 2, generator=gen) * 0.9 + 0.05).cuda()
+    gS = torch.randn(B, ts[0], ts[1], generator=gen).cuda()
+    gO = torch.randn(B, ts[1], ts[0], generator=gen).cuda()
+    per = ff.PatternStep(N, ts, sigma, B, per_sample_points=True)
+    sh = ff.PatternStep(N, ts, sigma, B, per_sample_points=False)
+    _, dp_a, _ = per.forward_backward(pattern, upstream=(gS, gO))
+    _, dp_b, _ = sh.forward_backward(pattern, upstream=(gS, gO))
+    close(dp_b, dp_a, rtol=1e-4, atol=1e-4 * float(dp_a.abs().max()))
+    assert sh.last[0].shape == (B, ts[0], ts[1]) and torch.equal(sh.last[1][3], per.last[1][3])
+    la, da, _ = per.forward_backward(pattern)                # L1(softor, sum) loss
+    lb, db, _ = sh.forward_backward(pattern)
+    close(lb, la, rtol=1e-5, atol=0)
+    close(db, da, rtol=1e-4, atol=1e-4 * float(da.abs().max()))

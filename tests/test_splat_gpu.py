@@ -285,7 +285,7 @@ def test_fused_l1_refuses_what_it_cannot_pair(R):
     assert plan.backward_l1(pts, s, o, True) is None
 
 
-@pytest.mark.parametrize("B,shape", [(1, (5, 2)), (7, (33, 2)), (37, (1000,)), (256, (4096, 2))])
+@pytest.mark.parametrize("B,shape", [(1, (5, 2)), (7, (33, 2)), (37, (1000,)), (256, (4096, 2)), (100, (300, 256)), (9, (256, 260))])
 def test_reduce_over_samples(R, B, shape):
     x = torch.randn((B,) + shape, generator=torch.Generator().manual_seed(B)).cuda()
     out = R.reduce_over_samples(x)
