@@ -225,6 +225,19 @@ def test_full_size_properties(R):
     # (5) a random 64x64 crop against the oracle evaluated on that crop's candidate points
     d = O.baked_sum(pts.cpu(), 100.0, ts)
     close(s[1000:1064, 300:364], d[1000:1064, 300:364])
+    # (5b) the whole 2048^2 textures and the gradient for random upstream weights against the oracle (its scatter form + autograd
+    #      finish in about a second at this size)
+    gen2 = torch.Generator().manual_seed(4)
+    wS, wO = torch.randn(2048, 2048, generator=gen2), torch.randn(2048, 2048, generator=gen2)
+    po = pts.cpu().clone().requires_grad_(True)
+    So = O.baked_softor(po, 100.0, ts)
+    Sd = O.baked_sum(po, 100.0, ts)
+    close(s, Sd.detach()); close(o, So.detach())
+    ((Sd * wS).sum() + (So * wO).sum()).backward()
+    pc = pts.clone().requires_grad_(True)
+    sc, oc = R.splat_reduce(pc, 100.0, ts)
+    ((sc * wS.cuda()).sum() + (oc * wO.cuda()).sum()).backward()
+    close(pc.grad, po.grad, rtol=1e-4, atol=1e-4 * float(po.grad.abs().max()))
     # (6) gradient of the total mass w.r.t. interior points vanishes (translation invariance)
     p = pts.clone().requires_grad_(True)
     R.splat_reduce(p, 100.0, ts, reduce=("sum",))[0].sum().backward()
