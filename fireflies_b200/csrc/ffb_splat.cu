@@ -268,7 +268,10 @@ __device__ __forceinline__ int origin_axis(float P, int baked, int half) {
 // index lists.  The tile grid is processed in bands of whole tile rows so that the
 // counters fit in shared memory for any texture size.
 template <bool FAST>
-__global__ void __launch_bounds__(PREP_CTA) prepare_kernel(PrepParams q) {
+#ifndef FFB_PREP_MINB
+#define FFB_PREP_MINB 1
+#endif
+__global__ void __launch_bounds__(PREP_CTA, FFB_PREP_MINB) prepare_kernel(PrepParams q) {
     extern __shared__ int sm[];
     const int band_tiles = q.band_rows * q.tgx;
     int* cnt = sm;                 // [band_tiles] counts, then exclusive offsets

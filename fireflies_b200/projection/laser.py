@@ -104,9 +104,13 @@ class Laser(Camera):
         order) is given.  ``self.last_respawned`` (device int32) holds the number of respawned rays."""
         rays = nat.require_cuda(self._rays.detach(), torch.float32, "rays")
         Minv = self._M().inverse().contiguous()
-        v = None if variates is None else nat.require_cuda(variates.float().contiguous(), torch.float32, "variates")
-        if v is not None and (v.dim() != 2 or v.shape[1] != 3 or v.shape[0] < rays.shape[0]) and v.shape[0] == 0:
-            raise ValueError("variates must be [K, 3]")
+        v = None
+        if variates is not None:
+            v = nat.require_cuda(variates.float().contiguous(), torch.float32, "variates")
+            if v.dim() != 2 or v.shape[1] != 3:
+                raise ValueError("variates must be [K, 3]")
+            if v.shape[0] < rays.shape[0]:          # the kernel consumes one row per out-of-bounds ray, at most N: never read past the end
+                v = torch.cat([v, v.new_zeros((rays.shape[0] - v.shape[0], 3))])
         self.last_respawned = torch.zeros(1, dtype=torch.int32, device=rays.device)
         self._respawn_calls = getattr(self, "_respawn_calls", 0) + 1
         nat.check(nat.lib().ffb_respawn_rays(rays.data_ptr(), rays.shape[0], nat.ptr(M), nat.ptr(ndc), float(lo), float(hi),
