@@ -335,3 +335,38 @@ def test_tma_and_plain_kernels_agree(R, monkeypatch):
     po = pts1.cpu().clone().requires_grad_(True)
     ((O.baked_sum(po, 16.0, ts_odd) * w.cpu()).sum() + (O.baked_softor(po, 16.0, ts_odd) * w.cpu()).sum()).backward()
     close(p.grad, po.grad, rtol=1e-4, atol=1e-4 * float(po.grad.abs().max()))
+
+
+@pytest.mark.parametrize("want", [("sum",), ("softor",), ("sum", "softor")])
+@pytest.mark.parametrize("sum_t", [False, True])
+def test_every_kernel_variant(R, want, sum_t):
+    """Each template instantiation of the production kernels (sum only / soft-OR only / both, natural or transposed sum,
+    backward with and without the saved soft-OR output) against the oracle, plus the dense-radius (num_std = None) windows."""
+    gen = torch.Generator().manual_seed(33)
+    B, N, ts, sigma = 2, 250, [288, 224], 36.0
+    pts = (torch.rand(B, N, 2, generator=gen) * 0.98 + 0.01)
+    wS = torch.randn(B, ts[0], ts[1], generator=gen) if sum_t else torch.randn(B, ts[1], ts[0], generator=gen)
+    wO = torch.randn(B, ts[1], ts[0], generator=gen)
+    ws, wo = "sum" in want, "softor" in want
+    for ns, no in ((4, 5), (0, 0), (3, 2)):                # baked footprints / dense semantics / a soft-OR window tighter than its no-op radius (MASK_O kernels)
+        plan = R._SplatPlan(pts.cuda(), B, sigma, ts[0], ts[1], ns, no)
+        s, o = plan.forward(pts.cuda(), ws, wo, sum_t)
+        grads = []
+        for saved in (None, o) if wo else (None,):
+            grads.append(plan.backward(pts.cuda(), wS.cuda() if ws else None, wO.cuda() if wo else None, sum_t, saved))
+        for b in range(B):
+            p = pts[b].clone().requires_grad_(True)
+            tot = 0.0
+            if ws:
+                S = O.baked_sum(p, sigma, ts, num_std=ns, transposed=sum_t) if ns else O.reduce_sum(O.splat_dense(p, sigma, ts))
+                if not ns and sum_t:
+                    S = S.T
+                close(s[b], S.detach())
+                tot = tot + (S * wS[b]).sum()
+            if wo:
+                So = O.baked_softor(p, sigma, ts, num_std=no) if no else O.softor(O.splat_dense(p, sigma, ts))
+                close(o[b], So.detach())
+                tot = tot + (So * wO[b]).sum()
+            tot.backward()
+            for g in grads:
+                close(g[b], p.grad, rtol=1e-4, atol=1e-4 * float(p.grad.abs().max()))
