@@ -213,7 +213,7 @@ def main_ours(args):
     import fireflies_b200 as ff
     from fireflies_b200 import _native as nat
     from fireflies_b200.graphics import rasterization as R
-    from fireflies_b200.parallel import allreduce_sum_, max_over_ranks, shard_samples
+    from fireflies_b200.parallel import fold_allreduce, max_over_ranks, shard_samples
 
     B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
     hw = TS[0] * TS[1]
@@ -252,9 +252,8 @@ def main_ours(args):
         if rec: rec[3].record()
         d = plan.backward(ptsB, gS, gO, True, softor)      # like autograd: the forward's soft-OR output is kept for the backward
         if rec: rec[4].record()
-        dp = R.reduce_over_samples(d)
         cur.wait_stream(side)
-        allreduce_sum_(dp)
+        dp = fold_allreduce(d)                             # fold over the samples + allreduce over the ranks (one kernel on NVLink)
         if rec: rec[5].record()
         return dp
 

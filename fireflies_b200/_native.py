@@ -59,6 +59,7 @@ SIGNATURES = {
     "ffb_splat_fwd": (C.c_int, [C.POINTER(SplatDesc), _P, _P, _P, C.c_int, _P, _P]),
     "ffb_splat_bwd": (C.c_int, [C.POINTER(SplatDesc), _P, _P, _P, C.c_int, _P, _P, _P, _P]),
     "ffb_splat_bwd_l1": (C.c_int, [C.POINTER(SplatDesc), _P, _P, _P, C.c_int, _P, _P, _P, _P]),
+    "ffb_fold_allreduce": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, C.c_int32, C.c_int32, C.c_uint32, _P, _P, _P]),
     "ffb_reduce_sample_groups": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
     "ffb_reduce_over_samples": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
     "ffb_splat_dense_fwd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P]),

@@ -346,17 +346,20 @@ class PatternStep:
             gs, go = upstream
         if d is None:
             d = plan.backward(pts, gs, go, self.sum_t, o)
-        dp = R.reduce_over_samples(d) if self.B > 1 else d[0]
-        return self._finish(loss, dp, s, o, res)
+        return self._finish(loss, None, s, o, res, per_sample=d)
 
-    def _finish(self, loss, dp, s, o, res):
+    def _finish(self, loss, dp, s, o, res, per_sample=None):
         if res is not None:
             cur = torch.cuda.current_stream()
             cur.wait_stream(self._side)
             for t in (res.world, res.sampled, res.vertices):      # produced on the side stream, consumed by the caller on this one
                 if t is not None:
                     t.record_stream(cur)
-        self._allreduce(dp)
+        if per_sample is not None:
+            from .parallel import fold_allreduce
+            dp = fold_allreduce(per_sample, self.pg)        # fold over the samples + the step's only exchange, one kernel on NVLink
+        else:
+            self._allreduce(dp)
         self.last = (s, o, res)
         return loss, dp, res
 

@@ -880,6 +880,63 @@ __global__ void __launch_bounds__(256) reduce_groups_kernel(const float4* __rest
     }
 }
 
+// Fold over this rank's samples + one-shot all-reduce over NVLink peer memory, one kernel (the path's only
+// exchange, [N,2] floats per step).  A CTA folds 32 columns over the B samples like reduce_samples_kernel, PUSHES its 32
+// partial sums into slot [rank] of every peer's receive buffer (plain stores through the NVSwitch fabric), publishes them
+// with a system-scope fence and a per-(rank, CTA) flag written into every peer's flag array, waits until the flags of all
+// ranks for this CTA show the current epoch, then sums the `world` slots of its own buffer in rank order -- every rank adds
+// in the same order, so the result is bit-identical everywhere.  No grid-wide barrier: CTA c only depends on CTA c of the
+// peers, and all CTAs of the launch are resident.  Receive buffers are double buffered by epoch parity; the flags only grow.
+struct PeerTable {
+    float* recv[8];             // per rank: [2][world][row] receive slots (symmetric memory)
+    unsigned* flag[8];          // per rank: [world][n_cta] epochs
+};
+__global__ void __launch_bounds__(256) fold_allreduce_kernel(const float* __restrict__ in, int B, long long row, PeerTable pt, int rank, int world,
+                                                             unsigned epoch, float* __restrict__ out, int* __restrict__ err) {
+    __shared__ float part[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long j = (long long)blockIdx.x * 32 + lane;
+    const int per = (B + 7) / 8, b0 = w * per, b1 = min(b0 + per, B);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (j < row) {
+        int b = b0;
+        for (; b + 3 < b1; b += 4) {
+            s0 += in[(long long)b * row + j]; s1 += in[(long long)(b + 1) * row + j];
+            s2 += in[(long long)(b + 2) * row + j]; s3 += in[(long long)(b + 3) * row + j];
+        }
+        for (; b < b1; ++b) s0 += in[(long long)b * row + j];
+    }
+    part[w][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (w != 0) return;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += part[k][lane];
+    const size_t slot = ((size_t)(epoch & 1u) * world + rank) * row;
+    if (j < row)
+        for (int r = 0; r < world; ++r) pt.recv[r][slot + j] = s;                 // push: remote stores
+    __threadfence_system();
+    __syncwarp();
+    if (lane < world) {
+        unsigned* f = pt.flag[lane] + (size_t)rank * gridDim.x + blockIdx.x;       // my flag in peer `lane`'s array
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+        const unsigned* mine = pt.flag[rank] + (size_t)lane * gridDim.x + blockIdx.x;   // peer `lane`'s flag in my array
+        unsigned v = 0;
+        long long spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        } while ((int)(v - epoch) < 0 && ++spins < (1ll << 26));
+        if ((int)(v - epoch) < 0) atomicExch(err, 1);                              // a peer never arrived: report instead of hanging
+    }
+    __syncwarp();
+    if (j < row) {
+        const float* mybuf = pt.recv[rank] + (size_t)(epoch & 1u) * world * row;
+        float t = 0.f;
+        for (int r = 0; r < world; ++r) t += __ldcv(mybuf + (size_t)r * row + j);
+        out[j] = t;
+    }
+}
+
 // mean |a - b| per sample and its gradients.  grid = (row blocks, B); each CTA handles 32x32 texels so the
 // transposed operand is read/written through a shared-memory transpose.
 template <bool BT>
@@ -1149,6 +1206,24 @@ extern "C" int ffb_reduce_over_samples(const float* in, int32_t B, int64_t row_e
     if (!in || !out || B <= 0 || row_elems <= 0) return fail_arg(FFB_E_ARG, "reduce_over_samples: bad argument");
     const unsigned grid = (unsigned)((row_elems + 31) / 32);
     reduce_samples_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, B, row_elems, out);
+    FFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ffb_fold_allreduce(const float* in, int32_t B, int64_t row_elems, float* const* recv_bufs, uint32_t* const* flag_bufs,
+                                  int32_t rank, int32_t world, uint32_t epoch, float* out, int32_t* err_flag, void* stream) {
+    if (!in || !out || !recv_bufs || !flag_bufs || !err_flag || B <= 0 || row_elems <= 0) return fail_arg(FFB_E_ARG, "fold_allreduce: bad argument");
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail_arg(FFB_E_LIMIT, "fold_allreduce: 1..8 ranks of one NVLink domain");
+    if (epoch == 0) return fail_arg(FFB_E_ARG, "fold_allreduce: epochs start at 1 (the flag arrays start zeroed)");
+    PeerTable pt;
+    for (int r = 0; r < 8; ++r) {
+        pt.recv[r] = r < world ? recv_bufs[r] : nullptr;
+        pt.flag[r] = r < world ? flag_bufs[r] : nullptr;
+        if (r < world && (!pt.recv[r] || !pt.flag[r])) return fail_arg(FFB_E_ARG, "fold_allreduce: null peer pointer");
+    }
+    const unsigned grid = (unsigned)((row_elems + 31) / 32);
+    if (grid > (unsigned)kNumSMs * 8) return fail_arg(FFB_E_LIMIT, "fold_allreduce: every CTA of the launch must be resident (row_elems <= 37888)");
+    fold_allreduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, B, row_elems, pt, rank, world, epoch, out, err_flag);
     FFB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -124,6 +124,16 @@ FFB_API int ffb_reduce_over_samples(const float* in, int32_t B, int64_t row_elem
  * Rows must be 16-byte aligned multiples of 4 elements (FFB_E_UNSUPPORTED otherwise). */
 FFB_API int ffb_reduce_sample_groups(const float* in, int32_t B, int64_t row_elems, float* out, void* stream);
 
+/* The path's only exchange fused with the fold that precedes it: out[row_elems] = sum over ALL
+ * ranks of sum_b in[b, :], one kernel, over NVLink peer memory (no NCCL call).  recv_bufs[r] / flag_bufs[r] are host
+ * arrays of `world` DEVICE pointers into symmetric memory of rank r: recv f32 [2][world][row_elems] (double buffered
+ * by epoch parity), flags u32 [world][ceil(row_elems/32)] zero-initialised once.  `epoch` is 1, 2, 3, ... -- the same
+ * on every rank for the same step.  Each CTA pushes its partial sums into every peer's slot [rank], publishes a flag,
+ * waits for the peers' flags of the same CTA and adds the slots in rank order (bit-identical result on all ranks).
+ * err_flag (device int32) is set when a peer did not arrive within the spin bound.  row_elems <= 37888, world <= 8. */
+FFB_API int ffb_fold_allreduce(const float* in, int32_t B, int64_t row_elems, float* const* recv_bufs, uint32_t* const* flag_bufs,
+                       int32_t rank, int32_t world, uint32_t epoch, float* out, int32_t* err_flag, void* stream);
+
 /* API-compatibility dense splat: rasterize_points (rasterization.py:7-37) -> [N,ts1,ts0],
  * and its backward given the upstream gradient of that tensor. */
 FFB_API int ffb_splat_dense_fwd(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sigma,
