@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fireflies_b200.parallel import allreduce_sum_, max_over_ranks, shard_samples
+from fireflies_b200.parallel import allreduce_sum_, fold_allreduce, max_over_ranks, shard_samples
 
 
 def test_shard_samples_partitions_exactly():
@@ -41,6 +41,9 @@ def _worker(rank, world, port, total, n_pts):
         allreduce_sum_(part)
         assert torch.allclose(part, per_sample.sum(0), rtol=1e-12, atol=1e-12)
         assert max_over_ranks(float(rank + 1), "cpu") == float(world)
+        # the fused fold + exchange is a GPU kernel (peer memory or fold + NCCL): host tensors are refused, not summed on the CPU
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            fold_allreduce(per_sample[first:first + n].float())
     finally:
         dist.destroy_process_group()
 
