@@ -191,6 +191,19 @@ class SceneBatch:
                                           dtype=torch.int32, device=self.device)
 
     def _mesh_table(self, train: bool) -> nat.MeshTable:
+        # the table only changes when a mesh's animation frames do: cache it per mode (keyed by the frame tensors' addresses)
+        key = (train, tuple((id(a._anim_data_train), id(a._anim_data_eval)) if a is not None else None for a in self._anim_meshes))
+        cached = getattr(self, "_mt_cache", {}).get(train)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        mt = self._build_mesh_table(train)
+        if not hasattr(self, "_mt_cache"):
+            self._mt_cache, self._mt_keep = {}, {}
+        self._mt_cache[train] = (key, mt)
+        self._mt_keep[train] = list(self._frames_keepalive)
+        return mt
+
+    def _build_mesh_table(self, train: bool) -> nat.MeshTable:
         mt = nat.MeshTable()
         mt.M = len(self.meshes)
         self._frames_keepalive = []
