@@ -286,6 +286,9 @@ class _L1Fn(torch.autograd.Function):
     def forward(ctx, a, b, b_transposed):
         a_ = nat.require_cuda(a.detach().contiguous(), torch.float32, "a")
         b_ = nat.require_cuda(b.detach().contiguous(), torch.float32, "b")
+        ctx.single = a_.dim() == 2                          # one texture pair ([ts1, ts0]): scalar loss, like torch.nn.L1Loss
+        if ctx.single:
+            a_, b_ = a_.unsqueeze(0), b_.unsqueeze(0)
         B, ts1, ts0 = a_.shape
         loss = torch.empty(B, dtype=torch.float32, device=a_.device)
         ga, gb = torch.empty_like(a_), torch.empty_like(b_)
@@ -293,19 +296,20 @@ class _L1Fn(torch.autograd.Function):
                                                 loss.data_ptr(), ga.data_ptr(), gb.data_ptr(), nat.stream()), "ffb_l1_loss_fwd_bwd")
         nat.count(2)
         ctx.save_for_backward(ga, gb)
-        return loss
+        return loss[0] if ctx.single else loss
 
     @staticmethod
     def backward(ctx, g):
         ga, gb = ctx.saved_tensors
         g = g.reshape(-1, 1, 1)
-        return ga * g, gb * g, None
+        da, db = ga * g, gb * g
+        return (da[0], db[0], None) if ctx.single else (da, db, None)
 
 
 def l1_loss(a: torch.Tensor, b: torch.Tensor, b_transposed: bool = False) -> torch.Tensor:
     """Per-sample ``torch.nn.L1Loss()(a, b)`` (mean |a-b|) for ``a`` ``[B,ts1,ts0]`` and ``b`` in the same or the
     transposed (``baked_sum_2``) layout -- the loss of the in-tree pattern optimisation
-    (fireflies/graphics/rasterization.py:589-599).  Returns ``[B]``."""
+    (fireflies/graphics/rasterization.py:589-599).  Returns ``[B]`` (a scalar for one ``[ts1,ts0]`` pair)."""
     return _L1Fn.apply(a, b, b_transposed)
 
 

@@ -45,4 +45,23 @@ sc._meshes += [vf, la]; sc.train()
 sb = sc.batch(seed=1)
 ms = timed(lambda: sb.randomize(Bs))
 out["scene_randomize_config1_B32"] = {"ms": ms, "samples_per_s": Bs / (ms * 1e-3), "GBs": 24 * (V1 + V2) * Bs / (ms * 1e-3) / 1e9}
+# configs[0]: examples/09-style single pattern, 100 points into 512^2, L1(softor, sum) step through the autograd API + one rotate_z mesh
+import time
+from fireflies_b200.graphics import rasterization as R
+gen = torch.Generator().manual_seed(0)
+p0 = (torch.rand(100, 2, generator=gen) * 0.8 + 0.1).cuda().requires_grad_(True)
+sc1 = ff.Scene(P())
+m1 = ff.entity.Mesh("mesh-One", (torch.rand(10000, 3, generator=gen) * 2 - 1).cuda()); m1.rotate_z(-3.14159, 3.14159)
+sc1._meshes.append(m1); sc1.train()
+def c0_step():
+    p0.grad = None
+    m1.randomize(); m1.get_randomized_vertices()
+    s, o = R.splat_reduce(p0, 100.0, [512, 512], sum_transposed=True)
+    R.l1_loss(o, s).backward()
+for _ in range(5): c0_step()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(50): c0_step()
+torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 50
+out["config0_single_sample_step"] = {"ms": dt * 1e3, "samples_per_s": 1.0 / dt,
+                                     "note": "host-launch bound: randomize + vertices + bin + fwd + L1 + bwd through the reference-shaped API, wall clock"}
 print(json.dumps(out, indent=1))

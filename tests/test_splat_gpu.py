@@ -370,3 +370,19 @@ def test_every_kernel_variant(R, want, sum_t):
             tot.backward()
             for g in grads:
                 close(g[b], p.grad, rtol=1e-4, atol=1e-4 * float(p.grad.abs().max()))
+
+
+def test_l1_loss_single_pair_matches_torch(R):
+    """test_point_reg's loop through the reference-shaped API for ONE pattern: 2-D textures in, scalar loss out."""
+    gen = torch.Generator().manual_seed(2)
+    pts = (torch.rand(100, 2, generator=gen) * 0.8 + 0.1)
+    p = pts.cuda().requires_grad_(True)
+    s, o = R.splat_reduce(p, 100.0, [512, 512], sum_transposed=True)
+    loss = R.l1_loss(o, s)
+    assert loss.dim() == 0
+    loss.backward()
+    po = pts.clone().requires_grad_(True)
+    lo = O.l1_loss(O.baked_softor(po, 100.0, [512, 512]), O.baked_sum(po, 100.0, [512, 512], transposed=True))
+    lo.backward()
+    close(loss, lo.detach(), rtol=1e-5, atol=1e-9)
+    close(p.grad, po.grad, rtol=1e-4, atol=1e-4 * float(po.grad.abs().max()))
