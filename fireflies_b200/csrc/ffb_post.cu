@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include "ffb_common.cuh"
+#include "ffb_tma.cuh"
 
 namespace ffb {
 namespace post {
@@ -116,28 +117,12 @@ __device__ __forceinline__ void store4(const PostParams& q, int b, int y, int x0
     }
 }
 
-// ---- mbarrier / TMA PTX -------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
+// mbarrier / TMA PTX helpers: ffb_tma.cuh (shared with the splat kernels)
+using tma::mbar_init;
+using tma::mbar_expect_tx;
+using tma::mbar_wait;
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+    tma::load_3d(dst, map, bar, x, y, z);
 }
 
 // Blur (+ optional noise/clip) of one 128x32 tile.  USE_TMA = false is the fallback for W % 4 != 0 (TMA
@@ -429,21 +414,8 @@ static void gaussian_taps(int k, float sigma, float* w) {
     for (int i = 0; i < k; ++i) w[i] /= sum;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
+using tma::EncodeTiledFn;
+using tma::get_encode;
 
 // ---- silhouette -------------------------------------------------------------------------------
 // ApplySilhouette.post_process (fireflies/postprocessing/apply_silhouette.py:17-40): a filled disc of ones per frame,
