@@ -289,7 +289,17 @@ __global__ void __launch_bounds__(PREP_CTA, FFB_PREP_MINB) prepare_kernel(PrepPa
     for (int n = tid; n < q.N; n += PREP_CTA) {
         const float2 xy = reinterpret_cast<const float2*>(pts)[n];
         int win[12];
-        recs[n] = make_rec(q, xy.x, xy.y, q.windows ? win : nullptr);
+        PointRec rec = make_rec(q, xy.x, xy.y, q.windows ? win : nullptr);
+        if (FAST) {
+            // the warp-tile kernels need {p0, p1, window origin, union spans}: keep exactly that in the record's first 24 bytes
+            // (the reduction windows sc / sr / oc / orow are only read by the general kernels), so a list entry is a copy
+            const bool bs = q.baked_s != 0;
+            const int baked = (bs || !q.baked_o) ? (int)bs : 1, half = (bs || !q.baked_o) ? q.half_s : q.half_o;
+            rec.sc = __float_as_uint((float)origin_axis(rec.p0, baked, half));
+            rec.sr = __float_as_uint((float)origin_axis(rec.p1, baked, half));
+            rec.oc = rec.ur; rec.orow = rec.uc;
+        }
+        recs[n] = rec;
         if (q.windows) {
             int* w = q.windows + ((size_t)bin * q.N + n) * 12;
 #pragma unroll
@@ -382,17 +392,14 @@ __global__ void __launch_bounds__(PREP_CTA, FFB_PREP_MINB) prepare_kernel(PrepPa
                 FFB_CE(1,9) FFB_CE(5,13) FFB_CE(5,9) FFB_CE(3,11) FFB_CE(7,15) FFB_CE(7,11) FFB_CE(3,5) FFB_CE(7,9) FFB_CE(11,13)
                 FFB_CE(1,2) FFB_CE(3,4) FFB_CE(5,6) FFB_CE(7,8) FFB_CE(9,10) FFB_CE(11,12) FFB_CE(13,14)
 #undef FFB_CE
-                const bool bs = q.baked_s != 0;
-                const int baked = (bs || !q.baked_o) ? (int)bs : 1, half = (bs || !q.baked_o) ? q.half_s : q.half_o;
 #pragma unroll
                 for (int i = 0; i < WCH; ++i) {
-                    if (b + i < e) {
-                        const PointRec r = recs[l[i]];
-                        Entry en;
-                        en.p0 = r.p0; en.p1 = r.p1;
-                        en.f0 = (float)origin_axis(r.p0, baked, half); en.f1 = (float)origin_axis(r.p1, baked, half);
-                        en.ur = r.ur; en.uc = r.uc; en.idx = l[i]; en.pad = 0;
-                        entries[b + i] = en;
+                    if (b + i < e) {                          // entry = {p0, p1, f0, f1 | ur, uc, idx, 0}: two 128-bit words of the record
+                        const uint4* r = reinterpret_cast<const uint4*>(recs + l[i]);
+                        const uint4 a = r[0], c = r[1];
+                        uint4* dst = reinterpret_cast<uint4*>(entries + b + i);
+                        dst[0] = a;
+                        dst[1] = make_uint4(c.x, c.y, (unsigned)l[i], 0u);
                     }
                 }
             } else if (FAST) {
@@ -401,14 +408,11 @@ __global__ void __launch_bounds__(PREP_CTA, FFB_PREP_MINB) prepare_kernel(PrepPa
                     const int v = list[i];
                     int rank = 0;
                     for (int j = b; j < e; ++j) rank += list[j] < v;
-                    const PointRec r = recs[v];
-                    const bool bs = q.baked_s != 0;
-                    const int baked = (bs || !q.baked_o) ? (int)bs : 1, half = (bs || !q.baked_o) ? q.half_s : q.half_o;
-                    Entry en;
-                    en.p0 = r.p0; en.p1 = r.p1;
-                    en.f0 = (float)origin_axis(r.p0, baked, half); en.f1 = (float)origin_axis(r.p1, baked, half);
-                    en.ur = r.ur; en.uc = r.uc; en.idx = v; en.pad = 0;
-                    entries[b + rank] = en;
+                    const uint4* r = reinterpret_cast<const uint4*>(recs + v);
+                    const uint4 a = r[0], c = r[1];
+                    uint4* dst = reinterpret_cast<uint4*>(entries + b + rank);
+                    dst[0] = a;
+                    dst[1] = make_uint4(c.x, c.y, (unsigned)v, 0u);
                 }
             } else {
                 for (int i = b + 1; i < e; ++i) {
