@@ -260,6 +260,9 @@ def laser_cases(ff):
     laser5 = Laser(tr, inside.clone(), K01, 60.0, 0.01, 1000.0, device=CPU)
     laser5.randomize_laser_out_of_bounds()
     out.update(respawn_inside=npy(inside), respawn_inside_after=npy(laser5._rays))
+    # generate_uniform_rays_by_count (laser.py:40-66): deterministic
+    out["by_count_5x4"] = npy(Laser.generate_uniform_rays_by_count(5, 4, K01, device=CPU))
+    out["by_count_3x3_K"] = npy(Laser.generate_uniform_rays_by_count(3, 3, K, device=CPU))
     np.savez_compressed(os.path.join(OUT, "laser.npz"), **out)
     print("wrote laser")
 

@@ -380,3 +380,26 @@ def test_batched_hand_off_to_the_parameter_map(ff):
         assert list(inten) == res.attribute("emit-Spot", "intensity.value")[b].cpu().tolist()
         rough = params["mat-Mucosa.brdf_0.roughness.value"]
         assert float(rough) == float(res.attribute("mat-Mucosa", "brdf_0.roughness.value")[b, 0])
+
+
+def test_ray_generators(ff, golden):
+    """Laser.generate_uniform_rays_by_count (laser.py:40-66) against reference-generated values; generate_random_rays and
+    initRandomRays (laser.py:69-92,185-194) draw from torch's CUDA generator (the reference's CPU fixture cannot pin those):
+    structure only -- unit length, spawn box, determinism under a seed."""
+    g = golden("laser")
+    Laser = ff.projection.Laser
+    K01, K = T(g["K01"]).cuda(), T(g["K"]).cuda()
+    close(Laser.generate_uniform_rays_by_count(5, 4, K01), g["by_count_5x4"], rtol=1e-5, atol=1e-6)
+    close(Laser.generate_uniform_rays_by_count(3, 3, K), g["by_count_3x3_K"], rtol=1e-5, atol=1e-6)
+    torch.manual_seed(3)
+    a = Laser.generate_random_rays(64, K01)
+    torch.manual_seed(3)
+    b = Laser.generate_random_rays(64, K01)
+    assert torch.equal(a, b) and a.shape == (64, 3)
+    close(torch.linalg.norm(a, dim=1), torch.ones(64), rtol=1e-6, atol=1e-6)
+    back = a.clone(); back[:, 2] *= -1.0                       # undo the final z flip, project: spawned in 0.5 +- 0.05
+    ndc = ff.utils.math.transform_points(back, K01)[:, 0:2]
+    assert float((ndc - 0.5).abs().max()) <= 0.05 + 1e-4
+    laser = Laser(ff.entity.Transformable("projector"), a.clone(), K01, 60.0, 0.01, 1000.0)
+    laser.initRandomRays()
+    close(torch.linalg.norm(laser._rays, dim=1), torch.ones(64), rtol=1e-6, atol=1e-6)
