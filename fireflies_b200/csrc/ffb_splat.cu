@@ -788,7 +788,8 @@ static void fill_raster(const ffb_splat_desc* d, const Plan& p, const void* ws, 
 }
 
 // ---- dense API-compat kernels -----------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dense_fwd_kernel(const float* __restrict__ pts, int N, int ts0, int ts1, float sigma,
+// sx, sy: the scale applied to the points (texture_size for rasterize_points, 1 for rasterize_points_in_non_ndc)
+__global__ void __launch_bounds__(256) dense_fwd_kernel(const float* __restrict__ pts, int N, int ts0, int ts1, float sx, float sy, float sigma,
                                                         float rcp_sigma, float* __restrict__ out) {
     const size_t frame = (size_t)ts0 * ts1;
     const size_t total = frame * N;
@@ -796,8 +797,8 @@ __global__ void __launch_bounds__(256) dense_fwd_kernel(const float* __restrict_
         const int n = (int)(i / frame);
         const size_t t = i - (size_t)n * frame;
         const int r = (int)(t / ts0), c = (int)(t - (size_t)r * ts0);
-        const float dx = (float)c - pts[2 * n] * (float)ts0;
-        const float dy = (float)r - pts[2 * n + 1] * (float)ts1;
+        const float dx = (float)c - pts[2 * n] * sx;
+        const float dy = (float)r - pts[2 * n + 1] * sy;
         const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
         const float u = div_by(d2, sigma, rcp_sigma);
         const float w = __fmul_rn(u, u);
@@ -805,12 +806,12 @@ __global__ void __launch_bounds__(256) dense_fwd_kernel(const float* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(256) dense_bwd_kernel(const float* __restrict__ pts, int N, int ts0, int ts1, float sigma,
+__global__ void __launch_bounds__(256) dense_bwd_kernel(const float* __restrict__ pts, int N, int ts0, int ts1, float sx, float sy, float sigma,
                                                         float rcp_sigma, const float* __restrict__ g_out, float* __restrict__ d_pts) {
     // grid = (chunks, N): each CTA reduces a slice of one point's frame
     const int n = blockIdx.y;
     const size_t frame = (size_t)ts0 * ts1;
-    const float p0 = pts[2 * n] * (float)ts0, p1 = pts[2 * n + 1] * (float)ts1;
+    const float p0 = pts[2 * n] * sx, p1 = pts[2 * n + 1] * sy;
     const float* go = g_out + (size_t)n * frame;
     float a0 = 0.f, a1 = 0.f;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < frame; t += (size_t)gridDim.x * blockDim.x) {
@@ -831,8 +832,8 @@ __global__ void __launch_bounds__(256) dense_bwd_kernel(const float* __restrict_
     if (threadIdx.x == 0) {
         float s0 = 0.f, s1 = 0.f;
         for (int i = 0; i < 8; ++i) { s0 += red[0][i]; s1 += red[1][i]; }
-        atomicAdd(&d_pts[2 * n], s0 * 4.f * (float)ts0 * rcp_sigma);
-        atomicAdd(&d_pts[2 * n + 1], s1 * 4.f * (float)ts1 * rcp_sigma);
+        atomicAdd(&d_pts[2 * n], s0 * 4.f * sx * rcp_sigma);
+        atomicAdd(&d_pts[2 * n + 1], s1 * 4.f * sy * rcp_sigma);
     }
 }
 
@@ -1253,18 +1254,17 @@ extern "C" int ffb_reduce_sample_groups(const float* in, int32_t B, int64_t row_
     return 0;
 }
 
-extern "C" int ffb_splat_dense_fwd(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sigma, float* out, void* stream) {
+static int dense_fwd_impl(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sx, float sy, float sigma, float* out, void* stream) {
     if (!pts || !out || N <= 0 || ts0 <= 0 || ts1 <= 0 || !(sigma > 0.f)) return fail_arg(FFB_E_ARG, "splat_dense_fwd: bad argument");
     const size_t total = (size_t)N * ts0 * ts1;
     size_t blocks = (total + 255) / 256;
     if (blocks > (size_t)kNumSMs * 32) blocks = (size_t)kNumSMs * 32;
-    dense_fwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(pts, N, ts0, ts1, sigma, 1.0f / sigma, out);
+    dense_fwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(pts, N, ts0, ts1, sx, sy, sigma, 1.0f / sigma, out);
     FFB_CUDA(cudaGetLastError());
     return 0;
 }
-
-extern "C" int ffb_splat_dense_bwd(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sigma,
-                                   const float* g_out, float* d_pts, void* stream) {
+static int dense_bwd_impl(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sx, float sy, float sigma, const float* g_out,
+                          float* d_pts, void* stream) {
     if (!pts || !g_out || !d_pts || N <= 0 || ts0 <= 0 || ts1 <= 0 || !(sigma > 0.f)) return fail_arg(FFB_E_ARG, "splat_dense_bwd: bad argument");
     if (N > 65535) return fail_arg(FFB_E_LIMIT, "splat_dense_bwd: N > 65535");
     cudaStream_t st = as_stream(stream);
@@ -1273,9 +1273,24 @@ extern "C" int ffb_splat_dense_bwd(const float* pts, int32_t N, int32_t ts0, int
     unsigned chunks = (unsigned)((frame + 256 * 16 - 1) / (256 * 16));
     if (chunks > 64) chunks = 64;
     if (chunks < 1) chunks = 1;
-    dense_bwd_kernel<<<dim3(chunks, N), 256, 0, st>>>(pts, N, ts0, ts1, sigma, 1.0f / sigma, g_out, d_pts);
+    dense_bwd_kernel<<<dim3(chunks, N), 256, 0, st>>>(pts, N, ts0, ts1, sx, sy, sigma, 1.0f / sigma, g_out, d_pts);
     FFB_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int ffb_splat_dense_fwd(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sigma, float* out, void* stream) {
+    return dense_fwd_impl(pts, N, ts0, ts1, (float)ts0, (float)ts1, sigma, out, stream);
+}
+extern "C" int ffb_splat_dense_bwd(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sigma,
+                                   const float* g_out, float* d_pts, void* stream) {
+    return dense_bwd_impl(pts, N, ts0, ts1, (float)ts0, (float)ts1, sigma, g_out, d_pts, stream);
+}
+extern "C" int ffb_splat_dense_px_fwd(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sigma, float* out, void* stream) {
+    return dense_fwd_impl(pts, N, ts0, ts1, 1.f, 1.f, sigma, out, stream);
+}
+extern "C" int ffb_splat_dense_px_bwd(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sigma,
+                                      const float* g_out, float* d_pts, void* stream) {
+    return dense_bwd_impl(pts, N, ts0, ts1, 1.f, 1.f, sigma, g_out, d_pts, stream);
 }
 
 extern "C" int ffb_l1_loss_fwd_bwd(const float* a, const float* b, int b_transposed, int32_t B, int32_t ts0, int32_t ts1,

@@ -200,25 +200,25 @@ def splat_windows(points: torch.Tensor, sigma, texture_size, num_std_sum: int = 
 
 class _DenseFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, points, sigma, ts0, ts1):
+    def forward(ctx, points, sigma, ts0, ts1, in_pixels=False):
         pts = _points(points.detach())
         N = pts.shape[0]
         out = torch.empty((N, ts1, ts0), dtype=torch.float32, device=pts.device)
-        nat.check(nat.lib().ffb_splat_dense_fwd(pts.data_ptr(), N, ts0, ts1, sigma, out.data_ptr(), nat.stream()),
-                  "ffb_splat_dense_fwd")
+        fn = nat.lib().ffb_splat_dense_px_fwd if in_pixels else nat.lib().ffb_splat_dense_fwd
+        nat.check(fn(pts.data_ptr(), N, ts0, ts1, sigma, out.data_ptr(), nat.stream()), "ffb_splat_dense_fwd")
         nat.count()
-        ctx.pts, ctx.args = pts, (sigma, ts0, ts1)
+        ctx.pts, ctx.args = pts, (sigma, ts0, ts1, in_pixels)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        sigma, ts0, ts1 = ctx.args
+        sigma, ts0, ts1, in_pixels = ctx.args
         g = g.contiguous().float()
         d = torch.empty_like(ctx.pts)
-        nat.check(nat.lib().ffb_splat_dense_bwd(ctx.pts.data_ptr(), ctx.pts.shape[0], ts0, ts1, sigma, g.data_ptr(),
-                                                d.data_ptr(), nat.stream()), "ffb_splat_dense_bwd")
+        fn = nat.lib().ffb_splat_dense_px_bwd if in_pixels else nat.lib().ffb_splat_dense_bwd
+        nat.check(fn(ctx.pts.data_ptr(), ctx.pts.shape[0], ts0, ts1, sigma, g.data_ptr(), d.data_ptr(), nat.stream()), "ffb_splat_dense_bwd")
         nat.count(2)
-        return d, None, None, None
+        return d, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------------------
@@ -232,6 +232,15 @@ def rasterize_points(points: torch.Tensor, sigma: float, texture_size: torch.Ten
     _device_ok(device)
     ts0, ts1 = _ts(texture_size)
     return _DenseFn.apply(points, _sigma(sigma), ts0, ts1)
+
+
+def rasterize_points_in_non_ndc(points: torch.Tensor, sigma: float, texture_size: torch.Tensor,
+                                device: torch.device = torch.device("cuda")) -> torch.Tensor:
+    """fireflies/graphics/rasterization.py:38-63 -- ``rasterize_points`` for points already in texel units (no scaling by
+    ``texture_size``): ``points[:,0]`` pairs with the column index, ``points[:,1]`` with the row index."""
+    _device_ok(device)
+    ts0, ts1 = _ts(texture_size)
+    return _DenseFn.apply(points, _sigma(sigma), ts0, ts1, True)
 
 
 def softor(texture: torch.Tensor, dim=0, keepdim: bool = False) -> torch.Tensor:

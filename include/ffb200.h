@@ -140,6 +140,12 @@ FFB_API int ffb_splat_dense_fwd(const float* pts, int32_t N, int32_t ts0, int32_
                         float* out, void* stream);
 FFB_API int ffb_splat_dense_bwd(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sigma,
                         const float* g_out, float* d_pts, void* stream);
+/* The same for points given in texel units (rasterize_points_in_non_ndc, fireflies/graphics/rasterization.py:38-63:
+ * no multiplication by texture_size). */
+FFB_API int ffb_splat_dense_px_fwd(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sigma,
+                           float* out, void* stream);
+FFB_API int ffb_splat_dense_px_bwd(const float* pts, int32_t N, int32_t ts0, int32_t ts1, float sigma,
+                           const float* g_out, float* d_pts, void* stream);
 
 /* ---- line and depth rasterisers ------------------------------------------------
  * lines f32 [L,2,2] = (start, end) x (x, y) in units of the texture size (16-byte aligned); the squared

@@ -101,6 +101,17 @@ def rasterize_lines(lines: torch.Tensor, sigma, texture_size) -> torch.Tensor:
     return torch.exp(-(d * d) / (s * s))                                                 # :153
 
 
+def splat_dense_px(points_px: torch.Tensor, sigma, texture_size) -> torch.Tensor:
+    """rasterize_points_in_non_ndc (graphics/rasterization.py:38-63): the dense splat for points in texel units."""
+    ts0, ts1 = _as_ts(texture_size)
+    cols = torch.arange(ts0, dtype=F32).view(1, 1, ts0)
+    rows = torch.arange(ts1, dtype=F32).view(1, ts1, 1)
+    dc = cols - points_px[:, 0].to(F32).view(-1, 1, 1)             # :52  (y grid = column index) - points[:, 0]
+    dr = rows - points_px[:, 1].to(F32).view(-1, 1, 1)             # :53
+    d2 = dc * dc + dr * dr
+    return torch.exp(-torch.pow(d2 / _sigma_f32(sigma), 2))         # :58
+
+
 def rasterize_depth(points: torch.Tensor, depth_vals: torch.Tensor, sigma, texture_size) -> torch.Tensor:
     """rasterize_depth (graphics/rasterization.py:66-104): the dense point splat, normalised by its per-point maximum
     over the frame (:96-99), scaled by the point's depth (:104).  ``depth_vals`` is ``[N,1]``."""

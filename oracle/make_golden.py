@@ -343,6 +343,13 @@ def line_depth_cases(ff):
         levels.append(npy(R.softor(d, keepdim=True)))
     for i, lv in enumerate(levels):
         out[f"depth_level{i}"] = lv
+    # rasterize_points_in_non_ndc (rasterization.py:38-63): points in texel units
+    ppx = torch.tensor([[3.25, 7.5], [20.0, 11.0], [-2.0, 5.0], [39.5, 23.75]])
+    lp = ppx.clone().requires_grad_(True)
+    tex = R.rasterize_points_in_non_ndc(lp, 6.0, torch.tensor([40, 24]), device=CPU)
+    gw2 = torch.randn(4, 24, 40, generator=torch.Generator().manual_seed(8))
+    (tex * gw2).sum().backward()
+    out.update(px_points=npy(ppx), px_dense=npy(tex), px_w=npy(gw2), px_grad=npy(lp.grad))
     np.savez_compressed(os.path.join(OUT, "lines_depth.npz"), **out)
 
 

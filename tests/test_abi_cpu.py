@@ -83,11 +83,12 @@ def test_api_surface_matches_reference_names():
     import fireflies_b200 as ff
     for mod, names in {
         ff.graphics.rasterization: ["rasterize_points", "softor", "sum", "baked_sum", "baked_sum_2", "baked_softor",
-                                    "baked_softor_2", "rasterize_points_baked_softor", "rasterize_points_baked_sum"],
+                                    "baked_softor_2", "rasterize_points_baked_softor", "rasterize_points_baked_sum",
+                                    "rasterize_points_in_non_ndc", "rasterize_lines", "rasterize_depth", "subsampled_point_raster"],
         ff.utils.math: ["getYawTransform", "getPitchTransform", "getRollTransform", "randomBetweenTensors", "toMat4x4",
                         "transform_points", "transform_directions", "convert_points_to_homogeneous"],
         ff.sampling: ["Sampler", "UniformSampler", "UniformScalarToVec3Sampler", "GaussianSampler", "AnimationSampler",
-                      "UniformIntegerSampler"],
+                      "UniformIntegerSampler", "NoiseTextureLerpSampler"],
         ff.entity: ["Transformable", "Mesh", "Curve"],
         ff.projection: ["Camera", "Laser"],
         ff.postprocessing: ["BasePostProcessingFunction", "PostProcessor", "GaussianBlur", "WhiteNoise", "ApplySilhouette"],
@@ -102,6 +103,7 @@ def test_api_surface_matches_reference_names():
               "sample_animation", "get_vertices", "set_vertices"]:
         assert hasattr(ff.entity.Mesh, n), n
     for n in ["generate_uniform_rays", "projectRaysToNDC", "projectNDCPointsToWorld", "generateTexture", "clamp_to_fov",
-              "normalize_rays", "save", "rays", "originPerRay"]:
+              "normalize_rays", "save", "rays", "originPerRay", "generate_uniform_rays_by_count", "generate_random_rays",
+              "initRandomRays", "randomize_laser_out_of_bounds", "randomize_camera_out_of_bounds", "render_epipolar_lines"]:
         assert hasattr(ff.projection.Laser, n), n
     assert ff.scene is ff.Scene

@@ -120,3 +120,14 @@ def test_epipolar_lines(R):
     lo2 = O.transform_points(O.transform_points(lo.cpu(), w2c), Kc.float())[:, 0:2]
     hi2 = O.transform_points(O.transform_points(hi.cpu(), w2c), Kc.float())[:, 0:2]
     close(tex, O.rasterize_lines(torch.stack([lo2, hi2], dim=1), 6.0, [64, 48]))
+
+
+def test_points_in_texel_units(R, golden):
+    """rasterize_points_in_non_ndc (rasterization.py:38-63), forward and gradient against reference-generated values."""
+    g = golden("lines_depth")
+    p = T(g["px_points"]).cuda().requires_grad_(True)
+    tex = R.rasterize_points_in_non_ndc(p, 6.0, T(np.array([40, 24])))
+    close(tex, g["px_dense"])
+    (tex * T(g["px_w"]).cuda()).sum().backward()
+    ref = g["px_grad"]
+    close(p.grad, ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())

@@ -262,6 +262,7 @@ def test_lines_and_depth_match_reference_fixture(golden):
     np.testing.assert_allclose(d.numpy(), g["depth_dense"], rtol=1e-6, atol=1e-9)
     for i, lv in enumerate(O.subsampled_point_raster(pts, 3, float(g["depth_sigma"]), g["depth_ts"].tolist())):
         np.testing.assert_allclose(lv.numpy(), g[f"depth_level{i}"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(O.splat_dense_px(T(g["px_points"]), 6.0, [40, 24]).numpy(), g["px_dense"], rtol=1e-6, atol=1e-9)
 
 
 def _perlin_angles(g, name):
