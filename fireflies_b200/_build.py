@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libffb200.so")
-SOURCES = ["ffb_api.cu", "ffb_splat.cu", "ffb_lines.cu", "ffb_scene.cu", "ffb_post.cu"]
+SOURCES = ["ffb_api.cu", "ffb_splat.cu", "ffb_lines.cu", "ffb_scene.cu", "ffb_post.cu", "ffb_curve.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

@@ -11,10 +11,12 @@ from __future__ import annotations
 import math
 from typing import List
 
+import numpy as np
 import torch
 
 from .. import _native as nat
 from ..graphics import rasterization
+from ..sampling import poisson
 from ..utils import math as ffmath
 from .camera import Camera
 
@@ -61,6 +63,24 @@ class Laser(Camera):
         rays[:, 2] *= -1.0
         return rays
 
+    @staticmethod
+    def generate_blue_noise_rays(image_size_x: int, image_size_y: int, num_beams: int, intrinsic_matrix: torch.Tensor,
+                                 device: torch.device = torch.device("cuda")) -> torch.Tensor:
+        """laser.py:94-145: Poisson-disk samples (radius chosen for roughly ``num_beams`` points) in the image box,
+        scaled to [0,1]^2, un-projected through the intrinsics, normalised, z flipped.  The sample count is whatever
+        the dart throwing yields, as in the reference."""
+        poisson_radius = math.sqrt((image_size_x * image_size_y) / (math.pi * num_beams))
+        poisson_radius += poisson_radius / 4.0
+        im = np.ones([image_size_x, image_size_y]) * poisson_radius
+        _, poisson_samples = poisson.bridson(im)
+        poisson_samples = torch.tensor(poisson_samples) / torch.tensor([image_size_x, image_size_y])     # fp64, like the reference
+        temp = torch.ones([poisson_samples.shape[0], 3]) * -1.0
+        temp[:, 0:2] = poisson_samples
+        rays = ffmath.transform_points(temp.to(device), intrinsic_matrix.inverse())
+        rays = rays / torch.linalg.norm(rays, dim=-1, keepdims=True)
+        rays[:, 2] *= -1.0
+        return rays
+
     def __init__(self, transformable, ray_directions, perspective: torch.Tensor, max_fov: float, near_clip: float = 0.01,
                  far_clip: float = 1000.0, device: torch.device = torch.device("cuda")):
         super().__init__(transformable, perspective, max_fov, near_clip, far_clip, device)
@@ -84,6 +104,9 @@ class Laser(Camera):
         spawned = torch.rand(self._rays.shape, device=self.device) * 2.0 - 1.0
         spawned[:, 2] = 1.0
         self._rays = self.normalize(self.projectNDCPointsToWorld(spawned))
+
+    def initPoissonDiskSamples(self, width, height, radius):
+        return None                                   # a stub in the reference as well (laser.py:196-197)
 
     def clamp_to_fov(self, clamp_val: float = 0.95, epsilon: float = 0.0001) -> None:
         """laser.py:199-206, one fused launch (project, clamp, un-project, renormalise)."""

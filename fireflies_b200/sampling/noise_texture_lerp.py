@@ -45,6 +45,19 @@ def perlin_texture(shape, res, octaves: int, persistence: float, angles: List[to
     return noise, out
 
 
+def rand_perlin_2d(shape, res, fade=None, device=torch.device("cuda")) -> torch.Tensor:
+    """noise_texture_lerp.py:8-50: one octave; draws ``torch.rand(res[0]+1, res[1]+1)`` like the reference.  Only the
+    reference's default quintic fade is compiled into the kernel."""
+    if fade is not None:
+        raise NotImplementedError("rand_perlin_2d: only the default fade 6t^5 - 15t^4 + 10t^3 is supported")
+    return perlin_texture(shape, res, 1, 1.0, perlin_angles(res, 1), device=device)[0]
+
+
+def rand_perlin_2d_octaves(shape, res, octaves=1, persistence=0.5, device=torch.device("cuda")) -> torch.Tensor:
+    """noise_texture_lerp.py:53-62."""
+    return perlin_texture(shape, res, octaves, persistence, perlin_angles(res, octaves), device=device)[0]
+
+
 class NoiseTextureLerpSampler(base.Sampler):
     def __init__(self, color_a: torch.Tensor, color_b: torch.Tensor, texture_shape: List[int], eval_step_size: float = 0.01,
                  device: torch.device = torch.device("cuda")) -> None:

@@ -1,5 +1,6 @@
 """``fireflies/utils/io.py`` subset: config reader and the pytorch3d-style projection matrix
-(utils/io.py:9-68).  ``importBlenderNurbsObj`` needs geomdl and is out of scope."""
+(utils/io.py:9-68) and the Blender NURBS .obj reader (utils/io.py:77-108; it returns this package's ``NurbsCurve``
+instead of a geomdl ``NURBS.Curve``)."""
 import math as _math
 from pathlib import Path
 
@@ -29,3 +30,18 @@ def build_projection_matrix(fov: float, near_clip: float, far_clip: float,
     K[2, 2] = -1.0 * far_clip / (far_clip - near_clip)
     K[2, 3] = -(far_clip * near_clip) / (far_clip - near_clip)
     return K.to(device)
+
+
+def importBlenderNurbsObj(path, device: torch.device = torch.device("cuda")):
+    """utils/io.py:77-108: control points from the ``v`` lines, the degree from ``deg``, the knot vector from ``parm u``."""
+    from .nurbs import NurbsCurve
+    control_points, deg, knotvector = [], None, None
+    with open(path, "r") as obj_file:
+        for line in obj_file:
+            if line.startswith("v "):
+                control_points.append([float(v) for v in line[2:].split()])
+            elif line.startswith("deg "):
+                deg = int(line[4:])
+            elif line.startswith("parm u "):
+                knotvector = [float(v) for v in line[7:].split()]
+    return NurbsCurve(deg, control_points, knotvector, device=device)

@@ -64,6 +64,20 @@ def rotation_matrix_from_vectors(v1, v2):
     return torch.eye(3, device=v1.device) + skew + torch.mm(skew, skew) * (1 - dot) / torch.norm(cross) ** 2
 
 
+def rotation_matrix_from_vectors_with_fixed_up(v1, v2, up_vector=torch.tensor([0.0, 0.0, 1.0])):
+    """utils/math.py:108-159.  The reference computes the Rodrigues matrix, uses it only to measure the angle between the
+    rotated and the original up vector, and returns ``eye + normalize(skew, dim=0) * angle`` -- reproduced as written."""
+    up_vector = F.normalize(up_vector.to(v1.device), dim=0)
+    rotation_matrix = rotation_matrix_from_vectors(v1, v2)
+    cross = torch.linalg.cross(F.normalize(v1, dim=0), F.normalize(v2, dim=0))
+    skew = torch.zeros(3, 3, dtype=torch.float32, device=v1.device)
+    skew[0, 1], skew[0, 2] = -cross[2], cross[1]
+    skew[1, 0], skew[1, 2] = cross[2], -cross[0]
+    skew[2, 0], skew[2, 1] = -cross[1], cross[0]
+    correction_angle = torch.acos(torch.dot(torch.mv(rotation_matrix, up_vector), up_vector))
+    return torch.eye(3, device=v1.device) + F.normalize(skew, dim=0) * correction_angle
+
+
 def singleRandomBetweenTensors(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     assert a.size() == b.size()
     assert a.device == b.device

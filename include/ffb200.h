@@ -16,7 +16,7 @@
  *   - return value: 0 = OK, >0 = cudaError_t from a launch/runtime call, <0 = argument error
  *     (FFB_E_*); ffb_last_error_string() describes the last failure on the calling thread;
  *   - no global mutable state; re-entrant across streams;
- *   - all floating point is IEEE fp32 ("f32"); index outputs are int32.
+ *   - all floating point is IEEE fp32 ("f32") except the NURBS evaluator (fp64, section 5); index outputs are int32.
  *
  * Texture orientation: "natural" = [ts1, ts0] row-major, rows pair with points[:,1] and columns
  * with points[:,0] -- the orientation of rasterize_points(...).sum(0)
@@ -333,6 +333,38 @@ FFB_API int ffb_silhouette(const float* img, const int32_t* discs, int32_t B, in
 FFB_API int ffb_perlin_texture(const float* angles, int32_t H, int32_t W, int32_t res0, int32_t res1, int32_t octaves,
                        double persistence, const float* color_a, const float* color_b, float* noise_scratch,
                        int32_t* minmax_scratch, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 5. NURBS-curve camera paths and batched intersections  (fireflies/entity/curve.py, utils/intersections.py)
+ * ------------------------------------------------------------------------------------------ */
+
+#define FFB_NURBS_MAX_DEGREE 7
+
+/* geomdl==5.3.1 NURBS.Curve.evaluate_single (the evaluator behind fireflies/entity/curve.py:52-53,74; the curve
+ * object is built by fireflies/utils/io.py:77-108) for B parameters at once, in fp64 like geomdl's Python floats:
+ * linear knot-span walk, the degree+1 non-vanishing basis functions (Piegl & Tiller A2.2), homogeneous sum,
+ * perspective divide (A4.1).  ctrlw f64 [n_ctrl,4] = (x*w, y*w, z*w, w); knots f64 [n_ctrl+degree+1], normalised to
+ * [0,1] by the caller (geomdl does so on assignment); t f64 [B] in [0,1]; out f64 [B,3].  geomdl is absent from the
+ * reference tree: parity with it is unpinned (see oracle/ff_oracle.py). */
+FFB_API int ffb_nurbs_curve_eval(const double* ctrlw, const double* knots, int32_t n_ctrl, int32_t degree, const double* t,
+                                 int32_t B, double* out, void* stream);
+
+/* Curve.randomize's matrix for B path parameters (fireflies/entity/curve.py:48-96):
+ *   out_world[b] = T(C(t_b)) @ toMat4x4(rotation_matrix_from_vectors([0,1,0], d_b)) @ world,
+ *   d_b = f32(C(t_b + dt)) - f32(C(t_b)) with x and z negated (dt = 0.001 in the reference).
+ * world f32 [16]; out_world / out_rot (sample_rotation) / out_trans (sample_translation) f32 [B,16], each nullable. */
+FFB_API int ffb_curve_pose(const double* ctrlw, const double* knots, int32_t n_ctrl, int32_t degree, const double* t, int32_t B,
+                           double dt, const float* world, float* out_world, float* out_rot, float* out_trans, void* stream);
+
+/* rayPlane (fireflies/utils/intersections.py:5-12): t_out[i] = ((po_i - o_i) . n_i) / (n_i . d_i), a denominator
+ * below 1e-6 in magnitude replaced by denom/denom.  All inputs f32 [N,3]; t_out f32 [N]. */
+FFB_API int ffb_ray_plane(const float* origin, const float* direction, const float* plane_origin, const float* plane_normal,
+                          int32_t N, float* t_out, void* stream);
+
+/* sphereSphere (fireflies/utils/intersections.py:26-33): hit[i] = |a_i - b_i|^2 <= (ra_i + rb_i)^2.
+ * a, b f32 [N,D]; ra, rb f32 [N]; hit u8 [N]. */
+FFB_API int ffb_sphere_sphere(const float* a, const float* ra, const float* b, const float* rb, int32_t N, int32_t D, uint8_t* hit,
+                              void* stream);
 
 #ifdef __cplusplus
 }

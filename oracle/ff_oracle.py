@@ -597,3 +597,161 @@ def silhouette(image: torch.Tensor, cx: int, cy: int, r: int) -> torch.Tensor:
     yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
     mask = (((xx - cx) ** 2 + (yy - cy) ** 2) <= r * r).to(F32)
     return image * gaussian_blur2d(mask, (11, 11), (5.0, 5.0))
+
+
+# ----------------------------------------------------------------------------
+# NURBS-curve camera path  (fireflies/entity/curve.py:48-96, utils/io.py:77-108)
+# ----------------------------------------------------------------------------
+# The curve arithmetic lives in geomdl==5.3.1 (requirements.txt:16), which is NOT under /root/reference and is not
+# installed: PARITY UNPINNED for the evaluator.  It is restated from the published algorithms geomdl implements
+# (Piegl & Tiller, "The NURBS Book": knot span search, A2.2 BasisFuns, A4.1 CurvePoint) with geomdl's conventions as
+# recalled from its 5.3.1 sources: knot vectors are normalised to [0, 1] on assignment, the span is found by a linear
+# walk, evaluation is Python floats (fp64), control points without weights get weight 1.  Anchors: Bernstein closed
+# form, the rational quadratic arc, partition of unity (tests/test_oracle_golden.py) and the reference's own Curve
+# methods run on top of this evaluator (oracle/make_golden.py::curve_cases).
+def nurbs_normalize_knots(knots: Sequence[float]) -> List[float]:
+    k0, k1 = float(knots[0]), float(knots[-1])
+    return [float("{:.18f}".format((float(k) - k0) / (k1 - k0))) for k in knots]
+
+
+def nurbs_find_span(degree: int, knots: Sequence[float], n_ctrl: int, t: float) -> int:
+    span = degree + 1
+    while span < n_ctrl and knots[span] <= t:
+        span += 1
+    return span - 1
+
+
+def nurbs_basis(degree: int, knots: Sequence[float], span: int, t: float) -> List[float]:
+    """The degree+1 non-vanishing B-spline basis functions at t (NURBS Book A2.2)."""
+    left, right, N = [0.0] * (degree + 1), [0.0] * (degree + 1), [1.0] * (degree + 1)
+    for j in range(1, degree + 1):
+        left[j] = t - knots[span + 1 - j]
+        right[j] = knots[span + j] - t
+        saved = 0.0
+        for r in range(j):
+            temp = N[r] / (right[r + 1] + left[j - r])
+            N[r] = saved + right[r + 1] * temp
+            saved = left[j - r] * temp
+        N[j] = saved
+    return N
+
+
+def nurbs_curve_point(ctrlpts: Sequence[Sequence[float]], knots: Sequence[float], degree: int, t: float,
+                      weights: Optional[Sequence[float]] = None) -> List[float]:
+    """Rational curve point in fp64 (NURBS Book A4.1): ``knots`` already normalised, ``t`` in [0, 1]."""
+    n = len(ctrlpts)
+    w = [1.0] * n if weights is None else [float(x) for x in weights]
+    span = nurbs_find_span(degree, knots, n, t)
+    N = nurbs_basis(degree, knots, span, t)
+    acc = [0.0, 0.0, 0.0, 0.0]
+    for i in range(degree + 1):
+        c = span - degree + i
+        pw = [float(ctrlpts[c][0]) * w[c], float(ctrlpts[c][1]) * w[c], float(ctrlpts[c][2]) * w[c], w[c]]
+        for d in range(4):
+            acc[d] = acc[d] + N[i] * pw[d]
+    return [acc[0] / acc[3], acc[1] / acc[3], acc[2] / acc[3]]
+
+
+def rotation_matrix_from_vectors(v1: torch.Tensor, v2: torch.Tensor) -> torch.Tensor:
+    """utils/math.py:67-105 (Rodrigues), fp32."""
+    v1 = torch.nn.functional.normalize(v1, dim=0)
+    v2 = torch.nn.functional.normalize(v2, dim=0)
+    c = torch.linalg.cross(v1, v2)
+    d = torch.dot(v1, v2)
+    K = torch.tensor([[0, -c[2], c[1]], [c[2], 0, -c[0]], [-c[1], c[0], 0]], dtype=F32)
+    return torch.eye(3) + K + torch.mm(K, K) * (1 - d) / torch.norm(c) ** 2
+
+
+def rotation_matrix_from_vectors_with_fixed_up(v1, v2, up=None) -> torch.Tensor:
+    """utils/math.py:108-159: the Rodrigues matrix is computed and then DISCARDED -- the function returns
+    ``eye + normalize(K, dim=0) * acos(dot(R @ up, up))`` (column-normalised skew matrix times the correction angle)."""
+    up = torch.tensor([0.0, 0.0, 1.0]) if up is None else up
+    v1n = torch.nn.functional.normalize(v1, dim=0)
+    v2n = torch.nn.functional.normalize(v2, dim=0)
+    up = torch.nn.functional.normalize(up, dim=0)
+    c = torch.linalg.cross(v1n, v2n)
+    K = torch.tensor([[0, -c[2], c[1]], [c[2], 0, -c[0]], [-c[1], c[0], 0]], dtype=F32)
+    R = rotation_matrix_from_vectors(v1, v2)
+    angle = torch.acos(torch.dot(torch.mv(R, up), up))
+    return torch.eye(3) + torch.nn.functional.normalize(K, dim=0) * angle
+
+
+def curve_pose(ctrlpts, knots, degree: int, t: float, world: torch.Tensor, weights=None, dt: float = 0.001) -> torch.Tensor:
+    """Curve.randomize's matrix (entity/curve.py:48-96): ``T(C(t)) @ toMat4x4(R([0,1,0] -> d)) @ W`` with
+    ``d = C(t + dt) - C(t)`` (fp32 difference of the fp64 points rounded to fp32), x and z negated."""
+    p1 = torch.tensor(nurbs_curve_point(ctrlpts, knots, degree, t + dt, weights), dtype=F32)
+    p0 = torch.tensor(nurbs_curve_point(ctrlpts, knots, degree, t, weights), dtype=F32)
+    d = p1 - p0
+    d[0] *= -1.0
+    d[2] *= -1.0
+    R = to_mat4(rotation_matrix_from_vectors(torch.tensor([0.0, 1.0, 0.0]), d))
+    T = torch.eye(4)
+    T[0:3, 3] = p0
+    return T @ R @ world
+
+
+# ----------------------------------------------------------------------------
+# Poisson-disk initialisation  (fireflies/sampling/poisson.py:16-116, projection/laser.py:94-145)
+# ----------------------------------------------------------------------------
+def bridson(radius: np.ndarray, k: int = 30, rng=np.random):
+    """Bridson's Poisson-disk sampling with a per-cell radius map, consuming the numpy stream draw for draw like the
+    reference: 2 draws for the seed point, then per round one ``randint`` (which active point) and per attempt one draw
+    for the distance in [r, 2r) and one for the angle; a round does not stop at its first accepted point; an active point
+    is retired only when all k attempts failed.  Occupancy test: any occupied cell in the square window of half-width
+    ``ceil(r)`` around the candidate's cell (poisson.py:82-98)."""
+    H, W = radius.shape
+    occ = np.zeros((H, W), dtype=bool)
+    first = (rng.random() * H, rng.random() * W)
+    occ[int(np.floor(first[0])), int(np.floor(first[1]))] = True
+    active, pts = [first], [first]
+    while active:
+        a = rng.randint(len(active))
+        ay, ax = active[a]
+        cy, cx = int(np.floor(ay)), int(np.floor(ax))
+        found = False
+        for _ in range(k):
+            dist = radius[cy, cx] * (rng.random() + 1)
+            ang = 2 * np.pi * rng.random()
+            ny, nx = ay + dist * np.sin(ang), ax + dist * np.cos(ang)
+            if not (0 <= nx <= W and 0 <= ny <= H):
+                continue
+            gy, gx = int(np.floor(ny)), int(np.floor(nx))
+            rr = int(np.ceil(radius[gy, gx]))     # IndexError at ny == H / nx == W exactly, like the reference
+            if occ[max(gy - rr, 0):min(gy + rr + 1, H), max(gx - rr, 0):min(gx + rr + 1, W)].any():
+                continue
+            active.append((ny, nx)); pts.append((ny, nx))
+            occ[gy, gx] = True
+            found = True
+        if not found:
+            del active[a]
+    return len(pts), np.array(pts)
+
+
+def blue_noise_rays(samples: np.ndarray, image_size_x: int, image_size_y: int, K: torch.Tensor) -> torch.Tensor:
+    """Laser.generate_blue_noise_rays after the sampler (laser.py:115-145): samples / size -> (x, y, -1) -> K^-1 ->
+    normalise -> flip z.  ``torch.tensor(fp64 samples)`` stays fp64 until it is copied into the fp32 ray tensor."""
+    ps = torch.tensor(samples) / torch.tensor([image_size_x, image_size_y])
+    temp = torch.ones([ps.shape[0], 3]) * -1.0
+    temp[:, 0:2] = ps
+    rays = transform_points(temp, K.inverse())
+    rays = rays / torch.linalg.norm(rays, dim=-1, keepdims=True)
+    rays[:, 2] *= -1.0
+    return rays
+
+
+def poisson_radius(image_size_x: int, image_size_y: int, num_beams: int) -> float:
+    r = math.sqrt((image_size_x * image_size_y) / (math.pi * num_beams))    # laser.py:109-112
+    return r + r / 4.0
+
+
+# ----------------------------------------------------------------------------
+# Batched intersections  (fireflies/utils/intersections.py:5-33)
+# ----------------------------------------------------------------------------
+def ray_plane(origin, direction, plane_origin, plane_normal) -> torch.Tensor:
+    denom = torch.sum(plane_normal * direction, dim=1)
+    denom = torch.where(torch.abs(denom) < 0.000001, denom / denom, denom)     # 0/0 -> NaN for exactly parallel rays
+    return (torch.sum((plane_origin - origin) * plane_normal, dim=1) / denom)[:, None]
+
+
+def sphere_sphere(a, ra, b, rb) -> torch.Tensor:
+    return (a - b).pow(2).sum(dim=1, keepdim=True) <= (ra + rb).pow(2)

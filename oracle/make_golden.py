@@ -380,10 +380,108 @@ def perlin_cases(ff):
     print("wrote perlin")
 
 
+class _OracleCurve:
+    """Stand-in for geomdl's NURBS.Curve (absent here): the attributes utils/io.py:105-108 sets, evaluated by the oracle's
+    restatement.  What the fixtures pin is the reference's Curve arithmetic AROUND the evaluator."""
+    def __init__(self, degree, ctrlpts, knotvector, weights=None):
+        from oracle import ff_oracle as O
+        self.degree, self.ctrlpts, self.weights = degree, ctrlpts, weights
+        self.knotvector = O.nurbs_normalize_knots(knotvector)
+        self._O = O
+
+    def evaluate_single(self, t):
+        return self._O.nurbs_curve_point(self.ctrlpts, self.knotvector, self.degree, t, self.weights)
+
+
+CURVE_CTRL = [[0.0, 0.0, 0.0], [1.0, 2.0, 0.5], [3.0, 2.5, -1.0], [4.0, 0.0, 2.0], [6.0, -1.0, 1.0], [7.5, 0.5, 0.0], [9.0, 2.0, 3.0]]
+CURVE_KNOTS = [0.0, 0.0, 0.0, 0.0, 1.0, 2.0, 2.5, 4.0, 4.0, 4.0, 4.0]
+CURVE_WEIGHTS = [1.0, 0.7, 1.3, 1.0, 2.0, 0.5, 1.0]
+
+
+def curve_cases(ff):
+    """The reference's Curve (entity/curve.py) driven through train / eval randomize() with the oracle evaluator as its
+    `_curve`.  Its constructor raises (`super().__init__(self, name, device)`, :24): the instance is assembled by hand
+    with the constructor's own attribute values (:26-34)."""
+    import random as pyrandom
+    from fireflies.entity.curve import Curve
+    from fireflies.entity.base import Transformable
+    out = {}
+    for tag, weights in (("bspline", None), ("rational", CURVE_WEIGHTS)):
+        c = object.__new__(Curve)
+        Transformable.__init__(c, "path", CPU)
+        c._curve = _OracleCurve(3, CURVE_CTRL, CURVE_KNOTS, weights)
+        c.curve_epsilon = 0.05; c.curve_delta = c.curve_epsilon
+        c._interp_steps = 1000; c._interp_delta = 1.0 / c._interp_steps
+        c.eval_interval_start = 0.05
+        g = torch.Generator().manual_seed(41)
+        W = torch.eye(4); W[0:3, 0:3] = torch.linalg.qr(torch.randn(3, 3, generator=g))[0]; W[0:3, 3] = torch.tensor([0.3, -1.0, 2.0])
+        c.set_world(W)
+        c.train(); pyrandom.seed(5)
+        deltas, worlds = [], []
+        for _ in range(3):
+            c.randomize(); deltas.append(c.curve_delta); worlds.append(npy(c.world()))
+        c.eval()
+        for _ in range(40):
+            c.randomize(); deltas.append(c.curve_delta); worlds.append(npy(c.world()))
+        c.curve_delta = 0.9485      # walk over the wrap at 1 - epsilon (:88-89)
+        for _ in range(4):
+            c.randomize(); deltas.append(c.curve_delta); worlds.append(npy(c.world()))
+        for t in (0.2, 0.5, 0.77):
+            c.curve_delta = t
+            out[f"{tag}_rot_{t}"] = npy(c.sample_rotation()); out[f"{tag}_trans_{t}"] = npy(c.sample_translation())
+        out[f"{tag}_deltas"] = np.array(deltas, dtype=np.float64)
+        out[f"{tag}_worlds"] = np.stack(worlds)
+        out[f"{tag}_W"] = npy(W)
+        ts = np.linspace(0.0, 1.0, 101)
+        out[f"{tag}_points64"] = np.array([c._curve.evaluate_single(float(t)) for t in ts])
+    out["ctrl"], out["knots"], out["weights"] = np.array(CURVE_CTRL), np.array(CURVE_KNOTS), np.array(CURVE_WEIGHTS)
+    np.savez_compressed(os.path.join(OUT, "curve.npz"), **out)
+    print("wrote curve")
+
+
+def poisson_cases(ff):
+    """bridson (sampling/poisson.py) under np.random.seed, Laser.generate_blue_noise_rays (laser.py:94-145),
+    utils/intersections.py and rotation_matrix_from_vectors[_with_fixed_up] (utils/math.py:67-159) from the reference."""
+    import fireflies.sampling.poisson as PS
+    import fireflies.utils.intersections as IS
+    out = {}
+    np.random.seed(17)
+    n, pts = PS.bridson(np.ones([48, 64]) * 5.5)
+    out["uniform_pts"], out["uniform_n"] = pts, np.int64(n)
+    rad = np.ones([40, 40]) * 6.0
+    rad[10:30, 10:30] = 2.5
+    np.random.seed(18)
+    n, pts = PS.bridson(rad, k=12)
+    out["varying_radius"], out["varying_pts"] = rad, pts
+    import fireflies.utils.io as IO
+    K = IO.build_projection_matrix(60.0, 0.01, 1000.0, device=CPU)
+    np.random.seed(19)
+    rays = ff.projection.Laser.generate_blue_noise_rays(64, 48, 60, K, device=CPU)
+    out["blue_K"], out["blue_rays"] = npy(K), npy(rays)
+    g = torch.Generator().manual_seed(51)
+    o, d = torch.randn(33, 3, generator=g), torch.nn.functional.normalize(torch.randn(33, 3, generator=g), dim=1)
+    po, pn = torch.randn(33, 3, generator=g), torch.nn.functional.normalize(torch.randn(33, 3, generator=g), dim=1)
+    d[4] = torch.linalg.cross(pn[4], torch.tensor([0.3, 0.2, 0.9]))          # (nearly) parallel to the plane
+    out.update(rp_o=npy(o), rp_d=npy(d), rp_po=npy(po), rp_pn=npy(pn), rp_t=npy(IS.rayPlane(o, d, po, pn)))
+    a, b = torch.rand(50, 2, generator=g) * 10, torch.rand(50, 2, generator=g) * 10
+    ra, rb = torch.rand(50, 1, generator=g) * 2, torch.rand(50, 1, generator=g) * 2
+    out.update(ss_a=npy(a), ss_b=npy(b), ss_ra=npy(ra), ss_rb=npy(rb), ss_hit=IS.sphereSphere(a, ra, b, rb).numpy())
+    M = ff.utils.math
+    v1, v2 = torch.tensor([0.0, 1.0, 0.0]), torch.tensor([0.3, -0.2, 0.8])
+    out.update(rot_v1=npy(v1), rot_v2=npy(v2), rot=npy(M.rotation_matrix_from_vectors(v1, v2)),
+               rot_up=npy(M.rotation_matrix_from_vectors_with_fixed_up(v1, v2)))
+    np.savez_compressed(os.path.join(OUT, "poisson_misc.npz"), **out)
+    print("wrote poisson_misc")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     ff = ref_loader.load()
+    if len(sys.argv) > 1:          # python oracle/make_golden.py curve_cases poisson_cases: only those fixture files
+        for name in sys.argv[1:]:
+            globals()[name](ff)
+        return
     # KAT1 (SURVEY App. B): point 2 exactly on pixel (3,4) -> g == 1
     splat_case(ff, "splat_kat1", torch.tensor([[0.25, 0.75], [0.5, 0.5]]), 4.0, [8, 6])
     g = torch.Generator().manual_seed(0)
@@ -401,6 +499,8 @@ def main():
     post_cases(ff)
     line_depth_cases(ff)
     perlin_cases(ff)
+    curve_cases(ff)
+    poisson_cases(ff)
 
 
 if __name__ == "__main__":

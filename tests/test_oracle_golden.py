@@ -280,3 +280,104 @@ def test_perlin_matches_reference_fixture(golden):
     for name in "abc":
         shape, res, oc, pers, angles = _perlin_angles(g, name)
         np.testing.assert_allclose(O.perlin_octaves(shape, res, oc, pers, angles).numpy(), g[f"{name}_noise"], rtol=1e-6, atol=1e-7)
+
+
+# ---- NURBS-curve camera path, Poisson-disk initialisation, intersections ------------------------------------------
+def test_nurbs_evaluator_known_answers():
+    """geomdl is absent (parity unpinned): the restated evaluator is anchored on closed forms."""
+    ctrl = [[0, 0, 0], [1, 2, 0], [3, 2, 1], [4, 0, 2]]
+    kn = O.nurbs_normalize_knots([0, 0, 0, 0, 2, 2, 2, 2])                     # one Bezier segment -> Bernstein polynomials
+    for t in (0.0, 0.3, 0.5, 0.99, 1.0):
+        b = [(1 - t) ** 3, 3 * t * (1 - t) ** 2, 3 * t * t * (1 - t), t ** 3]
+        want = [sum(b[i] * ctrl[i][d] for i in range(4)) for d in range(3)]
+        close(O.nurbs_curve_point(ctrl, kn, 3, t), want, rtol=1e-14, atol=1e-15)
+    s = np.sqrt(0.5)                                                           # rational quadratic quarter circle
+    for t in np.linspace(0, 1, 17):
+        p = O.nurbs_curve_point([[1, 0, 0], [1, 1, 0], [0, 1, 0]], [0, 0, 0, 1, 1, 1], 2, float(t), [1, s, 1])
+        assert abs(p[0] ** 2 + p[1] ** 2 - 1.0) < 1e-14
+    kn = O.nurbs_normalize_knots([0, 0, 0, 0, 1, 2, 2.5, 4, 4, 4, 4])            # partition of unity on a non-uniform vector
+    assert kn[0] == 0.0 and kn[-1] == 1.0 and kn[5] == 0.5
+    for t in np.linspace(0, 1, 41):
+        span = O.nurbs_find_span(3, kn, 7, float(t))
+        assert 3 <= span <= 6 and kn[span] <= t and (t < kn[span + 1] or t == 1.0)
+        assert abs(sum(O.nurbs_basis(3, kn, span, float(t))) - 1.0) < 1e-14
+
+
+@pytest.mark.parametrize("tag", ["bspline", "rational"])
+def test_curve_pose_matches_reference_curve(golden, tag):
+    """The reference's Curve.randomize / sample_rotation / sample_translation (run on the oracle evaluator) vs curve_pose."""
+    g = golden("curve")
+    kn = O.nurbs_normalize_knots(g["knots"])
+    w = g["weights"] if tag == "rational" else None
+    W = T(g[tag + "_W"])
+    for d, want in zip(g[tag + "_deltas"], g[tag + "_worlds"]):
+        assert np.array_equal(O.curve_pose(g["ctrl"], kn, 3, float(d), W, w).numpy(), want)
+    pts = np.array([O.nurbs_curve_point(g["ctrl"], kn, 3, float(t), w) for t in np.linspace(0.0, 1.0, 101)])
+    assert np.array_equal(pts, g[tag + "_points64"])
+    d = g[tag + "_deltas"]
+    assert np.all(d[:3] == 0.05) and abs(d[3] - 0.051) < 1e-12 and d[-3] == 0.05      # train quirk; eval walk; wrap at 1 - epsilon
+
+
+def test_bridson_and_misc_match_reference(golden):
+    g = golden("poisson_misc")
+    np.random.seed(17)
+    n, p = O.bridson(np.ones([48, 64]) * 5.5)
+    assert n == int(g["uniform_n"]) and np.array_equal(p, g["uniform_pts"])
+    np.random.seed(18)
+    assert np.array_equal(O.bridson(g["varying_radius"], k=12)[1], g["varying_pts"])
+    d = np.linalg.norm(p[:, None] - p[None], axis=-1) + np.eye(len(p)) * 1e9     # the property the sampler exists for
+    assert d.min() > 5.5 * 0.7
+    np.random.seed(19)
+    _, s = O.bridson(np.ones([64, 48]) * O.poisson_radius(64, 48, 60))
+    assert np.array_equal(O.blue_noise_rays(s, 64, 48, T(g["blue_K"])).numpy(), g["blue_rays"])
+    t = O.ray_plane(T(g["rp_o"]), T(g["rp_d"]), T(g["rp_po"]), T(g["rp_pn"]))
+    assert np.array_equal(t.numpy(), g["rp_t"], equal_nan=True)
+    assert np.array_equal(O.sphere_sphere(T(g["ss_a"]), T(g["ss_ra"]), T(g["ss_b"]), T(g["ss_rb"])).numpy(), g["ss_hit"])
+    close(O.rotation_matrix_from_vectors(T(g["rot_v1"]), T(g["rot_v2"])), g["rot"])
+    close(O.rotation_matrix_from_vectors_with_fixed_up(T(g["rot_v1"]), T(g["rot_v2"])), g["rot_up"])
+
+
+def test_product_poisson_sampler_consumes_the_numpy_stream_like_the_reference(golden):
+    """Host-side set-up code of the product (numpy, like the reference): same draws, same points."""
+    from fireflies_b200.sampling import poisson
+    g = golden("poisson_misc")
+    np.random.seed(17)
+    n, p = poisson.bridson(np.ones([48, 64]) * 5.5)
+    assert n == int(g["uniform_n"]) and np.array_equal(p, g["uniform_pts"])
+    np.random.seed(18)
+    assert np.array_equal(poisson.bridson(g["varying_radius"], k=12)[1], g["varying_pts"])
+    np.random.seed(3)
+    n, p = poisson.bridson(np.ones([20, 20]) * 4.0, k=8, radiusType="normDist")
+    assert n == len(p) > 4
+
+
+def test_nurbs_curve_object_host_logic(tmp_path):
+    """Attribute checks and knot normalisation of the geomdl stand-in need no GPU; evaluating without one raises."""
+    from fireflies_b200.utils.nurbs import NurbsCurve
+    from fireflies_b200.utils.io import importBlenderNurbsObj
+    c = NurbsCurve(device=torch.device("cpu"))
+    with pytest.raises(ValueError):
+        c.ctrlpts = [[0, 0, 0]] * 4                          # degree first
+    c.degree = 3
+    with pytest.raises(ValueError):
+        c.ctrlpts = [[0, 0, 0]] * 3                          # needs degree + 1 points
+    c.ctrlpts = [[0, 0, 0], [1, 2, 0], [3, 2, 1], [4, 0, 2], [5, 1, 1]]
+    with pytest.raises(ValueError):
+        c.knotvector = [0, 0, 0, 0, 1, 1, 1, 1]              # wrong length
+    with pytest.raises(ValueError):
+        c.knotvector = [0, 0, 0, 0, 3, 2, 4, 4, 4]           # decreasing
+    c.knotvector = [0, 0, 0, 0, 2, 4, 4, 4, 4]
+    assert c.knotvector == O.nurbs_normalize_knots([0, 0, 0, 0, 2, 4, 4, 4, 4]) and c.weights == [1.0] * 5
+    with pytest.raises(ValueError):
+        c.weights = [1, 1, 0, 1, 1]
+    with pytest.raises(ValueError):
+        NurbsCurve(9, [[0, 0, 0]] * 12, list(range(22)), device=torch.device("cpu"))
+    obj = tmp_path / "path.obj"
+    obj.write_text("# Blender\nv 0.0 0.0 0.0\nv 1.0 2.0 0.5\nv 3.0 2.5 -1.0\nv 4.0 0.0 2.0\ncstype bspline\ndeg 3\ncurv 0.0 1.0 1 2 3 4\n"
+                   "parm u 0.0 0.0 0.0 0.0 1.0 1.0 1.0 1.0\nend\n")
+    curve = importBlenderNurbsObj(str(obj), device=torch.device("cpu"))
+    assert curve.degree == 3 and len(curve.ctrlpts) == 4 and curve.ctrlpts[2] == [3.0, 2.5, -1.0] and curve.knotvector[4] == 1.0
+    with pytest.raises(ValueError):
+        curve.evaluate_single(1.5)                           # outside the domain, like geomdl
+    with pytest.raises(RuntimeError):
+        curve.evaluate_single(0.5)                           # no CPU path
