@@ -171,8 +171,8 @@ using namespace ffb::curve;
 extern "C" int ffb_nurbs_curve_eval(const double* ctrlw, const double* knots, int32_t n_ctrl, int32_t degree, const double* t,
                                     int32_t B, double* out, void* stream) {
     if (int rc = check_curve(ctrlw, knots, n_ctrl, degree, t, B, "nurbs_curve_eval: bad argument")) return rc;
-    if (!out) return fail_arg(FFB_E_ARG, "nurbs_curve_eval: null out");
     if (B == 0) return 0;
+    if (!out) return fail_arg(FFB_E_ARG, "nurbs_curve_eval: null out");
     nurbs_eval_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(ctrlw, knots, n_ctrl, degree, t, B, out);
     FFB_CUDA(cudaGetLastError());
     return 0;
@@ -181,9 +181,9 @@ extern "C" int ffb_nurbs_curve_eval(const double* ctrlw, const double* knots, in
 extern "C" int ffb_curve_pose(const double* ctrlw, const double* knots, int32_t n_ctrl, int32_t degree, const double* t, int32_t B,
                               double dt, const float* world, float* out_world, float* out_rot, float* out_trans, void* stream) {
     if (int rc = check_curve(ctrlw, knots, n_ctrl, degree, t, B, "curve_pose: bad argument")) return rc;
+    if (B == 0) return 0;
     if (out_world && !world) return fail_arg(FFB_E_ARG, "curve_pose: out_world needs world");
     if (!out_world && !out_rot && !out_trans) return fail_arg(FFB_E_ARG, "curve_pose: no output");
-    if (B == 0) return 0;
     curve_pose_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(ctrlw, knots, n_ctrl, degree, t, B, dt, world, out_world, out_rot,
                                                                      out_trans);
     FFB_CUDA(cudaGetLastError());
