@@ -358,7 +358,7 @@ def main_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n = 12
+        n = 40                                                    # ~12 s of CPU work on the box (3.4 samples/s)
         v, cores, dt = run_cpu(n)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n} scene samples of the 256-scene step at full size ({dt:.1f} s of CPU work), linear extrapolation"}

@@ -107,3 +107,90 @@ def test_api_surface_matches_reference_names():
               "initRandomRays", "randomize_laser_out_of_bounds", "randomize_camera_out_of_bounds", "render_epipolar_lines"]:
         assert hasattr(ff.projection.Laser, n), n
     assert ff.scene is ff.Scene
+
+
+def _ast_api(root):
+    import ast
+    out = {}
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            tree = ast.parse(open(os.path.join(dp, f)).read())
+            names = set()
+            for node in tree.body:
+                if isinstance(node, ast.FunctionDef):
+                    names.add(node.name)
+                elif isinstance(node, ast.ClassDef):
+                    names.add(node.name)
+                    names.update(f"{node.name}.{m.name}" for m in node.body if isinstance(m, ast.FunctionDef))
+                elif isinstance(node, ast.Assign):
+                    names.update(t.id for t in node.targets if isinstance(t, ast.Name))
+            out[os.path.relpath(os.path.join(dp, f), root)] = names
+    return out
+
+
+def test_every_reference_definition_has_a_counterpart_or_a_documented_reason():
+    """File by file, name by name (AST walk of both trees): everything the reference defines exists here under the same
+    module path and name, except the list below -- each entry is out of scope for a stated reason."""
+    ref_root = "/root/reference/fireflies"
+    if not os.path.isdir(ref_root):
+        pytest.skip("reference tree not mounted")
+    ref, ours = _ast_api(ref_root), _ast_api(os.path.join(ROOT, "fireflies_b200"))
+    allowed_files = {
+        "entity/flame.py": "FLAME shape model: external package + weights",
+        "entity/shape.py": "NotImplementedError stub in the reference",
+        "graphics/depth.py": "Mitsuba / drjit ray casting",
+        "utils/laser_estimation.py": "Mitsuba scene queries",
+    }
+    allowed_names = {
+        "graphics/rasterization.py": {"get_mpl_colormap", "main", "test_line_reg", "test_point_reg", "time_it"},   # matplotlib demos
+        "entity/mesh.py": {"Mesh.randomize"},                 # inherited: Transformable.randomize composes T, R and (for meshes) S in one launch
+        "projection/laser.py": {"Laser.near_clip", "Laser.far_clip"},     # inherited from Camera
+    }
+    missing = {}
+    for rel, names in ref.items():
+        if rel in allowed_files:
+            continue
+        assert rel in ours, f"{rel} has no counterpart"
+        gone = {n for n in names - ours[rel] if not n.startswith("_")} - allowed_names.get(rel, set())
+        if gone:
+            missing[rel] = sorted(gone)
+    assert not missing, missing
+    import fireflies_b200 as ff
+    assert hasattr(ff.entity.Mesh, "randomize") and hasattr(ff.projection.Laser, "near_clip") and hasattr(ff.projection.Laser, "far_clip")
+
+
+def test_signatures_are_prefix_compatible_with_the_reference():
+    """Every function / method that exists in both trees takes the reference's positional parameters, same names and order;
+    this package only ever appends optional ones (e.g. ``variates=``, ``camera_to_world=``)."""
+    import ast
+    ref_root = "/root/reference/fireflies"
+    if not os.path.isdir(ref_root):
+        pytest.skip("reference tree not mounted")
+
+    def sigs(root):
+        out = {}
+        for dp, _, files in os.walk(root):
+            for f in files:
+                if not f.endswith(".py"):
+                    continue
+                rel = os.path.relpath(os.path.join(dp, f), root)
+                tree = ast.parse(open(os.path.join(dp, f)).read())
+                for node in tree.body:
+                    fns = [("", node)] if isinstance(node, ast.FunctionDef) else (
+                        [(node.name + ".", m) for m in node.body if isinstance(m, ast.FunctionDef)] if isinstance(node, ast.ClassDef) else [])
+                    for prefix, fn in fns:
+                        names = [a.arg for a in fn.args.posonlyargs + fn.args.args]
+                        out[(rel, prefix + fn.name)] = (names, len(names) - len(fn.args.defaults))
+        return out
+
+    ref, ours = sigs(ref_root), sigs(os.path.join(ROOT, "fireflies_b200"))
+    both = [k for k in ref if k in ours]
+    assert len(both) >= 200
+    for k in both:
+        (rn, rreq), (on, oreq) = ref[k], ours[k]
+        if k == ("entity/curve.py", "Curve.fromObj"):
+            continue
+        assert on[:len(rn)] == rn, (k, rn, on)
+        assert oreq <= rreq, (k, "more required parameters than the reference")
