@@ -58,6 +58,9 @@ constexpr int WF_WARPS = WF_CTA / 32;
 #ifndef FFB_WF_MINB
 #define FFB_WF_MINB (1024 / FFB_WF_CTA)   // 32 warps per SM at 64 registers
 #endif
+#ifndef FFB_TMA_ELECT
+#define FFB_TMA_ELECT 1                   // backward TMA requests under elect.sync instead of lane == 0 (A/B knob)
+#endif
 #ifndef FFB_WB_CTA
 #define FFB_WB_CTA 32
 #endif
@@ -473,7 +476,9 @@ __device__ __forceinline__ bool strip_init(Strip& s, const RasterParams& q) {
     }
     s.bin = q.shared_pattern ? 0 : s.b;
     s.lane = threadIdx.x & 31;
-    s.sty0 = (by * WARPS + (threadIdx.x >> 5)) * S;
+    // one-warp CTAs: the warp index is the constant 0, which keeps the row coordinate of the TMA boxes in uniform registers
+    // (derived from threadIdx it costs a R2UR waterfall loop per box)
+    s.sty0 = (by * WARPS + (WARPS == 1 ? 0 : (int)(threadIdx.x >> 5))) * S;
     if (s.sty0 >= q.tgy) return false;
     s.nst = min(S, q.tgy - s.sty0);
     s.c0 = bx * (4 * WT);
@@ -925,7 +930,7 @@ __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_tma(RasterPara
     extern __shared__ __align__(1024) unsigned char wt_smem_tma[];
     Strip sp;
     if (!strip_init<WB_WARPS>(sp, q)) return;
-    const int wid = threadIdx.x >> 5;
+    const int wid = WB_WARPS == 1 ? 0 : (int)(threadIdx.x >> 5);
     unsigned char* tin = wt_smem_tma + wid * (NBUF * TMA_TILE_BYTES);            // [go | saved | gs | (LOSS) ot], 1 KB each, 1 KB aligned
     uint64_t* bar = reinterpret_cast<uint64_t*>(wt_smem_tma + WB_WARPS * NBUF * TMA_TILE_BYTES) + wid;
     Stage& st = reinterpret_cast<Stage*>(wt_smem_tma + WB_WARPS * NBUF * TMA_TILE_BYTES + 64)[wid];
@@ -949,8 +954,8 @@ __global__ void __launch_bounds__(WB_CTA, FFB_BWD_MINB) splat_bwd_tma(RasterPara
     // transposed tile (64-byte swizzle: 16-byte chunk index ^= (column >> 1) & 3): rows 4i + 2h + {0, 1} of column lc
     const unsigned tr_base = (unsigned)(2 * TMA_TILE_BYTES + w.lc * 64 + 8 * w.h), tr_x = (unsigned)((w.lc >> 1) & 3) << 4;
 
-    auto issue = [&](int r0, int j) {
-        if (sp.lane == 0) {
+    auto issue = [&](int r0, int j) {                      // called by the converged warp
+        if (FFB_TMA_ELECT ? tma::elect_one() : sp.lane == 0) {
             const int ct = w.c0 + WT * j;
             tma::mbar_expect_tx(bar, kBytes);
             if (LOSS) {

@@ -28,6 +28,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
 }
+// true in exactly one lane of a converged warp.  With this predicate (instead of `lane == 0`) the compiler issues the
+// uniform-datapath TMA instruction once under the elected predicate; under an ordinary divergent branch it wraps every
+// UTMALDG in an ELECT / BRA.U.ANY loop over the active lanes.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // one box of a rank-3 tensor map -> shared memory; completion is signalled on `bar` as transaction bytes
 __device__ __forceinline__ void load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
     asm volatile(
