@@ -58,6 +58,9 @@ constexpr int WF_WARPS = WF_CTA / 32;
 #ifndef FFB_WF_MINB
 #define FFB_WF_MINB (1024 / FFB_WF_CTA)   // 32 warps per SM at 64 registers
 #endif
+#ifndef FFB_FWD_ELECT
+#define FFB_FWD_ELECT 1                   // forward TMA stores / bulk-group waits under elect.sync (the same leader every time) instead of lane == 0 (A/B knob)
+#endif
 #ifndef FFB_TMA_ELECT
 #define FFB_TMA_ELECT 1                   // backward TMA requests under elect.sync instead of lane == 0 (A/B knob)
 #endif
@@ -571,7 +574,7 @@ __global__ void __launch_bounds__(WF_CTA, FFB_WF_MINB) splat_fwd_tma(RasterParam
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { acc_s[i] = bc(0.f); acc_p[i] = bc(1.f); }
                 accumulate_tile<SUM, SOFTOR, MASK_O>(st, tile_mask(mk, j), n, (float)(ct + w.lc), w.h, fc, acc_s, acc_p);
-                if (sp.lane == 0) tma::store_wait_read<0>();              // the previous tile's boxes have left the buffers
+                if (FFB_FWD_ELECT ? tma::elect_one() : sp.lane == 0) tma::store_wait_read<0>();   // the previous tile's boxes have left the buffers
                 __syncwarp();
                 if (SOFTOR) {
 #pragma unroll
@@ -586,7 +589,7 @@ __global__ void __launch_bounds__(WF_CTA, FFB_WF_MINB) splat_fwd_tma(RasterParam
                 }
                 tma::fence_async_smem();
                 __syncwarp();
-                if (sp.lane == 0) {
+                if (FFB_FWD_ELECT ? tma::elect_one() : sp.lane == 0) {
                     if (SOFTOR) tma::store_3d(&tm_o, tout, ct, w.r0, w.b);
                     if (SUM) {
                         if (SUM_T) tma::store_3d(&tm_s, tout + TMA_TILE_BYTES, w.r0, ct, w.b);
@@ -598,7 +601,7 @@ __global__ void __launch_bounds__(WF_CTA, FFB_WF_MINB) splat_fwd_tma(RasterParam
         }
         n = nn;
     }
-    if (sp.lane == 0) tma::store_wait_read<0>();           // shared memory must outlive the last boxes
+    if (FFB_FWD_ELECT ? tma::elect_one() : sp.lane == 0) tma::store_wait_read<0>();   // shared memory must outlive the last boxes
 }
 
 // Backward.  dL/dg = gS * m_s + gO * m_o * prod / (1 - g) per (texel, point); dg/dP = 4 g d2 (c - P) / sigma^2.
