@@ -194,3 +194,13 @@ def test_signatures_are_prefix_compatible_with_the_reference():
             continue
         assert on[:len(rn)] == rn, (k, rn, on)
         assert oreq <= rreq, (k, "more required parameters than the reference")
+
+
+def test_example_script_imports_without_a_gpu():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "point_pattern_optimization.py"), "--help"],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert out.returncode == 0 and "--api" in out.stdout, out.stdout
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "point_pattern_optimization.py"), "--steps", "1"],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    if not torch.cuda.is_available():
+        assert out.returncode != 0 and "needs a CUDA device" in out.stdout      # refuses instead of falling back
