@@ -185,7 +185,15 @@ class Scene:
             e.eval()
 
     def load_curve(self, path: str, name: str = "Curve") -> None:
-        raise NotImplementedError("NURBS curves are outside the B200 hot path (SURVEY.md section 2 #3b)")
+        """scene.py:237-241: a NURBS camera path from a Blender .obj.  (The reference calls ``fireflies.utils.importBlenderNurbsObj``
+        -- the function lives in ``fireflies.utils.io`` -- and appends to ``self.curves``, an attribute that does not exist; the
+        evident intent is implemented: ``utils.io.importBlenderNurbsObj`` and ``self._curves``.)"""
+        from .utils import io as ffio
+        curve = ffio.importBlenderNurbsObj(path, device=self._device)
+        self._curves.append(entity.Curve(name, curve, self._device))
+
+    def curves(self) -> list:
+        return self._curves
 
     # ---- write-back to Mitsuba (scene.py:243-342) ----------------------------------------------------
     def update_meshes(self) -> None:

@@ -204,3 +204,20 @@ def test_example_script_imports_without_a_gpu():
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     if not torch.cuda.is_available():
         assert out.returncode != 0 and "needs a CUDA device" in out.stdout      # refuses instead of falling back
+
+
+def test_scene_load_curve_reads_the_obj_then_refuses_a_cpu_device(tmp_path):
+    """Scene.load_curve (scene.py:237-241): the parser is host code; building the entity needs the device (no CPU path)."""
+    import fireflies_b200 as ff
+
+    class Params(dict):
+        def update(self, *a, **k):
+            return super().update(*a, **k) if (a or k) else None
+    sc = ff.Scene(Params(), device=torch.device("cpu"))
+    assert sc.curves() == []
+    with pytest.raises(FileNotFoundError):
+        sc.load_curve(str(tmp_path / "missing.obj"))
+    obj = tmp_path / "path.obj"
+    obj.write_text("v 0 0 0\nv 1 2 0.5\nv 3 2.5 -1\nv 4 0 2\ndeg 3\nparm u 0 0 0 0 1 1 1 1\n")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        sc.load_curve(str(obj), "CamPath")
