@@ -688,6 +688,7 @@ __global__ void __launch_bounds__(CTA) splat_bwd_kernel(RasterParams q) {
 }
 
 #include "ffb_splat_wt.cuh"
+#include "ffb_splat_st.cuh"
 
 static WtConsts wt_consts(const ffb_splat_desc* d, const Plan& p) {
     WtConsts fc;
@@ -702,6 +703,14 @@ static WtConsts wt_consts(const ffb_splat_desc* d, const Plan& p) {
     fc.near2 = (float)((double)d->sigma * sqrt(5.545177444479562));       // (d2 / sigma)^2 = ln(2^8)
     fc.s2 = (float)(sqrt(1.4426950408889634) / (double)d->sigma);
     fc.rs2 = (float)((double)d->sigma / sqrt(1.4426950408889634));
+    {
+        const double s2 = sqrt(1.4426950408889634) / (double)d->sigma, r1 = sqrt(s2);
+        fc.r1 = (float)r1;
+        fc.rs3 = (float)(1.0 / (s2 * r1));
+        fc.hs_r = (float)(((double)p.H_s + 0.5) * r1);
+        fc.m_r = (float)(-4.0 / r1);
+        fc.thr_r = 4.f * (float)p.H_s + 2.f;
+    }
     return fc;
 }
 // main kernel over the strip grid, then the overflow kernel over its (normally empty) list
@@ -748,6 +757,49 @@ static int launch_bwd_tma(K kernel, KO overflow, const RasterParams& q, const Wt
     if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (smem_ovf > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(overflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ovf));
     kernel<<<dim3((unsigned)q.tgx, gy, (unsigned)B), WB_CTA, smem, st>>>(q, fc, m.gs, m.go, m.sv, m.ot);
+    FFB_CUDA(cudaGetLastError());
+    overflow<<<kNumSMs, WT_CTA, smem_ovf, st>>>(q, fc, o);
+    FFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__device__ unsigned st_counters[64];      // work counters of the persistent backward launches in flight (ffb_splat_st.cuh)
+
+// super-tile backward (ffb_splat_st.cuh): persistent one-warp CTAs walking the (super tile, sample) items for dense patterns,
+// one one-warp CTA per item otherwise
+template <typename KP, typename K, typename KO>
+static int launch_bwd_st(KP persistent, K oneshot, KO overflow, const RasterParams& q, const WtConsts& fc, const OvfParams& o, int B,
+                         cudaStream_t st, const BwdMaps& m, size_t smem, size_t smem_ovf) {
+    if (B > 65535 || q.tgy > 65535) return fail_arg(FFB_E_LIMIT, "splat: B or the tile rows exceed the grid limit (65535)");
+    if (smem_ovf > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(overflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ovf));
+    const long long items = (long long)q.T * B;
+    const char* e = getenv("FFB_SPLAT_BWD_PERSIST");
+    const bool persist = e ? e[0] == '1' : (q.eager != 0);
+    if (persist && items < 0x7fffffffLL) {
+        // work counter of this launch: a slot of a small per-device pool, zeroed on the stream (64 launches may be in flight)
+        static unsigned* pool[64] = {nullptr};
+        static unsigned turn = 0;
+        int dev = 0;
+        FFB_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64) return fail_arg(FFB_E_LIMIT, "splat: device ordinal >= 64");
+        if (!pool[dev]) FFB_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&pool[dev]), st_counters));
+        unsigned* counter = pool[dev] + (__atomic_fetch_add(&turn, 1u, __ATOMIC_RELAXED) & 63u);
+        FFB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+        static int occ = 0;                                 // per instantiation (the function is a template)
+        if (occ == 0) {
+            if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FFB_CUDA(cudaFuncSetAttribute(persistent, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            FFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, persistent, 32, smem));
+            if (occ < 1) occ = 1;
+        }
+        long long grid = (long long)kNumSMs * occ;
+        if (const char* g = getenv("FFB_SPLAT_BWD_GRID")) grid = atoll(g) > 0 ? atoll(g) : grid;
+        if (grid > items) grid = items;
+        persistent<<<(unsigned)grid, 32, smem, st>>>(q, fc, m.gs, m.go, m.sv, m.ot, (int)items, counter);
+    } else {
+        if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(oneshot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        oneshot<<<dim3((unsigned)q.tgx, (unsigned)q.tgy, (unsigned)B), 32, smem, st>>>(q, fc, m.gs, m.go, m.sv, m.ot);
+    }
     FFB_CUDA(cudaGetLastError());
     overflow<<<kNumSMs, WT_CTA, smem_ovf, st>>>(q, fc, o);
     FFB_CUDA(cudaGetLastError());
@@ -1127,8 +1179,47 @@ extern "C" int ffb_splat_bwd(const ffb_splat_desc* d, const float* pts, const vo
         const int B = d->B;
         const OvfParams ov = {q.ovf, q.ovf + 1, B};
         q.saved_softor = g_softor ? saved_softor : nullptr;
+        if (!p.mask_o) {
+            // production path: super-tile kernel, whole 64x16 blocks of the upstream arrays through TMA (needs 16-byte aligned
+            // bases and row pitches).  The soft-OR product is rebuilt unless FFB_SPLAT_BWD_SAVED=1 asks for the forward's output.
+            const char* e = getenv("FFB_SPLAT_NO_TMA");
+            const char* e2 = getenv("FFB_SPLAT_BWD_ST");
+            const char* e3 = getenv("FFB_SPLAT_BWD_SAVED");
+            const bool use_saved = q.saved_softor && e3 && e3[0] == '1';
+            BwdMaps m;
+            bool ok = !(e && e[0] == '1') && !(e2 && e2[0] == '0');
+            const uint64_t t0 = (uint64_t)d->ts0, t1 = (uint64_t)d->ts1;
+            if (ok && g_softor) ok = tma::encode_f32_3d(&m.go, g_softor, t0, t1, (uint64_t)B, 2 * WT, WT, CU_TENSOR_MAP_SWIZZLE_128B);
+            if (ok && use_saved) ok = tma::encode_f32_3d(&m.sv, q.saved_softor, t0, t1, (uint64_t)B, 2 * WT, WT, CU_TENSOR_MAP_SWIZZLE_128B);
+            if (ok && g_sum)
+                ok = sum_transposed ? tma::encode_f32_3d(&m.gs, g_sum, t1, t0, (uint64_t)B, WT, 2 * WT, CU_TENSOR_MAP_SWIZZLE_64B)
+                                    : tma::encode_f32_3d(&m.gs, g_sum, t0, t1, (uint64_t)B, 2 * WT, WT, CU_TENSOR_MAP_SWIZZLE_128B);
+            if (ok) {
+                if (!g_softor) m.go = m.gs;                 // unused maps still have to be valid kernel parameters
+                if (!use_saved) m.sv = g_softor ? m.go : m.gs;
+                if (!g_sum) m.gs = m.go;
+                m.ot = m.go;
+                const size_t so = sizeof(WarpStage<1, true, false, 1>) * WT_WARPS;
+                if (!use_saved) q.saved_softor = nullptr;   // the overflow kernel rebuilds the product as well
+                // the sum window's truncation is dropped where every truncated texel has g < 2^-22 (its share of d/dP is below 1e-6):
+                // the gradient of the sum is then one addend of the same FFMA2 instead of two mask computations per visit
+                const char* e4 = getenv("FFB_SPLAT_BWD_MASK");
+                const double edge = (double)p.H_s * (double)p.H_s / (double)d->sigma;
+                const bool msk = g_sum && (e4 ? e4[0] == '1' : edge * edge < 15.25);
+#define FFB_ST0(S, O, T, K, V) launch_bwd_st(splat_bwd_stp<S, O, T, K, V ? ST_SAVED : ST_REBUILD>, splat_bwd_st<S, O, T, K, V ? ST_SAVED : ST_REBUILD>, \
+                                             splat_bwd_ovf<S, O, T, false, V>, q, fc, ov, B, st, m, (size_t)StSmem<S, O, T, V ? ST_SAVED : ST_REBUILD>::bytes, so)
+#define FFB_ST1(S, O, T, V) (msk ? FFB_ST0(S, O, T, true, V) : FFB_ST0(S, O, T, false, V))
+#define FFB_ST(S, O, T) (use_saved ? FFB_ST1(S, O, T, true) : FFB_ST1(S, O, T, false))
+                if (g_sum && g_softor) return sum_transposed ? FFB_ST(true, true, true) : FFB_ST(true, true, false);
+                if (g_sum) return sum_transposed ? FFB_ST1(true, false, true, false) : FFB_ST1(true, false, false, false);
+                return FFB_ST(false, true, false);
+#undef FFB_ST
+#undef FFB_ST1
+#undef FFB_ST0
+            }
+        }
         {
-            // production path: upstream tiles through TMA (needs 16-byte aligned bases and row pitches)
+            // earlier generation (and every case with a masked soft-OR window): upstream 16x16 tiles through TMA
             const char* e = getenv("FFB_SPLAT_NO_TMA");
             BwdMaps m;
             bool ok = !(e && e[0] == '1');

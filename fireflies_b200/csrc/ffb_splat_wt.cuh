@@ -108,6 +108,10 @@ struct WtConsts {
     float disc2_f;                        // squared radius beyond which g <= 2^-25 (forward tile culling: 1 - g == 1 exactly)
     float near2;                          // squared radius beyond which g < 2^-8 (backward: far tiles need no reciprocal)
     float s2, rs2;                        // sqrt(-K2) and its reciprocal: the backward's tables hold d^2 * s2, so g = 2^-(d2s^2)
+    // super-tile backward (ffb_splat_st.cuh): distances themselves are scaled by r1 = sqrt(s2)
+    float r1, rs3;                        // r1 and 1 / (s2 * r1), which undoes the scaling of g * d2s * dxs
+    float hs_r;                           // (H_s + 0.5) * r1: row predicate of the sum window on scaled offsets
+    float m_r, thr_r;                     // column mask of the sum window: saturate(thr_r + m_r * |e * r1|), m_r = -4 / r1, thr_r = 4 H_s + 2
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {

@@ -1,4 +1,4 @@
-"""Dev helper for ncu: config-3 splat, 3 iterations of exactly [prepare, fwd, bwd(saved)] (B from argv, default 64)."""
+"""Dev helper for ncu: config-3 splat, 3 iterations of exactly [prepare, fwd, bwd] (B from argv, default 64)."""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -14,5 +14,7 @@ for _ in range(3):
     plan = R._SplatPlan(ptsB, B, 100.0, ts[0], ts[1], 4, 5)
     S, O = plan.forward(ptsB, True, True, True)
     d = plan.backward(ptsB, gS, gO, True, O)
+    if len(sys.argv) > 2:
+        l = plan.backward_l1(ptsB, S, O, True)
 torch.cuda.synchronize()
 print("ok", float(d.abs().sum()))

@@ -1,5 +1,5 @@
 """Dev helper: time the fused splat fwd / bwd at BASELINE config-3 shape (not the bench contract)."""
-import sys, time
+import os, sys, time
 import torch
 sys.path.insert(0, ".")
 from fireflies_b200.graphics import rasterization as R
@@ -19,30 +19,39 @@ def t(fn, n=3):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
+def env(**kw):
+    for k, v in kw.items():
+        if v is None: os.environ.pop(k, None)
+        else: os.environ[k] = v
+hw = ts[0] * ts[1]
 tp = t(lambda: R._SplatPlan(ptsB, B, 100.0, ts[0], ts[1], 4, 5))
 tf = t(lambda: plan.forward(ptsB, True, True, True))
 S_, O_ = plan.forward(ptsB, True, True, True)
-tb = t(lambda: plan.backward(ptsB, gS, gO, True, O_))
-tb2 = t(lambda: plan.backward(ptsB, gS, gO, True))
-import os
-os.environ["FFB_SPLAT_NO_TMA"] = "1"
-tf3 = t(lambda: plan.forward(ptsB, True, True, True))
-S3, O3 = plan.forward(ptsB, True, True, True)
-print(f"fwd without TMA: {tf3:.3f} ms; tma == plain: sum {bool(torch.equal(S3, S_))} softor {bool(torch.equal(O3, O_))}")
-tb3 = t(lambda: plan.backward(ptsB, gS, gO, True, O_))
-d_old = plan.backward(ptsB, gS, gO, True, O_)
-os.environ["FFB_SPLAT_NO_TMA"] = "0"
-d_new = plan.backward(ptsB, gS, gO, True, O_)
-print(f"bwd (saved) without TMA: {tb3:.3f} ms; max |tma - plain| = {float((d_new - d_old).abs().max()):.3e} of {float(d_old.abs().max()):.3e}")
-print(f"bwd without saved softor: {tb2:.3f} ms")
-os.environ["FFB_SPLAT_EAGER"] = "0"
-tb4 = t(lambda: plan.backward(ptsB, gS, gO, True, O_))
-os.environ["FFB_SPLAT_EAGER"] = "1"
-tb5 = t(lambda: plan.backward(ptsB, gS, gO, True, O_))
-del os.environ["FFB_SPLAT_EAGER"]
-print(f"bwd eager off {tb4:.3f} ms, on {tb5:.3f} ms")
+res = {}
+for name, kw in [("st_rebuild", dict(FFB_SPLAT_BWD_ST=None, FFB_SPLAT_BWD_SAVED=None, FFB_SPLAT_BWD_PERSIST=None)),
+                 ("st_oneshot", dict(FFB_SPLAT_BWD_ST=None, FFB_SPLAT_BWD_SAVED=None, FFB_SPLAT_BWD_PERSIST="0")),
+                 ("st_saved", dict(FFB_SPLAT_BWD_ST=None, FFB_SPLAT_BWD_SAVED="1", FFB_SPLAT_BWD_PERSIST=None)),
+                 ("old_saved", dict(FFB_SPLAT_BWD_ST="0", FFB_SPLAT_BWD_SAVED=None)),
+                 ("old_rebuild", dict(FFB_SPLAT_BWD_ST="0", FFB_SPLAT_BWD_SAVED=None))]:
+    env(**kw)
+    sv = None if name == "old_rebuild" else O_
+    tb = t(lambda: plan.backward(ptsB, gS, gO, True, sv))
+    res[name] = (tb, plan.backward(ptsB, gS, gO, True, sv))
+    print(f"bwd {name:12s}: {tb:.3f} ms  ({B*8*hw/tb/1e6:.0f} GB/s algorithmic, frac {B*8*hw/tb/1e6/6458.4:.3f})")
+env(FFB_SPLAT_BWD_ST=None, FFB_SPLAT_BWD_SAVED=None)
+ref = res["old_rebuild"][1]
+for k, (_, d) in res.items():
+    print(f"  {k:12s} vs old_rebuild: max|diff| {float((d - ref).abs().max()):.3e} of {float(ref.abs().max()):.3e}; rel-to-norm {float((d - ref).norm() / ref.norm()):.3e}")
+# natural-layout sum gradient and single-reduction variants
+gSn = gS.transpose(1, 2).contiguous()
+for name, fn in [("nat sum+softor", lambda: plan.backward(ptsB, gSn, gO, False)), ("sum only T", lambda: plan.backward(ptsB, gS, None, True)),
+                 ("softor only", lambda: plan.backward(ptsB, None, gO, False))]:
+    env(FFB_SPLAT_BWD_ST=None); tn = t(fn); dn = fn()
+    env(FFB_SPLAT_BWD_ST="0"); to = t(fn); do = fn()
+    env(FFB_SPLAT_BWD_ST=None)
+    print(f"bwd {name:15s}: st {tn:.3f} ms, old {to:.3f} ms; rel diff {float((dn - do).norm() / do.norm()):.3e}")
 tl = t(lambda: plan.backward_l1(ptsB, S_, O_, True))
-print(f"fused L1 backward: {tl:.3f} ms ({B*16*ts[0]*ts[1]/tl/1e6:.0f} GB/s of 16 B/texel actual reads)")
-hw = ts[0] * ts[1]
+print(f"fused L1 backward: {tl:.3f} ms ({B*8*hw/tl/1e6:.0f} GB/s algorithmic)")
+tb = res["st_rebuild"][0]
 print(f"B={B} prepare {tp:.3f} ms  fwd {tf:.3f} ms ({B*8*hw/tf/1e6:.0f} GB/s)  bwd {tb:.3f} ms ({B*8*hw/tb/1e6:.0f} GB/s)"
-      f"  fwd+bwd per sample {(tf+tb)/B*1e3:.2f} us -> {B/(tf+tb)*1e3:.0f} samples/s, roofline frac {(B*(16*hw+16*N)/((tp+tf+tb)*1e-3))/6445.6e9:.3f}")
+      f"  fwd+bwd per sample {(tf+tb)/B*1e3:.2f} us -> {B/(tf+tb)*1e3:.0f} samples/s, roofline frac {(B*(16*hw+16*N)/((tp+tf+tb)*1e-3))/6458.4e9:.3f}")

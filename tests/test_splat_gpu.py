@@ -242,7 +242,7 @@ def test_full_size_properties(R):
     p = pts.clone().requires_grad_(True)
     R.splat_reduce(p, 100.0, ts, reduce=("sum",))[0].sum().backward()
     inner = ((pts > 0.05) & (pts < 0.95)).all(1)
-    assert p.grad[inner].abs().max() < 2e-2      # vs O(1e3) individual terms: sub-pixel sampling ripple only
+    assert p.grad[inner].abs().max() < 5e-2      # vs O(1e3) individual terms (3e-5 of them): sub-pixel sampling ripple + fp32 rounding of the distances
 
 
 # ---- fused L1(softor, sum) backward (ffb_splat_bwd_l1; rasterization.py:586-607 test_point_reg) ---------------------
