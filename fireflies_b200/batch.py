@@ -91,24 +91,28 @@ class SceneBatch:
         self.device = torch.device(scene.device())
         self._next_sample = 0
         # ---- entities, parents before children ----
-        ents: List[Transformable] = []
-
-        def add_chain(lst):
-            for root in [e for e in lst if e.parent() is None]:
-                node = root
-                while node is not None:
-                    if node not in ents:
-                        ents.append(node)
-                    node = node.child()
-            for e in lst:
-                if e not in ents:
-                    ents.append(e)
-
-        add_chain(scene._meshes)
-        add_chain(scene._lights)
+        # The compose kernel walks the table once, so every parent row must precede its children -- whichever list the parent
+        # lives in (a light parented to the camera, two children of one parent, ...): depth-first over the parent() links.
+        pool: List[Transformable] = list(scene._meshes) + list(scene._lights)
         for e in (scene._camera, scene._projector):
             if e is not None:
-                ents.append(e)
+                pool.append(e)
+        ents: List[Transformable] = []
+
+        def place(e, chain=()):
+            if any(e is x for x in ents):
+                return
+            if any(e is x for x in chain):
+                raise ValueError(f"SceneBatch: parent cycle through entity {e.name()!r}")
+            par = e.parent()
+            if par is not None:
+                if not any(par is x for x in pool):
+                    raise ValueError(f"SceneBatch: parent {par.name()!r} of {e.name()!r} is not an entity of this scene")
+                place(par, chain + (e,))
+            ents.append(e)
+
+        for e in pool:
+            place(e)
         self.entities = ents
         self._entity_index = {e.name(): i for i, e in enumerate(ents)}
         # ---- sampler table ----
@@ -156,7 +160,12 @@ class SceneBatch:
         ints = np.full((max(self.E, 1), _ENT_INTS), -1, dtype=np.int32)
         cents, worlds = [], []
         for i, e in enumerate(self.entities):
-            parent = self._entity_index[e.parent().name()] if e.parent() is not None else -1
+            parent = -1
+            if e.parent() is not None:
+                parent = self._entity_index.get(e.parent().name(), -2)
+                if not 0 <= parent < i:         # re-parented after construction: the row order no longer fits
+                    raise ValueError(f"SceneBatch.refresh: parent {e.parent().name()!r} of {e.name()!r} does not precede it in the "
+                                     "entity table; build a new SceneBatch after changing parent links")
             ints[i] = (e._KIND, parent, int(e.randomizable()), *self._trs_rows[i])
             cents.append(e._centroid_mat[0:3, 3].to(self.device).float())
             worlds.append(e._world.to(self.device).float().reshape(16))

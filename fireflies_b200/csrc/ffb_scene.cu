@@ -209,7 +209,11 @@ __global__ void __launch_bounds__(128) compose_kernel(const ffb_entity* __restri
             local = mul4(local, W);
         }
         float* o = out_world + ((size_t)b * E + e) * 16;
-        if (en.parent >= 0 && en.parent < e) {
+        if (en.parent >= e) {
+            // a parent row that does not precede its child has no world matrix yet: fail loudly (NaN) instead of dropping the parent
+#pragma unroll
+            for (int k = 0; k < 16; ++k) local.m[k] = __int_as_float(0x7fc00000);
+        } else if (en.parent >= 0) {
             M4 Pw;
             const float* pw = out_world + ((size_t)b * E + en.parent) * 16;
 #pragma unroll

@@ -1299,6 +1299,32 @@ extern "C" int ffb_splat_bwd_l1(const ffb_splat_desc* d, const float* pts, const
     const WtConsts fc = wt_consts(d, p);
     const OvfParams ov = {q.ovf, q.ovf + 1, B};
     const size_t stage = sizeof(WarpStage<1, true, false, 1>);
+    {
+        // the super-tile kernel in its loss mode (whole 64x16 blocks of the forward's outputs, two request rounds per item).  Measured
+        // 0.702 ms per 64 samples against 0.698 ms for splat_bwd_tma<LOSS> (profiles/r02i): not yet ahead, so it is opt-in
+        // (FFB_SPLAT_L1_ST=1) and the parity tests run both.
+        const char* e2 = getenv("FFB_SPLAT_L1_ST");
+        BwdMaps n;
+        bool ok2 = e2 && e2[0] == '1';
+        if (ok2) ok2 = tma::encode_f32_3d(&n.go, out_softor, t0, t1, (uint64_t)B, 2 * WT, WT, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (ok2) ok2 = sum_transposed ? tma::encode_f32_3d(&n.gs, out_sum, t1, t0, (uint64_t)B, 2 * WT, WT, CU_TENSOR_MAP_SWIZZLE_128B)
+                                      : tma::encode_f32_3d(&n.gs, out_sum, t0, t1, (uint64_t)B, 2 * WT, WT, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (ok2 && sum_transposed)
+            ok2 = tma::encode_f32_3d(&n.sv, out_sum, t1, t0, (uint64_t)B, WT, 2 * WT, CU_TENSOR_MAP_SWIZZLE_64B) &&
+                  tma::encode_f32_3d(&n.ot, out_softor, t0, t1, (uint64_t)B, WT, 2 * WT, CU_TENSOR_MAP_SWIZZLE_64B);
+        else if (ok2) { n.sv = n.gs; n.ot = n.go; }
+        if (ok2) {
+            const char* e4 = getenv("FFB_SPLAT_BWD_MASK");
+            const double edge = (double)p.H_s * (double)p.H_s / (double)d->sigma;
+            const bool msk = e4 ? e4[0] == '1' : edge * edge < 15.25;
+            q.eager = 1;                                    // the loss needs every texel: every item requests its blocks
+#define FFB_SL(T, K) launch_bwd_st(splat_bwd_stp<true, true, T, K, ST_LOSS>, splat_bwd_st<true, true, T, K, ST_LOSS>, \
+                                   splat_bwd_ovf<true, true, T, false, true, true>, q, fc, ov, B, st, n, (size_t)StSmem<true, true, T, ST_LOSS>::bytes, stage * WT_WARPS)
+            if (sum_transposed) return msk ? FFB_SL(true, true) : FFB_SL(true, false);
+            return msk ? FFB_SL(false, true) : FFB_SL(false, false);
+#undef FFB_SL
+        }
+    }
     if (sum_transposed)
         return launch_bwd_tma(splat_bwd_tma<true, true, true, false, true, true>, splat_bwd_ovf<true, true, true, false, true, true>, q, fc, ov,
                               B, st, m, stage, stage * WT_WARPS, 4);

@@ -48,11 +48,12 @@ enum StMode { ST_REBUILD = 0, ST_SAVED = 1, ST_LOSS = 2 };
 
 template <bool SUM, bool SOFTOR, bool SUM_T, int MODE>
 struct StSmem {
-    static constexpr int n_box = MODE == ST_LOSS ? (SUM_T ? 4 : 2) : ((SOFTOR ? 1 : 0) + (SUM ? 1 : 0) + ((SOFTOR && MODE == ST_SAVED) ? 1 : 0));
+    static constexpr int n_box = MODE == ST_LOSS ? 2 : ((SOFTOR ? 1 : 0) + (SUM ? 1 : 0) + ((SOFTOR && MODE == ST_SAVED) ? 1 : 0));
     static constexpr int off_go = 0;                                   // LOSS: the soft-OR output at the tile's own index
     static constexpr int off_gs = MODE == ST_LOSS ? ST_BOX : (SOFTOR ? ST_BOX : 0);       // LOSS: the sum output at the tile's own index (as stored)
-    static constexpr int off_sv = 2 * ST_BOX;                          // SAVED: forward's soft-OR output; LOSS + SUM_T: mirrored sum output
-    static constexpr int off_ot = 3 * ST_BOX;                          // LOSS + SUM_T: mirrored soft-OR output
+    static constexpr int off_sv = 2 * ST_BOX;                          // SAVED: forward's soft-OR output
+    // LOSS + SUM_T: the same two boxes first hold the outputs at the MIRRORED index (soft-OR in off_go, sum in off_gs, {16,32} boxes),
+    // from which the lane keeps two sign bits per texel, and then the outputs at the tile's own index
     static constexpr int off_bar = n_box * ST_BOX;
     static constexpr int off_rec = off_bar + 16;
     static constexpr int off_idx = off_rec + WCH * 16;
@@ -340,10 +341,33 @@ __device__ __forceinline__ WtMasks st_stage(const RasterParams& q, const WtConst
     return mk;
 }
 
+// LOSS + SUM_T, first request round: the boxes hold the forward's outputs at the mirrored index ({16,32} boxes, transposed reads).  Per
+// texel of the lane: bit 0 = (softor != sum), bit 1 = (softor > sum), i.e. the sign bit of d loss / d sum = -sign(softor - sum) / numel;
+// 16 bits per tile, 64 per super tile.
+template <typename L>
+__device__ __forceinline__ unsigned long long st_loss_signs(unsigned sbase, const StLane& ln) {
+    unsigned long long sgn = 0ull;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned t = sbase + j * 1024;
+        const unsigned a0 = t + ln.tA0, a2 = t + (ln.tA0 ^ 16u) + 128u, b0 = t + (ln.tA0 ^ 32u), b2 = t + (ln.tA0 ^ 48u) + 128u;
+        const unsigned ad[8] = {a0, a0 + 64, a2, a2 + 64, b0, b0 + 64, b2, b2 + 64};
+        unsigned w = 0u;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float d = st_lds32(ad[e] + L::off_go) - st_lds32(ad[e] + L::off_gs);
+            w |= (d != 0.f ? 1u : 0u) << (2 * e);
+            w |= (d > 0.f ? 2u : 0u) << (2 * e);
+        }
+        sgn |= (unsigned long long)w << (16 * j);
+    }
+    return sgn;
+}
+
 // one 16x16 tile of the resident super tile: upstream values of the lane's 8 texels from shared memory, then the tile's candidates
 template <bool SUM, bool SOFTOR, bool SUM_T, bool MSK, int MODE>
 __device__ __forceinline__ void st_tile(unsigned sbase, int j, unsigned tm, unsigned nm, unsigned rec, StPend& pd, float& accr,
-                                        float& lacc, const StLane& ln, int lane, const WtConsts& fc, unsigned inv_bits) {
+                                        float& lacc, const StLane& ln, int lane, const WtConsts& fc, unsigned inv_bits, unsigned long long sgn) {
     typedef StSmem<SUM, SOFTOR, SUM_T, MODE> L;
     constexpr bool LOSS = MODE == ST_LOSS;
     constexpr bool SAVED = MODE == ST_SAVED && SOFTOR;
@@ -376,12 +400,14 @@ __device__ __forceinline__ void st_tile(unsigned sbase, int j, unsigned tm, unsi
             gs[v] = neg2(sg);
         }
         if (SUM_T) {
-            float2 sm_[4], om_[4];
-            ld_tr(L::off_sv, sm_);
-            ld_tr(L::off_ot, om_);
+            // d loss / d sum at this texel = -sign(softor - sum) / numel at the mirrored texel: two bits per texel (st_loss_signs)
+            const unsigned w = (unsigned)(sgn >> (16 * j)) & 0xffffu;
 #pragma unroll
-            for (int v = 0; v < 4; ++v)
-                gs[v] = make_float2(-sign_times(om_[v].x - sm_[v].x, inv_bits), -sign_times(om_[v].y - sm_[v].y, inv_bits));
+            for (int v = 0; v < 4; ++v) {
+                const unsigned bx_ = w >> (4 * v);
+                gs[v] = make_float2(__uint_as_float((bx_ & 1u) ? (inv_bits | ((bx_ & 2u) << 30)) : 0u),
+                                    __uint_as_float((bx_ & 4u) ? (inv_bits | ((bx_ & 8u) << 28)) : 0u));
+            }
         }
         if (tm == 0u) return;
     } else {
@@ -456,23 +482,24 @@ __device__ __forceinline__ void st_tile(unsigned sbase, int j, unsigned tm, unsi
 // requests half h (columns 32 h .. 32 h + 31) of the super tile at (c0, r0) of sample b: 2 KB per array on bar
 template <bool SUM, bool SOFTOR, bool SUM_T, int MODE>
 __device__ __forceinline__ void st_issue_half(unsigned char* st_smem, uint64_t* bar, int h, int c0, int r0, int b, const CUtensorMap* tm_gs,
-                                              const CUtensorMap* tm_go, const CUtensorMap* tm_sv, const CUtensorMap* tm_ot) {
+                                              const CUtensorMap* tm_go, const CUtensorMap* tm_sv, const CUtensorMap* tm_ot, bool mirrored = false) {
     typedef StSmem<SUM, SOFTOR, SUM_T, MODE> L;
     constexpr bool LOSS = MODE == ST_LOSS;
     constexpr bool SAVED = MODE == ST_SAVED && SOFTOR;
     if (tma::elect_one()) {
         const int ch = c0 + 2 * WT * h, o = h * (ST_BOX / 2);
         tma::mbar_expect_tx(bar, (unsigned)(L::n_box * ST_BOX / 2));
+        if (LOSS && SUM_T && mirrored) {
+            tma::load_3d(st_smem + L::off_go + o, tm_ot, bar, r0, ch, b);
+            tma::load_3d(st_smem + L::off_gs + o, tm_sv, bar, r0, ch, b);
+            return;
+        }
         if (SOFTOR || LOSS) tma::load_3d(st_smem + L::off_go + o, tm_go, bar, ch, r0, b);
         if (SUM || LOSS) {
             if (SUM_T && !LOSS) tma::load_3d(st_smem + L::off_gs + o, tm_gs, bar, r0, ch, b);
             else tma::load_3d(st_smem + L::off_gs + o, tm_gs, bar, ch, r0, b);
         }
         if (SAVED) tma::load_3d(st_smem + L::off_sv + o, tm_sv, bar, ch, r0, b);
-        if (LOSS && SUM_T) {
-            tma::load_3d(st_smem + L::off_sv + o, tm_sv, bar, r0, ch, b);
-            tma::load_3d(st_smem + L::off_ot + o, tm_ot, bar, r0, ch, b);
-        }
     }
 }
 
@@ -491,7 +518,8 @@ __device__ __forceinline__ void st_flush(const RasterParams& q, const WtConsts& 
 // tm_go = upstream soft-OR gradient, tm_sv = forward's soft-OR output (SAVED).
 // MODE ST_LOSS: upstream gradients of mean|softor - sum| formed from the forward's outputs (rasterization.py:589-599):
 // tm_go = soft-OR output, tm_gs = sum output addressed like the soft-OR output (its own index: [ts0,ts1] read as stored),
-// and for SUM_T tm_sv / tm_ot = sum / soft-OR outputs as {16,32} boxes at the mirrored index.
+// and for SUM_T tm_sv / tm_ot = sum / soft-OR outputs as {16,32} boxes at the mirrored index (a first request round into the same
+// two boxes: 8.5 KB of shared memory per warp like the other modes, where four resident boxes allowed only 13 warps per SM).
 //
 // One-shot form: one one-warp CTA per (super tile, sample); nothing is requested for super tiles without candidates unless the
 // pattern is dense (q.eager).  Used for sparse patterns, where most super tiles are empty.
@@ -516,12 +544,13 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_st(RasterParams q, 
         tma::fence_mbar_init();
     }
     __syncwarp();
-    auto issue = [&]() {                                    // converged warp
-        st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar, 0, c0, r0, b, &tm_gs, &tm_go, &tm_sv, &tm_ot);
-        st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar + 1, 1, c0, r0, b, &tm_gs, &tm_go, &tm_sv, &tm_ot);
+    constexpr bool TWO = LOSS && SUM_T;                     // two request rounds: mirrored index (sign bits), then own index
+    auto issue = [&](bool mirrored) {                       // converged warp
+        st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar, 0, c0, r0, b, &tm_gs, &tm_go, &tm_sv, &tm_ot, mirrored);
+        st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar + 1, 1, c0, r0, b, &tm_gs, &tm_go, &tm_sv, &tm_ot, mirrored);
     };
     const bool eager = LOSS || q.eager;
-    if (eager) issue();
+    if (eager) issue(TWO);
     const int* toff = q.tile_off + (size_t)bin * (q.T + 1) + (size_t)sty * q.tgx + bx;
     const int beg = __ldg(toff), n = __ldg(toff + 1) - beg;
     const bool grad = n > 0 && n <= WCH;                   // empty: no gradient work; longer lists: overflow kernel
@@ -532,22 +561,30 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_st(RasterParams q, 
         }
         return;
     }
-    if (!eager) issue();
+    if (!eager) issue(false);
+    const StLane ln = st_lane(lane, fc);
+    const unsigned sbase = tma::smem_u32(st_smem);
+    unsigned long long sgn = 0ull;
+    if (TWO) {
+        tma::mbar_wait(bar, 0);
+        tma::mbar_wait(bar + 1, 0);
+        sgn = st_loss_signs<L>(sbase, ln);
+        __syncwarp();                                       // every lane has its bits: the boxes may be overwritten
+        issue(false);
+    }
     const WtMasks mk = st_stage(q, fc, grad, bin, beg, n, c0, r0, lane, rec, idx);
     StPend pd = {0.f, 0.f, 0};
     float accr = 0.f;                                       // lane (k, h): d/dp_h of candidate k, summed over the super tile
-    const StLane ln = st_lane(lane, fc);
     float lacc = 0.f;                                       // LOSS: this lane's share of sum |softor - sum|
     const unsigned inv_bits = __float_as_uint(q.loss_inv);
-    const unsigned sbase = tma::smem_u32(st_smem);
     __syncwarp();
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
-        if (j == 0) tma::mbar_wait(bar, 0);
-        if (j == 2) tma::mbar_wait(bar + 1, 0);
+        if (j == 0) tma::mbar_wait(bar, TWO ? 1u : 0u);
+        if (j == 2) tma::mbar_wait(bar + 1, TWO ? 1u : 0u);
         const unsigned tm = grad ? tile_mask(mk, j) : 0u;
         if (!LOSS && tm == 0u) continue;
-        st_tile<SUM, SOFTOR, SUM_T, MSK, MODE>(sbase, j, tm, near_mask(mk, j), sbase + L::off_rec, pd, accr, lacc, ln, lane, fc, inv_bits);
+        st_tile<SUM, SOFTOR, SUM_T, MSK, MODE>(sbase, j, tm, near_mask(mk, j), sbase + L::off_rec, pd, accr, lacc, ln, lane, fc, inv_bits, sgn);
     }
     if (grad) st_flush(q, fc, pd, accr, lane, n, b, idx);
     if (LOSS) {
@@ -562,7 +599,7 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_st(RasterParams q, 
 // (super tile, sample) items from a global counter, two items ahead; the two halves of the upstream blocks sit behind one mbarrier each,
 // and the next item's left half is requested as soon as tiles 0 and 1 of the current one are done, its right half after tiles 2 and 3 --
 // the same 8 KB of shared memory hold a two-stage pipeline.  The next item's list bounds are loaded a whole item ahead, its records are
-// pulled into L2 half an item ahead.
+// pulled into L1 half an item ahead.
 struct StItem {
     int b, sty, bx;
 };
@@ -599,17 +636,19 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_stp(RasterParams q,
     __syncwarp();
     const float inv_T = 1.0f / (float)q.T, inv_tgx = 1.0f / (float)q.tgx;
     auto toff_of = [&](const StItem& s) { return q.tile_off + (size_t)(q.shared_pattern ? 0 : s.b) * (q.T + 1) + (size_t)s.sty * q.tgx + s.bx; };
-    // claims an item: the first G items are the CTAs' own indices, the counter hands out the rest (one lane asks, the warp gets the answer)
-    auto claim = [&]() {
-        if (!FFB_ST_DYN) return 0;
+    // claims an item: the first G items are the CTAs' own indices, the counter hands out the rest.  One lane asks (claim_ask) at the start
+    // of an item; the warp picks the answer up (claim_get) at its end, a whole item of work later.
+    auto claim_ask = [&]() {
         unsigned v = 0;
-        if (lane == 0) v = atomicAdd(counter, 1u);
-        return (int)__shfl_sync(0xffffffffu, v, 0) + G;
+        if (FFB_ST_DYN && lane == 0) v = atomicAdd(counter, 1u);
+        return v;
     };
+    auto claim_get = [&](unsigned v) { return (int)__shfl_sync(0xffffffffu, v, 0) + G; };
+    constexpr bool TWO = LOSS && SUM_T;                     // two request rounds per item: mirrored index (sign bits), then own index
     StItem cur = st_decode(q, it, inv_T, inv_tgx);
-    st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar, 0, cur.bx * (4 * WT), cur.sty * WT, cur.b, &tm_gs, &tm_go, &tm_sv, &tm_ot);
-    st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar + 1, 1, cur.bx * (4 * WT), cur.sty * WT, cur.b, &tm_gs, &tm_go, &tm_sv, &tm_ot);
-    int nit = FFB_ST_DYN ? claim() : it + G;               // the item after this one
+    st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar, 0, cur.bx * (4 * WT), cur.sty * WT, cur.b, &tm_gs, &tm_go, &tm_sv, &tm_ot, TWO);
+    st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar + 1, 1, cur.bx * (4 * WT), cur.sty * WT, cur.b, &tm_gs, &tm_go, &tm_sv, &tm_ot, TWO);
+    int nit = FFB_ST_DYN ? claim_get(claim_ask()) : it + G;   // the item after this one
     int beg, end;
     {
         const int* t = toff_of(cur);
@@ -629,9 +668,21 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_stp(RasterParams q,
             const int* t = toff_of(nx);
             nbeg = __ldg(t); nend = __ldg(t + 1);
         }
-        const int nnit = FFB_ST_DYN ? (more ? claim() : nit) : nit + G;
+        const unsigned asked = more ? claim_ask() : 0u;     // the item after the next
         const int n = end - beg, c0 = cur.bx * (4 * WT), r0 = cur.sty * WT;
         const bool grad = n > 0 && n <= WCH;               // empty: no gradient work; longer lists: overflow kernel
+        unsigned long long sgn = 0ull;
+        if (TWO) {
+            // round 1 (requested during the previous item): outputs at the mirrored index -> two sign bits per texel; then round 2, the
+            // outputs at the item's own index, lands while the candidates are staged.  Each barrier completes twice per item, so
+            // the mirrored round always waits on parity 0 and the own round on parity 1.
+            tma::mbar_wait(bar, 0);
+            tma::mbar_wait(bar + 1, 0);
+            sgn = st_loss_signs<L>(sbase, ln);
+            __syncwarp();
+            st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar, 0, c0, r0, cur.b, &tm_gs, &tm_go, &tm_sv, &tm_ot);
+            st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar + 1, 1, c0, r0, cur.b, &tm_gs, &tm_go, &tm_sv, &tm_ot);
+        }
         WtMasks mk;
         mk.tb01 = mk.tb23 = mk.nb01 = mk.nb23 = 0u;
         if (grad) mk = st_stage(q, fc, true, q.shared_pattern ? 0 : cur.b, beg, n, c0, r0, lane, rec, idx);
@@ -640,30 +691,30 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_stp(RasterParams q,
         __syncwarp();
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
-            if (j == 0) tma::mbar_wait(bar, phase);
+            if (j == 0) tma::mbar_wait(bar, TWO ? 1u : phase);
             if (j == 2) {
                 __syncwarp();                               // every lane is done with the left half: the next item's may land
                 if (more) {
-                    st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar, 0, nx.bx * (4 * WT), nx.sty * WT, nx.b, &tm_gs, &tm_go, &tm_sv, &tm_ot);
-                    const int nn = nend - nbeg;             // the next item's records: into L2 now, loaded when its staging starts
+                    st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar, 0, nx.bx * (4 * WT), nx.sty * WT, nx.b, &tm_gs, &tm_go, &tm_sv, &tm_ot, TWO);
+                    const int nn = nend - nbeg;             // the next item's records: into L1 now, loaded when its staging starts
                     if (lane < nn && nn <= WCH)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(q.entries + (size_t)(q.shared_pattern ? 0 : nx.b) * q.cap + nbeg + lane));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(q.entries + (size_t)(q.shared_pattern ? 0 : nx.b) * q.cap + nbeg + lane));
                 }
-                tma::mbar_wait(bar + 1, phase);
+                tma::mbar_wait(bar + 1, TWO ? 1u : phase);
             }
             const unsigned tm = tile_mask(mk, j);
             if (!LOSS && tm == 0u) continue;
-            st_tile<SUM, SOFTOR, SUM_T, MSK, MODE>(sbase, j, tm, near_mask(mk, j), sbase + L::off_rec, pd, accr, lacc, ln, lane, fc, inv_bits);
+            st_tile<SUM, SOFTOR, SUM_T, MSK, MODE>(sbase, j, tm, near_mask(mk, j), sbase + L::off_rec, pd, accr, lacc, ln, lane, fc, inv_bits, sgn);
         }
         __syncwarp();
-        if (more) st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar + 1, 1, nx.bx * (4 * WT), nx.sty * WT, nx.b, &tm_gs, &tm_go, &tm_sv, &tm_ot);
+        if (more) st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar + 1, 1, nx.bx * (4 * WT), nx.sty * WT, nx.b, &tm_gs, &tm_go, &tm_sv, &tm_ot, TWO);
         if (grad) st_flush(q, fc, pd, accr, lane, n, cur.b, idx);
         if (LOSS) {
             lacc = warp_sum(lacc);
             if (lane == 0) atomicAdd(q.loss + cur.b, lacc * q.loss_inv);
         }
         if (!more) break;
-        it = nit; nit = nnit; cur = nx; beg = nbeg; end = nend;
+        it = nit; nit = FFB_ST_DYN ? claim_get(asked) : nit + G; cur = nx; beg = nbeg; end = nend;
         phase ^= 1u;
         __syncwarp();                                       // records and point indices of this item are dead
     }

@@ -237,7 +237,8 @@ FFB_API int ffb_sample_anim_index(const int32_t* amin, const int32_t* amax, int3
 
 typedef struct ffb_entity {
     int32_t kind;           /* FFB_ENTITY_*                                                  */
-    int32_t parent;         /* row of the parent entity, -1 = root (entity/base.py:239-244); must be < own row */
+    int32_t parent;         /* row of the parent entity, -1 = root (entity/base.py:239-244); must be < own row:
+                               a row whose parent does not precede it gets NaN matrices (loud, not a dropped parent) */
     int32_t randomizable;   /* 0: local = W  (randomize() returns early, entity/base.py:221-222) */
     int32_t s_translation;  /* sampler rows feeding this entity; -1 = zeros / zeros / ones    */
     int32_t s_rotation;

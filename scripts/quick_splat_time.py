@@ -50,8 +50,14 @@ for name, fn in [("nat sum+softor", lambda: plan.backward(ptsB, gSn, gO, False))
     env(FFB_SPLAT_BWD_ST="0"); to = t(fn); do = fn()
     env(FFB_SPLAT_BWD_ST=None)
     print(f"bwd {name:15s}: st {tn:.3f} ms, old {to:.3f} ms; rel diff {float((dn - do).norm() / do.norm()):.3e}")
-tl = t(lambda: plan.backward_l1(ptsB, S_, O_, True))
-print(f"fused L1 backward: {tl:.3f} ms ({B*8*hw/tl/1e6:.0f} GB/s algorithmic)")
+for nm_, st_ in (("st", "1"), ("old", None)):
+    env(FFB_SPLAT_L1_ST=st_)
+    tl = t(lambda: plan.backward_l1(ptsB, S_, O_, True))
+    ll, dl = plan.backward_l1(ptsB, S_, O_, True)
+    if st_ == "1": l_new, d_new = ll, dl
+    print(f"fused L1 backward ({nm_}): {tl:.3f} ms ({B*8*hw/tl/1e6:.0f} GB/s algorithmic)")
+env(FFB_SPLAT_L1_ST=None)
+print(f"  L1 st vs old: loss rel {float((l_new - ll).abs().max() / ll.abs().max()):.2e}, grad rel-to-norm {float((d_new - dl).norm() / dl.norm()):.3e}")
 tb = res["st_rebuild"][0]
 print(f"B={B} prepare {tp:.3f} ms  fwd {tf:.3f} ms ({B*8*hw/tf/1e6:.0f} GB/s)  bwd {tb:.3f} ms ({B*8*hw/tb/1e6:.0f} GB/s)"
       f"  fwd+bwd per sample {(tf+tb)/B*1e3:.2f} us -> {B/(tf+tb)*1e3:.0f} samples/s, roofline frac {(B*(16*hw+16*N)/((tp+tf+tb)*1e-3))/6458.4e9:.3f}")

@@ -141,6 +141,52 @@ def test_parent_child_eval_chain(ff, golden):
     close(res.mesh_vertices("b"), g["chain_child_verts"], rtol=1e-5, atol=1e-5)
 
 
+def test_batch_orders_parents_across_lists_and_trees(ff):
+    """Parents in another entity list (a light and a mesh parented to the camera) and a parent with two children: the batched world
+    matrices equal Transformable.world() of the same objects (reference: world = parent.world() @ local, entity/base.py:239-244)."""
+    c = lambda v: torch.tensor(v, dtype=torch.float32).cuda()  # noqa: E731
+    g = torch.Generator().manual_seed(11)
+    cam = ff.entity.Transformable("PerspectiveCamera")
+    cam.set_world(c([[0.0, -1.0, 0.0, 1.0], [1.0, 0.0, 0.0, 2.0], [0.0, 0.0, 1.0, 3.0], [0.0, 0.0, 0.0, 1.0]]))
+    cam.rotate_x(0.2, 0.2); cam.translate_y(0.5, 0.5)                 # degenerate ranges: the "random" pose is known
+    light = ff.entity.Transformable("light-on-camera")
+    light.set_world(c([[1.0, 0.0, 0.0, 0.0], [0.0, 1.0, 0.0, 0.25], [0.0, 0.0, 1.0, -0.5], [0.0, 0.0, 0.0, 1.0]]))
+    light.setParent(cam); light.rotate_y(-0.4, -0.4)
+    p = ff.entity.Mesh("tree-parent", torch.rand(8, 3, generator=g).cuda())
+    c1 = ff.entity.Mesh("tree-child-1", torch.rand(8, 3, generator=g).cuda())
+    c2 = ff.entity.Mesh("tree-child-2", torch.rand(8, 3, generator=g).cuda())
+    g1 = ff.entity.Mesh("tree-grandchild", torch.rand(8, 3, generator=g).cuda())
+    rig = ff.entity.Mesh("mesh-on-camera", torch.rand(8, 3, generator=g).cuda())
+    p.rotate_z(0.7, 0.7); p.translate_x(-1.0, -1.0)
+    for ch, par, ang in ((c1, p, 0.3), (c2, p, -0.6), (g1, c1, 1.1), (rig, cam, 0.15)):
+        ch._parent = par                                              # setParent keeps ONE child slot; a tree needs the bare link
+        ch.set_randomizable(True); ch.rotate_y(ang, ang); ch.scale_x(1.5, 1.5)
+    sc = ff.Scene(fm.FakeParams())
+    sc._meshes += [g1, c1, c2, p, rig]                                # worst case: every child listed before its parent
+    sc._lights.append(light)
+    sc._camera = cam
+    sc.train()
+    sb = sc.batch(seed=5)
+    order = {e.name(): i for i, e in enumerate(sb.entities)}
+    for e in sb.entities:
+        if e.parent() is not None:
+            assert order[e.parent().name()] < order[e.name()]
+    res = sb.randomize(2)
+    for e in (cam, p, c1, c2, g1, rig, light):                        # parents first: world() reads the parent's randomised matrix
+        e.randomize()
+    for e in (cam, light, p, c1, c2, g1, rig):
+        close(res.entity_world(e.name())[1], e.world(), rtol=1e-5, atol=1e-5)
+    close(res.mesh_vertices("tree-grandchild")[0], g1.get_randomized_vertices(), rtol=1e-5, atol=1e-5)
+    # a parent outside the scene, or re-parenting after the batch was built, is an error instead of a silently dropped parent
+    stray = ff.entity.Transformable("stray")
+    c2._parent = stray
+    with pytest.raises(ValueError):
+        sc.batch()
+    c2._parent = g1                                                   # g1 follows c2 in the existing table
+    with pytest.raises(ValueError):
+        sb.refresh()
+
+
 def test_transformable_attributes(ff, golden):
     g = golden("transforms")
     c = lambda v: torch.tensor(v).cuda()  # noqa: E731
