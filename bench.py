@@ -7,9 +7,12 @@
 Workload = BASELINE.json configs[2] ("batched pattern optimisation": 4096 laser points into a 2048x2048
 projector texture, 256 randomised scenes per step, fwd+bwd); with N GPUs every rank runs 256 scenes per step
 (weak scaling; N=8 is configs[4], 2048 scenes/step) and the only collective is the allreduce of the [4096,2]
-pattern gradient.  One step = randomise B scenes (sampling + 4x4 compose + 100k-vertex transform), bin + splat
-forward (baked_sum_2 + baked_softor_2 semantics), splat backward against resident upstream texture gradients,
-fold the per-sample gradients, allreduce.
+pattern gradient.  One step = fireflies_b200.PatternStep.forward_backward(pattern, upstream=...):
+randomise B scenes (sampling + 4x4 compose + 100k-vertex transform), bin + splat forward (baked_sum_2 +
+baked_softor_2 semantics), splat backward against resident upstream texture gradients, fold the per-sample
+gradients, allreduce.  With N > 1 the run starts with parallel.multi_gpu_selfcheck (`multi_gpu_check` in the line;
+a mismatch exits non-zero).  `side` carries the other single-GPU configs (configs[0] step latency, configs[1],
+configs[3]).
 
 Prints ONE JSON line (rank 0).  `value` is device-timed with all inputs resident in HBM; `e2e` is the same step
 through the public API (fireflies_b200.PatternStep.step_host) with HOST buffers for the pattern, the loss and the
@@ -43,6 +46,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=256, help="scene samples per step per GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the side measurements of the other single-GPU configs")
     return ap.parse_args()
 
 
@@ -194,6 +198,107 @@ def build_scene(ff, device):
     return sc
 
 
+def side_configs(ff, device, peak):
+    """The other single-GPU BASELINE configs, as short side measurements (CUDA events, medians; inputs resident; a 256 MB buffer is
+    rewritten between iterations so that nothing is served from L2).  Not the headline metric."""
+    from fireflies_b200.graphics import rasterization as R
+    from fireflies_b200.postprocessing.base import run_postprocess
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def timed(fn, n=10, do_flush=True):
+        for _ in range(3):
+            fn()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for a, b in ev:
+            if do_flush:
+                flush.zero_()
+            a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        t = sorted(a.elapsed_time(b) for a, b in ev)
+        return t[len(t) // 2]
+
+    out = {}
+    # ---- configs[0]: the reference's own loop (rasterization.py:583-607): 100 points -> 512^2, L1(softor, sum), one sample, plus a
+    #      single mesh with rotate_z randomised (examples/01_hello_world.py:23-33).  Launch-bound: eager API vs the captured graph.
+    g0 = torch.Generator().manual_seed(0)
+    p0 = (torch.rand(100, 2, generator=g0) * 0.8 + 0.1).to(device)
+    sc0 = ff.Scene(_Params(), device=device)
+    m0 = ff.entity.Mesh("mesh-One", (torch.rand(10_000, 3, generator=g0) * 2 - 1).to(device), device)
+    m0.rotate_z(-3.14159, 3.14159)
+    sc0._meshes.append(m0)
+    sc0.train()
+    sb0 = sc0.batch(seed=9)
+    step0 = ff.PatternStep(100, (512, 512), 100.0, 1, scene_batch=None, device=device)
+    replay = step0.capture(p0)
+    side = torch.cuda.Stream(device=device)
+
+    def graphed():
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            sb0.randomize(1)
+        replay(p0)
+        cur.wait_stream(side)
+
+    def eager():
+        q = p0.clone().requires_grad_(True)
+        m0.randomize(); m0.get_randomized_vertices()
+        s, o = R.splat_reduce(q, 100.0, [512, 512], sum_transposed=True)
+        R.l1_loss(o, s).backward()
+
+    n_wall = 200
+    for fn_name, fn in (("graph", graphed), ("eager_reference_api", eager)):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_wall):
+            fn()
+        torch.cuda.synchronize()
+        out.setdefault("config0_step_ms", {})[fn_name] = (time.perf_counter() - t0) / n_wall * 1e3
+    out["config0_step_ms"]["splat_graph_only_device"] = timed(lambda: replay(p0), n=20, do_flush=False)
+    out["config0_step_ms"]["note"] = ("100 points -> 512^2, B=1, bin + splat fwd + fused L1(softor,sum) backward + fold (+ one 10k-vertex mesh "
+                                      "randomised); wall clock per step over 200 steps, graph = PatternStep.capture replay next to SceneBatch.randomize")
+    # ---- configs[1]: vocal-fold scene, B = 32: 18x18 grid pattern -> 500^2 sum texture + (5,5)/(3,3) blur (main.py:51-77), VocalFold
+    #      (animated, V=20000, F=64) + Larynx (V=50000) randomised (examples/vocalfold_scene.py:73-77)
+    g = torch.Generator().manual_seed(2)
+    F, V1, V2, Bs = 64, 20000, 50000, 32
+    frames = (torch.rand(F, V1, 3, generator=g) * 2 - 1).to(device)
+    sc = ff.Scene(_Params(), device=device)
+    vf = ff.entity.Mesh("mesh-VocalFold", frames[0], device)
+    vf.add_train_animation(frames); vf.add_eval_animation(frames, max=F - 1)
+    vf.scale_x(0.5, 2.0); vf.rotate_y(-0.25, 0.25)
+    la = ff.entity.Mesh("mesh-Larynx", (torch.rand(V2, 3, generator=g) * 2 - 1).to(device), device)
+    la.scale_x(0.8, 1.2); la.rotate_y(-0.1, 0.1)
+    sc._meshes += [vf, la]
+    sc.train()
+    sb = sc.batch(seed=1)
+    rays = ff.projection.Laser.generate_uniform_rays(0.0275, 18, 18)
+    K = ff.utils.io.build_projection_matrix(60, 0.01, 1000.0)
+    laser = ff.projection.Laser(ff.entity.Transformable("projector"), rays, K, 60.0, 0.01, 1000.0)
+    pts01 = (laser.projectRaysToNDC()[:, 0:2] * 0.5 + 0.5).detach().contiguous()
+    ptsB = pts01.unsqueeze(0).repeat(Bs, 1, 1).contiguous()
+
+    def c1():
+        sb.randomize(Bs)
+        tex = R.splat_reduce(ptsB, 10.0, [500, 500], num_std_sum=None, reduce=("sum",))[0]
+        run_postprocess(tex, blur=((5, 5), (3.0, 3.0)))
+    ms = timed(c1)
+    by = Bs * (8 * 250_000 + 8 * 250_000 + 24 * (V1 + V2))
+    out["config1_vocalfold_B32"] = {"ms_per_32_samples": ms, "samples_per_s": Bs / (ms * 1e-3), "GBs": by / (ms * 1e-3) / 1e9,
+                                    "frac_of_measured_peak": by / (ms * 1e-3) / 1e9 / peak,
+                                    "note": "randomise two meshes (70k vertices, animated gather) + 324-point sum texture at 500^2 + 5x5 blur per sample"}
+    # ---- configs[3]: post-processing, 64 x 1024^2 frames: blur (3,3) sigma (5,5) + white noise (0, 0.05) + clip
+    Bf, H, W = 64, 1024, 1024
+    x = torch.rand(Bf, H, W, device=device)
+    gates_on = torch.ones(Bf, 2, dtype=torch.uint8, device=device)
+    ms = timed(lambda: run_postprocess(x, gates=gates_on, seed=1, frame0=0, blur=((3, 3), (5.0, 5.0)), noise=(0.0, 0.05)))
+    gbs = 8 * Bf * H * W / (ms * 1e-3) / 1e9
+    out["config3_postprocess_64x1024x1024"] = {"ms_per_64_frames": ms, "frames_per_s": Bf / (ms * 1e-3), "GBs": gbs,
+                                               "frac_of_measured_peak": gbs / peak, "note": "blur3x3 + noise + clip, both gates on, 8 B/texel"}
+    return out
+
+
 def main_ours(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -212,49 +317,42 @@ def main_ours(args):
         dist.init_process_group("nccl", device_id=device)
     import fireflies_b200 as ff
     from fireflies_b200 import _native as nat
-    from fireflies_b200.graphics import rasterization as R
-    from fireflies_b200.parallel import fold_allreduce, max_over_ranks, shard_samples
+    from fireflies_b200 import parallel as par
+    from fireflies_b200.parallel import max_over_ranks, shard_samples
 
     B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
     hw = TS[0] * TS[1]
     first, _ = shard_samples(B * world, rank, world)
+
+    # ---- N > 1: correctness of the exchange, of the sample split and of the sharded gradient, before anything is timed ----
+    mg_check = None
+    if world > 1:
+        try:
+            mg_check = par.multi_gpu_selfcheck(device)
+        except AssertionError as exc:
+            sys.stderr.write(f"bench.py: multi-GPU self check FAILED on rank {rank}: {exc}\n")
+            os.dup2(saved_stdout, 1)
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "impl": "ours", "multi_gpu_check": {"failed": str(exc)}, "n_gpus": world}))
+            sys.stdout.flush()
+            os._exit(3)
+
     # ---- resident inputs ----
     g0 = torch.Generator().manual_seed(0)
     pattern = (torch.rand(N_POINTS, 2, generator=g0) * 0.96 + 0.02).to(device)
-    ptsB = pattern.unsqueeze(0).repeat(B, 1, 1).contiguous()
     gdev = torch.Generator(device=device).manual_seed(4 + rank)
     gS = torch.randn(B, TS[0], TS[1], device=device, generator=gdev)       # layout of baked_sum_2 ([ts0, ts1])
     gO = torch.randn(B, TS[1], TS[0], device=device, generator=gdev)
     scene = build_scene(ff, device)
     sb = scene.batch(seed=1234)
     step_obj = ff.PatternStep(N_POINTS, TS, SIGMA, B, scene_batch=sb, device=device)
+    phases = ["prepare", "fwd", "bwd", "fold"]
+    marks = [dict() for _ in range(K)]
 
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    phases = ["randomize", "prepare", "fwd", "bwd", "fold"]
-    marks = [[ev() for _ in range(len(phases) + 1)] for _ in range(K)]
-
-    side = torch.cuda.Stream(device=device)
-    rmarks = [[ev(), ev()] for _ in range(K)]
-
-    def one_step(i, rec=None, rrec=None):
-        # scene randomisation on a side stream next to the (latency-bound) binning kernel, as PatternStep does
-        cur = torch.cuda.current_stream()
-        if rec: rec[0].record()
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            if rrec: rrec[0].record()
-            sb.randomize(B, sample0=i * B * world + first)
-            if rrec: rrec[1].record()
-        if rec: rec[1].record()
-        plan = R._SplatPlan(ptsB, B, SIGMA, TS[0], TS[1], 4, 5)
-        if rec: rec[2].record()
-        _, softor = plan.forward(ptsB, True, True, True)
-        if rec: rec[3].record()
-        d = plan.backward(ptsB, gS, gO, True, softor)      # like autograd: the forward's soft-OR output is kept for the backward
-        if rec: rec[4].record()
-        cur.wait_stream(side)
-        dp = fold_allreduce(d)                             # fold over the samples + allreduce over the ranks (one kernel on NVLink)
-        if rec: rec[5].record()
+    def one_step(i, rec=None):
+        # the public API: randomise B scenes (side stream) | bin + splat forward -> backward against the resident upstream
+        # gradients -> fold over the samples + allreduce over the ranks
+        _, dp, _ = step_obj.forward_backward(pattern, upstream=(gS, gO), sample0=i * B * world + first, marks=rec)
         return dp
 
     def barrier():
@@ -262,6 +360,7 @@ def main_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     for i in range(Wm):
         one_step(i)
     barrier()
@@ -275,42 +374,46 @@ def main_ours(args):
     barrier()
     e0.record()
     for i in range(K):
-        one_step(Wm + i, marks[i], rmarks[i])
+        one_step(Wm + i, marks[i])
     e1.record()
     barrier()
-    from fireflies_b200 import parallel as _par
-    for f in _par._FOLDERS.values():                       # the peer-memory allreduce reports a missing peer instead of hanging
-        if f is not None:
-            f.check()
+    par.check_folders()                                    # the peer-memory allreduce reports a missing peer instead of hanging
     total_ms = max_over_ranks(e0.elapsed_time(e1), device)
     launches = nat.launch_count - l0          # our kernels only (the NCCL allreduce is not counted)
     clk = clocks.stop()
     ms_step = total_ms / K
     value = B * world * K / (total_ms * 1e-3)
-    ph_ms = {p: sum(m[j].elapsed_time(m[j + 1]) for m in marks) / K for j, p in enumerate(phases)}
-    ph_ms["randomize"] = sum(r[0].elapsed_time(r[1]) for r in rmarks) / K      # side stream, concurrent with prepare / fwd
+    order = ["start"] + phases[:-1] + ["end"]
+    ph_ms = {p: sum(m[order[j]].elapsed_time(m[order[j + 1]]) for m in marks) / K for j, p in enumerate(phases)}
+    ph_ms["randomize"] = sum(m["randomize0"].elapsed_time(m["randomize1"]) for m in marks) / K      # side stream, concurrent with prepare / fwd
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    spec = 8000.0
     alg = {"fwd": B * (8 * hw + 8 * N_POINTS), "bwd": B * (8 * hw + 16 * N_POINTS), "randomize": B * 24 * V_MESH}
     dom = max(("fwd", "bwd"), key=lambda p: ph_ms[p])
-    traffic = None
-    kname = {"fwd": "splat_fwd_tma", "bwd": "splat_bwd_tma"}[dom]
+    traffic, traffic_src = None, None
+    kname = {"fwd": "splat_fwd_tma", "bwd": "splat_bwd_stp"}[dom]
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath):                   # DRAM bytes per sample from the committed ncu --set full capture, scaled to this launch
-        per_sample = json.load(open(tpath)).get("per_sample_bytes", {}).get(kname)
+        tj = json.load(open(tpath))
+        per_sample = tj.get("per_sample_bytes", {}).get(kname)
         traffic = per_sample * B if per_sample else None
+        traffic_src = tj.get("source")
     ach = alg[dom] / (ph_ms[dom] * 1e-3) / 1e9
     step_bytes = B * (16 * hw + 16 * N_POINTS + 24 * V_MESH)
+    step_ach = step_bytes / (ms_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
-                "whole_step": {"achieved": step_bytes / (ms_step * 1e-3) / 1e9, "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                "frac_of_spec_8TBs": ach / spec, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dom],
+                "whole_step": {"achieved": step_ach, "frac": step_ach / peak, "frac_of_spec_8TBs": step_ach / spec,
                                "algorithmic_bytes_per_step": step_bytes},
                 "kernels_ms": ph_ms,
-                "kernels_gbs": {p: alg[p] / (ph_ms[p] * 1e-3) / 1e9 for p in alg}}
+                "kernels_gbs": {p: alg[p] / (ph_ms[p] * 1e-3) / 1e9 for p in alg},
+                "kernels_frac": {p: alg[p] / (ph_ms[p] * 1e-3) / 1e9 / peak for p in alg}}
 
     # ---- optimisation mode, reported separately: one pattern shared by all scenes of the step ----
     # The B textures are then one texture and the backward is linear in the upstream gradients: fold them over the samples
@@ -356,6 +459,13 @@ def main_ours(args):
                "path": "PatternStep.step_host: pinned pattern H2D -> randomise (side stream) | bin + splat fwd -> fused L1(softor,sum) "
                        "loss + backward (rasterization.py:589-599, ffb_splat_bwd_l1) -> fold -> allreduce -> gradient+loss D2H"}
 
+    side = None
+    if rank == 0 and world == 1 and not args.no_side:
+        try:
+            side = side_configs(ff, device, peak)
+        except Exception as exc:  # noqa: BLE001  (a side measurement must not take the headline line down)
+            side = {"error": repr(exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = 40                                                    # ~12 s of CPU work on the box (3.4 samples/s)
@@ -368,7 +478,7 @@ def main_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config(B, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "shared_pattern_mode": shared,
-            "gpu_launches": launches,
+            "multi_gpu_check": mg_check, "side": side, "gpu_launches": launches,
             "clocks": clk}))
     if world > 1:
         dist.destroy_process_group()

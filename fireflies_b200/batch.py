@@ -323,19 +323,34 @@ class PatternStep:
         allreduce_sum_(t, self.pg)
 
     def forward_backward(self, points: torch.Tensor, upstream: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-                         sample0: Optional[int] = None):
+                         sample0: Optional[int] = None, marks: Optional[dict] = None, randomize: bool = True):
         """points: ``[N,2]`` or ``[B,N,2]`` (device, or pinned host -> copied inside).  Returns
-        ``(loss [B] or None, dpoints [N,2] summed over the B samples and all ranks, BatchResult or None)``."""
+        ``(loss [B] or None, dpoints [N,2] summed over the B samples and all ranks, BatchResult or None)``.
+        ``marks``: a dict that receives one CUDA event per phase boundary (``start, prepare, fwd, bwd, end`` on the calling stream,
+        ``randomize0 / randomize1`` on the side stream) -- how ``bench.py`` times the kernels of the step it measures.
+        Phases are wrapped in NVTX ranges (``ffb.randomize / prepare / fwd / bwd / fold``)."""
+        nvtx = torch.cuda.nvtx
+
+        def mark(name, stream=None):
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream) if stream is not None else ev.record()
+                marks[name] = ev
         # the scene randomisation (HBM-bound vertex transform) does not depend on the pattern: it runs on a side stream
         # next to the latency-bound binning kernel and joins before the fold
         res = None
-        if self.scene_batch is not None:
+        mark("start")
+        if self.scene_batch is not None and randomize:
             cur = torch.cuda.current_stream()
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.device)
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
+                nvtx.range_push("ffb.randomize")
+                mark("randomize0", self._side)
                 res = self.scene_batch.randomize(self.B, sample0=sample0)
+                mark("randomize1", self._side)
+                nvtx.range_pop()
         if points.dim() == 2:
             if self.per_sample:
                 # one 8N-byte host->device copy, then a device-side broadcast (a copy from an expanded host view costs 0.5 ms)
@@ -349,10 +364,17 @@ class PatternStep:
             loss, dp, s, o = self._shared_pattern(self.pts_dev[0], upstream)
             return self._finish(loss, dp, s, o, res)
         pts = self.pts_dev
+        nvtx.range_push("ffb.prepare")
         plan = R._SplatPlan(pts, self.B, self.sigma, self.ts0, self.ts1, self.ns, self.no)
+        nvtx.range_pop()
+        mark("prepare")
+        nvtx.range_push("ffb.fwd")
         s, o = plan.forward(pts, True, True, self.sum_t)
+        nvtx.range_pop()
+        mark("fwd")
         loss = None
         d = None
+        nvtx.range_push("ffb.bwd")
         if upstream is None:
             # rasterization.py:589-599: L1(softored, summed) -- the reference compares against the transposed sum as-is
             fused = plan.backward_l1(pts, s, o, self.sum_t) if self.fuse_loss else None
@@ -368,7 +390,42 @@ class PatternStep:
             gs, go = upstream
         if d is None:
             d = plan.backward(pts, gs, go, self.sum_t, o)
-        return self._finish(loss, None, s, o, res, per_sample=d)
+        nvtx.range_pop()
+        mark("bwd")
+        nvtx.range_push("ffb.fold")
+        out = self._finish(loss, None, s, o, res, per_sample=d)
+        nvtx.range_pop()
+        mark("end")
+        return out
+
+    def capture(self, points: torch.Tensor, upstream: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        """CUDA-graph form of the step for small, launch-bound problems (the reference's own loop, rasterization.py:583-607, runs
+        100 points into 512^2 for one sample: ten kernels of a few microseconds each).  Captures bin + splat forward + loss +
+        backward + fold once and returns ``replay(points) -> (loss, dpoints)``; the tensors are overwritten by every replay.
+        The scene randomisation is not captured (its sample index is a host-side kernel argument): call
+        ``scene_batch.randomize`` next to the replay.  One rank only (the exchange agrees on its path with a host read)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1:
+            raise NotImplementedError("PatternStep.capture: single rank only")
+        static_pts = torch.empty_like(points, device=self.device)
+        static_pts.copy_(points)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):                              # warm-up: one-time attribute / occupancy queries happen outside the capture
+                self.forward_backward(static_pts, upstream=upstream, randomize=False)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss, dp, _ = self.forward_backward(static_pts, upstream=upstream, randomize=False)
+
+        def replay(new_points: Optional[torch.Tensor] = None):
+            if new_points is not None:
+                static_pts.copy_(new_points, non_blocking=True)
+            graph.replay()
+            return loss, dp
+        replay.graph = graph
+        return replay
 
     def _finish(self, loss, dp, s, o, res, per_sample=None):
         if res is not None:

@@ -73,13 +73,18 @@ class FoldAllreduce:
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         nat, C = self._nat, self._C
         x = nat.require_cuda(x, torch.float32, "x")
+        if x.shape[0] == 0:                     # a rank without samples still takes part in the exchange: it contributes zeros
+            x = torch.zeros((1,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
         if x[0].numel() != self.row:
             raise ValueError("FoldAllreduce: row size differs from the one it was built for")
+        if x.device != self.recv.device:
+            raise ValueError("FoldAllreduce: tensor lives on another device than the receive buffers")
         self.epoch += 1
-        out = torch.empty(x.shape[1:], dtype=torch.float32, device=x.device)
-        nat.check(nat.lib().ffb_fold_allreduce(x.data_ptr(), x.shape[0], self.row, C.cast(self._recv_ptrs, C.c_void_p),
-                                               C.cast(self._flag_ptrs, C.c_void_p), self.rank, self.world, self.epoch,
-                                               out.data_ptr(), self.err.data_ptr(), nat.stream()), "ffb_fold_allreduce")
+        with torch.cuda.device(x.device):       # the launch uses the current device's stream
+            out = torch.empty(x.shape[1:], dtype=torch.float32, device=x.device)
+            nat.check(nat.lib().ffb_fold_allreduce(x.data_ptr(), x.shape[0], self.row, C.cast(self._recv_ptrs, C.c_void_p),
+                                                   C.cast(self._flag_ptrs, C.c_void_p), self.rank, self.world, self.epoch,
+                                                   out.data_ptr(), self.err.data_ptr(), nat.stream()), "ffb_fold_allreduce")
         nat.count()
         return out
 
@@ -92,25 +97,129 @@ class FoldAllreduce:
 _FOLDERS = {}
 
 
+def _peer_path_available(x: torch.Tensor, group) -> bool:
+    """Whether EVERY rank can take the peer-memory path.  The choice must be collective: a rank that fell back to NCCL on its own
+    would leave its peers spinning in the flag wait of the kernel."""
+    import os
+    ok = x.is_cuda and os.environ.get("FFB_SYMM_ALLREDUCE", "1") != "0" and dist.get_backend(group) == "nccl"
+    ok = ok and x[0].numel() <= 37888 and dist.get_world_size(group) <= 8
+    if ok:
+        try:
+            import torch.distributed._symmetric_memory  # noqa: F401
+        except Exception:  # noqa: BLE001
+            ok = False
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=x.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(flag.item())
+
+
 def fold_allreduce(x: torch.Tensor, group=None) -> torch.Tensor:
     """``x.sum(0)`` over this rank's samples, summed over all ranks.  One rank: the fold kernel.  Several ranks on NCCL:
-    the fused peer-memory kernel (:class:`FoldAllreduce`) unless ``FFB_SYMM_ALLREDUCE=0`` or symmetric memory is unavailable,
-    in which case fold + ``dist.all_reduce``."""
-    import os
+    the fused peer-memory kernel (:class:`FoldAllreduce`) when every rank can take it (agreed once per tensor shape with an
+    allreduce(MIN); ``FFB_SYMM_ALLREDUCE=0``, more than 8 ranks or a system without symmetric memory switch ALL ranks to fold +
+    ``dist.all_reduce``).  A rank with zero samples contributes zeros."""
     from .graphics import rasterization as R
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-    if multi and x.is_cuda and os.environ.get("FFB_SYMM_ALLREDUCE", "1") != "0" and dist.get_backend(group) == "nccl":
+    if multi and x.is_cuda:
         key = (x[0].numel(), x.device.index, id(group))
-        f = _FOLDERS.get(key)
-        if f is None and key not in _FOLDERS:
-            try:
-                f = FoldAllreduce(x[0].numel(), x.device, group) if x[0].numel() <= 37888 and dist.get_world_size(group) <= 8 else None
-            except Exception as exc:  # noqa: BLE001  (no symmetric memory on this system: keep the NCCL form)
-                import warnings
-                warnings.warn(f"fireflies_b200: peer-memory allreduce unavailable ({exc}); using NCCL")
-                f = None
-            _FOLDERS[key] = f
+        if key not in _FOLDERS:
+            # construction is collective (symmetric-memory rendezvous + barrier): an error here is raised, not papered over
+            _FOLDERS[key] = FoldAllreduce(x[0].numel(), x.device, group) if _peer_path_available(x, group) else None
+        f = _FOLDERS[key]
         if f is not None:
             return f(x)
-    out = R.reduce_over_samples(x) if x.shape[0] > 1 else x[0].clone()
+    if x.shape[0] == 0:
+        out = torch.zeros(x.shape[1:], dtype=torch.float32, device=x.device)
+    else:
+        out = R.reduce_over_samples(x) if x.shape[0] > 1 else x[0].clone()
     return allreduce_sum_(out, group)
+
+
+def check_folders() -> None:
+    """Raises if any peer-memory exchange so far missed a peer (host sync; :meth:`FoldAllreduce.check`)."""
+    for f in _FOLDERS.values():
+        if f is not None:
+            f.check()
+
+
+def multi_gpu_selfcheck(device, group=None, n_points: int = 512, texture=(256, 256), sigma: float = 25.0, per_rank: int = 4,
+                        mesh_vertices: int = 3000, rounds: int = 6) -> dict:
+    """Correctness of the N > 1 path on real devices; every rank calls it.  Small shapes, a few milliseconds.
+
+    1. ``allreduce``: :func:`fold_allreduce` of this rank's per-sample pattern gradients equals fold + ``dist.all_reduce`` (1e-5
+       relative) and is bit-identical on every rank (all_gather), ``rounds`` times in a row (epoch double buffering), the kernel's
+       missing-peer flag checked every round.
+    2. ``rng_split_invariant``: the scene samples of rank 0's shard recomputed on this rank are bit-identical to rank 0's own
+       (broadcast), and this rank's shard equals the same rows of a full-batch randomisation.
+    3. ``sharded_gradient``: the allreduced gradient of the sharded step equals the full batch evaluated on this rank alone (1e-4
+       relative to the gradient's norm).
+    Returns ``{check: "ok"}``; raises ``AssertionError`` naming the first failing check."""
+    import fireflies_b200 as ff
+    from .graphics import rasterization as R
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    world = dist.get_world_size(group) if multi else 1
+    rank = dist.get_rank(group) if multi else 0
+    device = torch.device(device)
+    total = per_rank * world
+    first, n = shard_samples(total, rank, world)
+    out = {}
+    # ---- scene: one mesh with ranged translation / rotation / scale, Philox train mode ----
+    class _P(dict):
+        def update(self, *a, **k):
+            if a or k:
+                return super().update(*a, **k)
+    verts = torch.rand(mesh_vertices, 3, generator=torch.Generator().manual_seed(21)) * 2 - 1
+    sc = ff.Scene(_P(), device=device)
+    m = ff.entity.Mesh("mesh-selfcheck", verts.to(device), device)
+    c = lambda v: torch.tensor(v, device=device)  # noqa: E731
+    m.translate(c([-0.5, -0.5, -0.5]), c([0.5, 0.5, 0.5]))
+    m.rotate(c([-3.1, -3.1, -3.1]), c([3.1, 3.1, 3.1]))
+    m.scale(c([0.5, 0.5, 0.5]), c([2.0, 2.0, 2.0]))
+    sc._meshes.append(m)
+    sc.train()
+    sb = sc.batch(seed=4321)
+    own = sb.randomize(n, sample0=first)
+    shard0 = sb.randomize(per_rank, sample0=0)
+    ref = shard0.vertices.clone()
+    if multi:
+        dist.broadcast(ref, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    full = sb.randomize(total, sample0=0)
+    ok = torch.equal(ref, shard0.vertices) and torch.equal(full.vertices[first:first + n], own.vertices) \
+        and torch.equal(full.world[first:first + n], own.world)
+    assert ok, "rng_split_invariant: randomised scene samples depend on the rank layout"
+    out["rng_split_invariant"] = "ok"
+    # ---- pattern gradients: per-sample upstream gradients keyed by the GLOBAL sample index ----
+    ts0, ts1 = int(texture[0]), int(texture[1])
+    pattern = (torch.rand(n_points, 2, generator=torch.Generator().manual_seed(3)) * 0.9 + 0.05).to(device)
+    def upstream(i):
+        g = torch.Generator().manual_seed(1000 + i)
+        return torch.randn(ts0, ts1, generator=g), torch.randn(ts1, ts0, generator=g)
+    ups = [upstream(i) for i in range(total)]
+    gS = torch.stack([u[0] for u in ups]).to(device)
+    gO = torch.stack([u[1] for u in ups]).to(device)
+    def per_sample_grads(lo, cnt):
+        pts = pattern.unsqueeze(0).repeat(cnt, 1, 1).contiguous()
+        plan = R._SplatPlan(pts, cnt, sigma, ts0, ts1, 4, 5)
+        plan.forward(pts, True, True, True)
+        return plan.backward(pts, gS[lo:lo + cnt].contiguous(), gO[lo:lo + cnt].contiguous(), True)
+    d_own = per_sample_grads(first, n)
+    gathered = None
+    for _ in range(rounds):
+        a = fold_allreduce(d_own, group)
+        b = R.reduce_over_samples(d_own) if n > 1 else d_own[0].clone()
+        allreduce_sum_(b, group)
+        scale = float(b.abs().max())
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-5 * scale), "allreduce: peer-memory exchange differs from fold + NCCL allreduce"
+        if multi:
+            gathered = [torch.empty_like(a) for _ in range(world)]
+            dist.all_gather(gathered, a.contiguous(), group=group)
+            assert all(torch.equal(gathered[0], g) for g in gathered), "allreduce: result is not bit-identical on every rank"
+        check_folders()
+    out["allreduce"] = "ok"
+    d_full = per_sample_grads(0, total).double().sum(0)
+    err = float((a.double() - d_full).norm() / d_full.norm())
+    assert err < 1e-4, f"sharded_gradient: allreduced gradient differs from the full batch by {err:.2e} of its norm"
+    out["sharded_gradient"] = "ok"
+    out["ranks"] = world
+    out["exchange"] = "peer-memory kernel" if any(f is not None for f in _FOLDERS.values()) else ("nccl" if multi else "single rank")
+    return out

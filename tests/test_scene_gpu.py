@@ -182,7 +182,8 @@ def test_batch_orders_parents_across_lists_and_trees(ff):
     c2._parent = stray
     with pytest.raises(ValueError):
         sc.batch()
-    c2._parent = g1                                                   # g1 follows c2 in the existing table
+    c2._parent = p
+    c1._parent = c2                                                   # c2's row follows c1's in the existing table
     with pytest.raises(ValueError):
         sb.refresh()
 
