@@ -13,9 +13,11 @@ the oracle against the reference's own code executed in the build container:
 ``oracle/make_golden.py`` imports ``/root/reference`` (``oracle/ref_loader.py``)
 and writes ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks every
 function here against those fixtures (and against the live reference when it is
-mounted).  Third-party arithmetic that is absent from ``/root/reference``
-(kornia 0.7.1 ``gaussian_blur2d``) is restated from its published algorithm and
-stays "parity unpinned" -- see ``gaussian_blur2d`` below.
+mounted).  Third-party arithmetic that is absent from ``/root/reference`` and not
+installed (kornia 0.7.1 ``gaussian_blur2d``, geomdl 5.3.1 ``NURBS.Curve``) is restated
+from its published algorithm and pinned against independent implementations that ARE
+in the image (OpenCV, scipy): see ``gaussian_blur2d``, ``silhouette`` and the NURBS
+section below.  ``cv2.circle`` is the real OpenCV in the fixtures.
 
 All citations are ``path:line`` relative to ``/root/reference``.
 """
@@ -485,7 +487,8 @@ def clamp_to_fov(rays: torch.Tensor, K: torch.Tensor, clamp_val: float = 0.95) -
 # ----------------------------------------------------------------------------
 def gaussian_kernel1d(ksize: int, sigma: float) -> torch.Tensor:
     """kornia 0.7.1 ``get_gaussian_kernel1d``: ``x = i - k//2`` (+0.5 for even k),
-    ``exp(-x^2 / (2 sigma^2))`` normalised to sum 1.  Third-party, absent here: parity unpinned."""
+    ``exp(-x^2 / (2 sigma^2))`` normalised to sum 1.  kornia itself is not installed; the taps are pinned against
+    ``cv2.getGaussianKernel`` (tests/test_oracle_golden.py::test_blur_restatement_against_opencv_and_scipy)."""
     x = torch.arange(ksize, dtype=F32) - ksize // 2
     if ksize % 2 == 0:
         x = x + 0.5
@@ -497,7 +500,9 @@ def gaussian_blur2d(img: torch.Tensor, kernel_size: Tuple[int, int], sigma: Tupl
     """kornia 0.7.1 ``filters.gaussian_blur2d(x, (ky,kx), (sy,sx))`` with its defaults
     ``border_type='reflect'``, ``separable=True`` -- restated as reflect padding followed by a
     horizontal then a vertical 1-D correlation (postprocessing/gauss_blur.py:18-28 call site).
-    ``img`` is ``[..., H, W]``."""
+    ``img`` is ``[..., H, W]``.  Pinned against two independent implementations that are in the image:
+    ``cv2.GaussianBlur(BORDER_REFLECT_101)`` and ``scipy.ndimage.correlate1d(mode="mirror")``; the residual caveat is
+    only that kornia 0.7.1's defaults are as recalled (reflect border, separable)."""
     ky, kx = int(kernel_size[0]), int(kernel_size[1])
     sy, sx = float(sigma[0]), float(sigma[1])
     lead = img.shape[:-2]
@@ -591,8 +596,9 @@ def noise_texture_lerp(noise: torch.Tensor, color_a: torch.Tensor, color_b: torc
 
 def silhouette(image: torch.Tensor, cx: int, cy: int, r: int) -> torch.Tensor:
     """ApplySilhouette.post_process (postprocessing/apply_silhouette.py:17-40) with the disc drawn analytically
-    (``(x-cx)^2 + (y-cy)^2 <= r^2``; cv2.circle is absent: parity with OpenCV's rasteriser is unpinned), blurred with the
-    restated kornia gaussian_blur2d (11,11)/(5,5) and multiplied into the image."""
+    (``(x-cx)^2 + (y-cy)^2 <= r^2``, which is exactly what the filled ``cv2.circle`` rasterises -- pinned against the reference
+    run with the real OpenCV, tests/golden/postprocess.npz::silhouette_*), blurred with the restated kornia
+    gaussian_blur2d (11,11)/(5,5) and multiplied into the image."""
     H, W = image.shape
     yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
     mask = (((xx - cx) ** 2 + (yy - cy) ** 2) <= r * r).to(F32)
@@ -603,7 +609,9 @@ def silhouette(image: torch.Tensor, cx: int, cy: int, r: int) -> torch.Tensor:
 # NURBS-curve camera path  (fireflies/entity/curve.py:48-96, utils/io.py:77-108)
 # ----------------------------------------------------------------------------
 # The curve arithmetic lives in geomdl==5.3.1 (requirements.txt:16), which is NOT under /root/reference and is not
-# installed: PARITY UNPINNED for the evaluator.  It is restated from the published algorithms geomdl implements
+# installed.  The evaluator is pinned against an independent implementation that is in the image (scipy.interpolate.BSpline on
+# homogeneous control points, tests/test_oracle_golden.py::test_nurbs_evaluator_against_scipy_bspline); what stays unpinned is
+# only geomdl's conventions around it, as recalled.  It is restated from the published algorithms geomdl implements
 # (Piegl & Tiller, "The NURBS Book": knot span search, A2.2 BasisFuns, A4.1 CurvePoint) with geomdl's conventions as
 # recalled from its 5.3.1 sources: knot vectors are normalised to [0, 1] on assignment, the span is found by a linear
 # walk, evaluation is Python floats (fp64), control points without weights get weight 1.  Anchors: Bernstein closed

@@ -298,6 +298,24 @@ def post_cases(ff):
         pp.post_process(img)
         gates.append([0 in calls, 1 in calls])
     out["gates_seed6"] = np.array(gates)
+    # ApplySilhouette (postprocessing/apply_silhouette.py:17-40) run as the reference runs it: its own random.randint draws and the
+    # REAL cv2.circle (OpenCV is installed; only kornia is not, so kornia.filters.gaussian_blur2d is the restated blur).  A frame of
+    # ones makes the result the blurred disc itself, which is what pins the rasterisation of the disc.
+    from oracle import ff_oracle as O
+    sys.modules["kornia.filters"].gaussian_blur2d = lambda x, k, sg: O.gaussian_blur2d(x, k, tuple(float(v) for v in sg))
+    sys.modules["kornia"].filters = sys.modules["kornia.filters"]
+    sil = P.ApplySilhouette()
+    ones = np.ones((512, 448), dtype=np.float32)
+    grad = (np.add.outer(np.arange(512), np.arange(448)) / 960.0).astype(np.float32)
+    discs, outs = [], []
+    for seed, frame in ((4, ones), (5, ones), (6, grad)):
+        random.seed(seed)
+        cx, cy, r = random.randint(100, 200), random.randint(200, 300), random.randint(170, 230)
+        random.seed(seed)
+        outs.append(np.asarray(sil.post_process(frame.copy()), dtype=np.float32))
+        discs.append([cx, cy, r])
+    out.update(silhouette_discs=np.array(discs, dtype=np.int32), silhouette_seeds=np.array([4, 5, 6]), silhouette_out=np.stack(outs),
+               silhouette_grad=grad)
     np.savez_compressed(os.path.join(OUT, "postprocess.npz"), **out)
     print("wrote postprocess")
 

@@ -381,3 +381,56 @@ def test_nurbs_curve_object_host_logic(tmp_path):
         curve.evaluate_single(1.5)                           # outside the domain, like geomdl
     with pytest.raises(RuntimeError):
         curve.evaluate_single(0.5)                           # no CPU path
+
+
+# ---- third-party arithmetic pinned against independent implementations that ARE in the image -----------------
+def test_silhouette_oracle_equals_reference_with_real_opencv(golden):
+    """The reference's ApplySilhouette.post_process (apply_silhouette.py:17-40) executed with the real cv2.circle and its own
+    random.randint draws (oracle/make_golden.py::post_cases; only kornia's blur is restated) against the oracle's analytic disc."""
+    g = golden("postprocess")
+    ones = np.ones((512, 448), dtype=np.float32)
+    for i, (cx, cy, r) in enumerate(g["silhouette_discs"].tolist()):
+        frame = g["silhouette_grad"] if i == 2 else ones
+        close(O.silhouette(torch.from_numpy(frame), cx, cy, r), g["silhouette_out"][i], rtol=1e-6, atol=1e-7)
+    # the filled cv2.circle itself is the analytic disc (x - cx)^2 + (y - cy)^2 <= r^2, also where it leaves the frame
+    cv2 = pytest.importorskip("cv2")
+    for cx, cy, r in [(150, 250, 200), (100, 300, 170), (380, 20, 60), (0, 0, 5), (447, 511, 33), (200, 200, 1), (37, 41, 0)]:
+        m = cv2.circle(np.zeros((512, 448), np.float32), (cx, cy), r, color=1, thickness=-1)
+        yy, xx = np.mgrid[0:512, 0:448]
+        assert np.array_equal(m, (((xx - cx) ** 2 + (yy - cy) ** 2) <= r * r).astype(np.float32)), (cx, cy, r)
+
+
+def test_blur_restatement_against_opencv_and_scipy():
+    """oracle.gaussian_blur2d (kornia 0.7.1 restated: reflect border without edge repeat, separable, taps exp(-x^2 / 2 sigma^2) / sum)
+    against cv2.GaussianBlur(BORDER_REFLECT_101) and scipy.ndimage.correlate1d(mode="mirror") for the three (kernel, sigma) pairs the
+    reference uses (gauss_blur.py:18-28 callers: (3,3)/(5,5), main.py:69 (5,5)/(3,3), apply_silhouette.py:31 (11,11)/(5,5))."""
+    cv2 = pytest.importorskip("cv2")
+    ndi = pytest.importorskip("scipy.ndimage")
+    img = np.random.default_rng(12).random((61, 47), dtype=np.float32)
+    for (ky, kx), (sy, sx) in (((3, 3), (5.0, 5.0)), ((5, 5), (3.0, 3.0)), ((11, 11), (5.0, 5.0)), ((5, 3), (2.0, 1.0))):
+        ours = O.gaussian_blur2d(torch.from_numpy(img), (ky, kx), (sy, sx)).numpy()
+        for k, sg in ((ky, sy), (kx, sx)):          # taps: cv2.getGaussianKernel is the same normalised Gaussian
+            close(O.gaussian_kernel1d(k, sg), cv2.getGaussianKernel(k, sg, cv2.CV_32F)[:, 0], rtol=1e-6, atol=1e-8)
+        ocv = cv2.GaussianBlur(img, (kx, ky), sigmaX=sx, sigmaY=sy, borderType=cv2.BORDER_REFLECT_101)
+        close(ours, ocv, rtol=1e-5, atol=1e-6)
+        wy, wx = O.gaussian_kernel1d(ky, sy).double().numpy(), O.gaussian_kernel1d(kx, sx).double().numpy()
+        sp = ndi.correlate1d(ndi.correlate1d(img.astype(np.float64), wx, axis=1, mode="mirror"), wy, axis=0, mode="mirror")
+        close(ours, sp, rtol=1e-5, atol=1e-6)
+
+
+def test_nurbs_evaluator_against_scipy_bspline():
+    """oracle.nurbs_curve_point (geomdl 5.3.1 restated, entity/curve.py:52-53,74 call sites) against scipy.interpolate.BSpline on
+    homogeneous control points: non-uniform knots, non-unit weights, degrees 2-4, parameters across every span."""
+    BSpline = pytest.importorskip("scipy.interpolate").BSpline
+    rng = np.random.default_rng(5)
+    for degree, n in ((2, 5), (3, 7), (3, 12), (4, 9)):
+        ctrl = rng.normal(size=(n, 3))
+        w = rng.uniform(0.5, 2.0, size=n)
+        inner = np.sort(rng.uniform(0.0, 1.0, size=n - degree - 1))
+        knots = np.concatenate([np.zeros(degree + 1), inner, np.ones(degree + 1)])
+        kn = O.nurbs_normalize_knots(knots.tolist())
+        hom = np.concatenate([ctrl * w[:, None], w[:, None]], axis=1)
+        spl = BSpline(np.asarray(kn), hom, degree)
+        for t in np.concatenate([np.linspace(0.0, 1.0, 41)[:-1], inner, [0.999999]]):
+            h = spl(float(t))
+            close(O.nurbs_curve_point(ctrl.tolist(), kn, degree, float(t), w.tolist()), h[:3] / h[3], rtol=1e-12, atol=1e-13)

@@ -111,3 +111,12 @@ def test_silhouette_batch(golden):
     random.seed(4)
     res = ApplySilhouette().post_process(frames[0].numpy())
     close(torch.from_numpy(res), O.silhouette(frames[0], cx, cy, r))
+    # against the reference itself, run with the real cv2.circle under the same seeds (oracle/make_golden.py::post_cases)
+    g = golden("postprocess")
+    ones = np.ones((512, 448), dtype=np.float32)
+    for i, seed in enumerate(g["silhouette_seeds"].tolist()):
+        frame = g["silhouette_grad"] if i == 2 else ones
+        random.seed(seed)
+        close(torch.from_numpy(ApplySilhouette().post_process(frame.copy())), g["silhouette_out"][i], rtol=1e-5, atol=1e-6)
+    out2 = run_silhouette(torch.from_numpy(np.stack([ones, ones, g["silhouette_grad"]])).cuda(), torch.from_numpy(g["silhouette_discs"]).cuda())
+    close(out2, g["silhouette_out"], rtol=1e-5, atol=1e-6)
