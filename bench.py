@@ -326,7 +326,7 @@ def main_ours(args):
 
     # ---- N > 1: correctness of the exchange, of the sample split and of the sharded gradient, before anything is timed ----
     mg_check = None
-    if world > 1:
+    if world > 1 and os.environ.get("FFB_BENCH_SKIP_SELFCHECK") != "1":
         try:
             mg_check = par.multi_gpu_selfcheck(device)
         except AssertionError as exc:

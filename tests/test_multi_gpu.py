@@ -24,6 +24,16 @@ def _worker(rank, world, port, symm):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
+        _checks(rank, world, dev, symm)
+    except BaseException:  # noqa: BLE001  (a failing rank must not wait for its peers in destroy_process_group: leave at once)
+        import traceback
+        traceback.print_exc()
+        os._exit(1)
+    dist.destroy_process_group()
+
+
+def _checks(rank, world, dev, symm):
+    if True:
         from fireflies_b200.parallel import multi_gpu_selfcheck
         res = multi_gpu_selfcheck(dev)
         assert res["allreduce"] == res["rng_split_invariant"] == res["sharded_gradient"] == "ok" and res["ranks"] == world
@@ -37,8 +47,6 @@ def _worker(rank, world, port, symm):
             assert torch.equal(y, torch.full((64, 2), 4.5, device=dev))
         check_folders()
         torch.cuda.synchronize()
-    finally:
-        dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("symm", ["1", "0"])
