@@ -267,12 +267,15 @@ __device__ __forceinline__ int origin_axis(float P, int baked, int half) {
 // One CTA per binned pattern instance.  FAST: 64x16 super tiles, 32-byte entries; otherwise 64x32 CTA tiles,
 // index lists.  The tile grid is processed in bands of whole tile rows so that the
 // counters fit in shared memory for any texture size.
-template <bool FAST>
+// SREC (FAST only): the point records live in shared memory instead of the workspace -- only this kernel reads them in the fast
+// path (a list entry is a copy of its record), and the random 32-byte record reads of the emit phase were the kernel's
+// long-scoreboard stalls (profiles/r01n: issue 41 %, long scoreboard 51 % of the stall samples)
+template <bool FAST, bool SREC = false>
 #ifndef FFB_PREP_MINB
 #define FFB_PREP_MINB 1
 #endif
 __global__ void __launch_bounds__(PREP_CTA, FFB_PREP_MINB) prepare_kernel(PrepParams q) {
-    extern __shared__ int sm[];
+    extern __shared__ __align__(16) int sm[];
     const int band_tiles = q.band_rows * q.tgx;
     int* cnt = sm;                 // [band_tiles] counts, then exclusive offsets
     int* cur = sm + band_tiles;    // [band_tiles] fill cursors
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(PREP_CTA, FFB_PREP_MINB) prepare_kernel(PrepPa
     __shared__ int band_base;
     const int bin = blockIdx.x, tid = threadIdx.x;
     const float* pts = q.pts + (long long)bin * q.stride;
-    PointRec* recs = q.recs + (size_t)bin * q.N;
+    PointRec* recs = SREC ? reinterpret_cast<PointRec*>(sm + ((2 * band_tiles + 3) & ~3)) : q.recs + (size_t)bin * q.N;
     int* tile_off = q.tile_off + (size_t)bin * (q.T + 1);
     int* list = q.list + (size_t)bin * q.cap;          // FAST: unsorted scratch; otherwise the final index lists
     Entry* entries = q.entries + (FAST ? (size_t)bin * q.cap : 0);
@@ -442,6 +445,7 @@ struct RasterParams {
     const float* g_sum; const float* g_softor;    // backward
     float* d_pts;
     int eager;                // backward: request a super tile's first upstream boxes before its candidate list is known (dense patterns)
+    int log_tgx, log_T;       // log2 of tgx and T when both are powers of two (item decode of the persistent backward by shifts), else -1
     float* loss;              // fused L1 backward: per-sample mean |softor - sum| (accumulated)
     float loss_inv;           // 1 / (ts0 * ts1)
 };
@@ -792,7 +796,10 @@ static int launch_bwd_st(KP persistent, K oneshot, KO overflow, const RasterPara
             FFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, persistent, 32, smem));
             if (occ < 1) occ = 1;
         }
-        long long grid = (long long)kNumSMs * occ;
+        // 20 resident warps per SM, not the 24 that fit: inside the full step on a board at its power cap 148 x 20 measured
+        // 4.11 ms per step against 4.32 (x 24, with 4.9 ms outliers when the power controller overshoots), 4.32 (x 16), 4.15 for
+        // the one-shot form and 4.41 for round 1's kernel (scripts/bench_ab.py, 5 alternating rounds of 10 steps on one box)
+        long long grid = (long long)kNumSMs * (occ < 20 ? occ : 20);
         if (const char* g = getenv("FFB_SPLAT_BWD_GRID")) grid = atoll(g) > 0 ? atoll(g) : grid;
         if (grid > items) grid = items;
         persistent<<<(unsigned)grid, 32, smem, st>>>(q, fc, m.gs, m.go, m.sv, m.ot, (int)items, counter);
@@ -836,6 +843,9 @@ static void fill_raster(const ffb_splat_desc* d, const Plan& p, const void* ws, 
         const double per_tile = (double)d->N * (wwin + 4 * WT - 1) * (wwin + WT - 1) / ((double)d->ts0 * (double)d->ts1);
         const char* e = getenv("FFB_SPLAT_EAGER");
         q.eager = e ? (e[0] == '1') : (per_tile >= 2.0);
+        auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
+        q.log_tgx = lg(p.tgx); q.log_T = lg(p.T);
+        if (q.log_tgx < 0 || q.log_T < 0) q.log_tgx = q.log_T = -1;
     }
 }
 
@@ -1096,6 +1106,14 @@ extern "C" int ffb_splat_prepare(const ffb_splat_desc* d, const float* pts, void
     const size_t smem = (size_t)p.band_rows * p.tgx * 2 * sizeof(int);
     if (p.fast) {
         FFB_CUDA(cudaMemsetAsync(q.ovf, 0, sizeof(int), as_stream(stream)));
+        const size_t smem_rec = (((size_t)p.band_rows * p.tgx * 2 + 3) & ~(size_t)3) * sizeof(int) + (size_t)d->N * sizeof(PointRec);
+        const char* e = getenv("FFB_PREP_SREC");
+        if (smem_rec <= 200 * 1024 && !(e && e[0] == '0')) {        // records in shared memory
+            FFB_CUDA(cudaFuncSetAttribute(prepare_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rec));
+            prepare_kernel<true, true><<<p.Bp, PREP_CTA, smem_rec, as_stream(stream)>>>(q);
+            FFB_CUDA(cudaGetLastError());
+            return 0;
+        }
         if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         prepare_kernel<true><<<p.Bp, PREP_CTA, smem, as_stream(stream)>>>(q);
     } else {

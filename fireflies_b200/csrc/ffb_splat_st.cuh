@@ -30,7 +30,7 @@
 #pragma once
 
 #ifndef FFB_ST_MINB
-#define FFB_ST_MINB 24                    // resident one-warp CTAs per SM: 8.4 KB of shared memory + 1 KB reserved per CTA, 80 registers
+#define FFB_ST_MINB 22                    // register target of the allocation (80 registers: up to 24 one-warp CTAs per SM fit, 8.5 KB of shared memory + 1 KB reserved each); measured 0.526 / 0.542 / 0.823 ms per 64 samples at 22 / 20 / 24
 #endif
 #ifndef FFB_ST_PAIR
 #define FFB_ST_PAIR 1                     // two-candidate tiles: exclusive products are the other candidate's factor (no pass 1, no reciprocal)
@@ -38,6 +38,9 @@
 #ifndef FFB_ST_EXACT
 #define FFB_ST_EXACT 0                    // 1: distances as exact differences scaled afterwards (three more packed multiplies per visit); 0: differences of
 #endif                                    // pre-scaled tile-relative coordinates (operands rounded to ~3e-7 before the subtraction)
+#ifndef FFB_ST_TRIPLE
+#define FFB_ST_TRIPLE 1                   // three-candidate tiles: all exponentials in registers, exclusive products are the other two factors
+#endif
 #ifndef FFB_ST_DYN
 #define FFB_ST_DYN 1                      // persistent kernel: items claimed from a global counter (1) or walked with a fixed stride (0)
 #endif
@@ -308,6 +311,43 @@ __device__ __forceinline__ void st_weigh_pair(unsigned rec, StPend& pd, float& a
     st_weigh_one_of_pair<SUM, MSK>(rc1, pd, accr, k1, tc, ln, lane, fc, gs, go, g1, g0);
 }
 
+// three-candidate tile (the most frequent kind: 22 % of the tiles at config 3): the three sets of exponentials stay in registers, a
+// candidate's exclusive product is the other two factors -- no pass 1, no reciprocal, 24 instead of ~50 special-function ops
+template <bool SUM, bool MSK>
+__device__ __forceinline__ void st_weigh_one_of_triple(const float4 rc, StPend& pd, float& accr, int k, const StTileCols& tc, const StLane& ln,
+                                                       int lane, const WtConsts& fc, const float2 (&gs)[4], const float2 (&go)[4],
+                                                       const float2 (&gn)[4], const float2 (&ga)[4], const float2 (&gb)[4]) {
+    st_reduce(pd, accr, lane);
+    const StRow r = st_row<SUM && MSK>(rc, ln, fc);
+    const StCol c = st_col<SUM && MSK>(rc, tc, fc);
+    float2 a0 = bc(0.f), a1 = bc(0.f);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const float2 d2 = st_d2(r, c, v);
+        const float2 e1 = __ffma2_rn(neg2(ga[v]), go[v], go[v]);                      // gO * (1 - g_a)
+        float2 x = __ffma2_rn(neg2(gb[v]), e1, (SUM && !MSK) ? __fadd2_rn(e1, gs[v]) : e1);   // gO * (1 - g_a)(1 - g_b) [+ gS]
+        const bool pr = v < 2 ? r.pa : r.pb;
+        if (SUM && MSK) { if (pr) x = __ffma2_rn(gs[v], c.mc[v & 1], x); }
+        const float2 wgt = __fmul2_rn(__fmul2_rn(x, gn[v]), d2);
+        a0 = __ffma2_rn(wgt, c.dxs[v & 1], a0);
+        a1 = __ffma2_rn(wgt, bc(v < 2 ? r.dys.x : r.dys.y), a1);
+    }
+    st_park(pd, k, a0, a1);
+}
+template <bool SUM, bool MSK>
+__device__ __forceinline__ void st_weigh_triple(unsigned rec, StPend& pd, float& accr, unsigned tm, const StTileCols& tc, const StLane& ln,
+                                                int lane, const WtConsts& fc, const float2 (&gs)[4], const float2 (&go)[4]) {
+    const int k0 = st_next(tm), k1 = st_next(tm), k2 = st_next(tm);
+    const float4 rc0 = st_lds128(rec + 16u * (unsigned)k0), rc1 = st_lds128(rec + 16u * (unsigned)k1), rc2 = st_lds128(rec + 16u * (unsigned)k2);
+    float2 g0[4], g1[4], g2[4];
+    st_g(rc0, tc, ln, fc, g0);
+    st_g(rc1, tc, ln, fc, g1);
+    st_g(rc2, tc, ln, fc, g2);
+    st_weigh_one_of_triple<SUM, MSK>(rc0, pd, accr, k0, tc, ln, lane, fc, gs, go, g0, g1, g2);
+    st_weigh_one_of_triple<SUM, MSK>(rc1, pd, accr, k1, tc, ln, lane, fc, gs, go, g1, g0, g2);
+    st_weigh_one_of_triple<SUM, MSK>(rc2, pd, accr, k2, tc, ln, lane, fc, gs, go, g2, g0, g1);
+}
+
 // ---- staging: one candidate per lane -> tile masks (ballots) and 16-byte records {(P0 - c0) r1, (P1 - r0) r1, (P0 - f0) r1, (P1 - f1) r1} ----
 __device__ __forceinline__ WtMasks st_stage(const RasterParams& q, const WtConsts& fc, bool grad, int bin, int beg, int n, int c0, int r0, int lane,
                                             float4* rec, int* idx) {
@@ -439,8 +479,13 @@ __device__ __forceinline__ void st_tile(unsigned sbase, int j, unsigned tm, unsi
         st_weigh<SUM, SOFTOR, MSK, 2>(rec, pd, accr, tm, tc, ln, lane, fc, gs, gp);
         return;
     }
-    if (FFB_ST_PAIR && MODE == ST_REBUILD && __popc(tm) == 2) {
+    const int cands = __popc(tm);
+    if (FFB_ST_PAIR && MODE == ST_REBUILD && cands == 2) {
         st_weigh_pair<SUM, MSK>(rec, pd, accr, tm, tc, ln, lane, fc, gs, gp);
+        return;
+    }
+    if (FFB_ST_TRIPLE && MODE == ST_REBUILD && cands == 3) {
+        st_weigh_triple<SUM, MSK>(rec, pd, accr, tm, tc, ln, lane, fc, gs, gp);
         return;
     }
     unsigned rest = tm;
@@ -504,11 +549,13 @@ __device__ __forceinline__ void st_issue_half(unsigned char* st_smem, uint64_t* 
 }
 
 // the item's d/dP: lane (k, h) holds candidate k's component h
-__device__ __forceinline__ void st_flush(const RasterParams& q, const WtConsts& fc, const StPend& pd, float accr, int lane, int n, int b, const int* idx) {
+__device__ __forceinline__ float st_scale(const RasterParams& q, const WtConsts& fc, int lane) {
+    return 4.f * ((lane >> 4) ? (float)q.ts1 : (float)q.ts0) * q.rcp_sigma * q.rcp_sigma * fc.rs3;
+}
+__device__ __forceinline__ void st_flush(const RasterParams& q, float kh, const StPend& pd, float accr, int lane, int n, int b, const int* idx) {
     st_reduce(pd, accr, lane);                              // the last visit's sums
     const int lc = lane & 15, h = lane >> 4;
     if (lc < n) {
-        const float kh = 4.f * (h ? (float)q.ts1 : (float)q.ts0) * q.rcp_sigma * q.rcp_sigma * fc.rs3;
         const float val = accr * kh;
         if (val != 0.f) atomicAdd(q.d_pts + ((size_t)b * q.N + idx[lc]) * 2 + h, val);
     }
@@ -586,7 +633,7 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_st(RasterParams q, 
         if (!LOSS && tm == 0u) continue;
         st_tile<SUM, SOFTOR, SUM_T, MSK, MODE>(sbase, j, tm, near_mask(mk, j), sbase + L::off_rec, pd, accr, lacc, ln, lane, fc, inv_bits, sgn);
     }
-    if (grad) st_flush(q, fc, pd, accr, lane, n, b, idx);
+    if (grad) st_flush(q, st_scale(q, fc, lane), pd, accr, lane, n, b, idx);
     if (LOSS) {
         lacc = warp_sum(lacc);
         if (lane == 0) atomicAdd(q.loss + b, lacc * q.loss_inv);
@@ -605,6 +652,13 @@ struct StItem {
 };
 __device__ __forceinline__ StItem st_decode(const RasterParams& q, int it, float inv_T, float inv_tgx) {
     StItem s;
+    if (q.log_T >= 0) {                                      // power-of-two tile grids (2048^2: 32 x 128 super tiles): shifts
+        s.b = it >> q.log_T;
+        const int rem = it & (q.T - 1);
+        s.sty = rem >> q.log_tgx;
+        s.bx = rem & (q.tgx - 1);
+        return s;
+    }
     s.b = __float2int_rz(__int2float_rn(it) * inv_T);
     int rem = it - s.b * q.T;
     if (rem < 0) { --s.b; rem += q.T; } else if (rem >= q.T) { ++s.b; rem -= q.T; }
@@ -657,6 +711,7 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_stp(RasterParams q,
     const StLane ln = st_lane(lane, fc);
     const unsigned inv_bits = __float_as_uint(q.loss_inv);
     const unsigned sbase = tma::smem_u32(st_smem);
+    const float kh = st_scale(q, fc, lane);
     unsigned phase = 0;
 #pragma unroll 1
     for (;;) {
@@ -708,7 +763,7 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_stp(RasterParams q,
         }
         __syncwarp();
         if (more) st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar + 1, 1, nx.bx * (4 * WT), nx.sty * WT, nx.b, &tm_gs, &tm_go, &tm_sv, &tm_ot, TWO);
-        if (grad) st_flush(q, fc, pd, accr, lane, n, cur.b, idx);
+        if (grad) st_flush(q, kh, pd, accr, lane, n, cur.b, idx);
         if (LOSS) {
             lacc = warp_sum(lacc);
             if (lane == 0) atomicAdd(q.loss + cur.b, lacc * q.loss_inv);
