@@ -1318,12 +1318,12 @@ extern "C" int ffb_splat_bwd_l1(const ffb_splat_desc* d, const float* pts, const
     const OvfParams ov = {q.ovf, q.ovf + 1, B};
     const size_t stage = sizeof(WarpStage<1, true, false, 1>);
     {
-        // the super-tile kernel in its loss mode (whole 64x16 blocks of the forward's outputs, two request rounds per item).  Measured
-        // 0.702 ms per 64 samples against 0.698 ms for splat_bwd_tma<LOSS> (profiles/r02i): not yet ahead, so it is opt-in
-        // (FFB_SPLAT_L1_ST=1) and the parity tests run both.
+        // production path: the super-tile kernel in its loss mode (whole 64x16 blocks of the forward's outputs, two request rounds per
+        // item: mirrored index -> signs in shared memory, then own index).  Measured 0.676 ms per 64 samples against 0.695 ms for
+        // splat_bwd_tma<LOSS> (profiles/r02q; 2000 against 2630 warp instructions per item); FFB_SPLAT_L1_ST=0 selects the latter.
         const char* e2 = getenv("FFB_SPLAT_L1_ST");
         BwdMaps n;
-        bool ok2 = e2 && e2[0] == '1';
+        bool ok2 = !(e2 && e2[0] == '0');
         if (ok2) ok2 = tma::encode_f32_3d(&n.go, out_softor, t0, t1, (uint64_t)B, 2 * WT, WT, CU_TENSOR_MAP_SWIZZLE_128B);
         if (ok2) ok2 = sum_transposed ? tma::encode_f32_3d(&n.gs, out_sum, t1, t0, (uint64_t)B, 2 * WT, WT, CU_TENSOR_MAP_SWIZZLE_128B)
                                       : tma::encode_f32_3d(&n.gs, out_sum, t0, t1, (uint64_t)B, 2 * WT, WT, CU_TENSOR_MAP_SWIZZLE_128B);

@@ -60,7 +60,10 @@ struct StSmem {
     static constexpr int off_bar = n_box * ST_BOX;
     static constexpr int off_rec = off_bar + 16;
     static constexpr int off_idx = off_rec + WCH * 16;
-    static constexpr int bytes = off_idx + WCH * 4;
+    // LOSS + SUM_T: signs of (softor - sum) at the mirrored index as bf16 (-1, 0, +1), [column 64][row 16] with a 40-byte pitch
+    static constexpr int off_sgn = off_idx + WCH * 4;
+    static constexpr int sgn_pitch = 40;
+    static constexpr int bytes = off_sgn + ((MODE == ST_LOSS && SUM_T) ? 4 * WT * sgn_pitch : 0);
 };
 
 // Everything is measured in units of 1 / r1 (r1 = sqrt(s2)) relative to the super tile's first texel, so that d2s = dxs^2 + dys^2 feeds
@@ -381,33 +384,43 @@ __device__ __forceinline__ WtMasks st_stage(const RasterParams& q, const WtConst
     return mk;
 }
 
-// LOSS + SUM_T, first request round: the boxes hold the forward's outputs at the mirrored index ({16,32} boxes, transposed reads).  Per
-// texel of the lane: bit 0 = (softor != sum), bit 1 = (softor > sum), i.e. the sign bit of d loss / d sum = -sign(softor - sum) / numel;
-// 16 bits per tile, 64 per super tile.
+// LOSS + SUM_T, first request round: the boxes hold the forward's outputs at the mirrored index ({16,32} boxes: [column 64][row 16]).
+// sign(softor - sum) of all 1024 texels goes to shared memory as bf16 (-1, 0, +1): lane L takes columns L and L + 32 -- four
+// conflict-free LDS.128 per array and column (the 64-byte swizzle spreads the eight lanes of a phase over all banks), packed
+// subtractions, and one 8-byte store per four rows.  The consumer mapping (rows q, q + 8; columns 4 cg ..) reads them back with
+// conflict-free 16-bit loads.  (A first version kept two bits per texel in registers: 64 scalar loads and ~350 instructions per item.)
+__device__ __forceinline__ unsigned st_sign_bf16x2(float a, float b) {
+    // (sign(b) as bf16) << 16 | (sign(a) as bf16): bf16(+-1) = 0x3f80 / 0xbf80, 0 for a zero difference
+    const unsigned ua = __float_as_uint(a), ub = __float_as_uint(b);
+    const unsigned sa = (a != 0.f) ? ((ua >> 16) & 0x8000u) | 0x3f80u : 0u;
+    const unsigned sb_ = (b != 0.f) ? ((ub >> 16) & 0x8000u) | 0x3f80u : 0u;
+    return sa | (sb_ << 16);
+}
 template <typename L>
-__device__ __forceinline__ unsigned long long st_loss_signs(unsigned sbase, const StLane& ln) {
-    unsigned long long sgn = 0ull;
+__device__ __forceinline__ void st_loss_signs(unsigned sbase, int lane) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const unsigned t = sbase + j * 1024;
-        const unsigned a0 = t + ln.tA0, a2 = t + (ln.tA0 ^ 16u) + 128u, b0 = t + (ln.tA0 ^ 32u), b2 = t + (ln.tA0 ^ 48u) + 128u;
-        const unsigned ad[8] = {a0, a0 + 64, a2, a2 + 64, b0, b0 + 64, b2, b2 + 64};
-        unsigned w = 0u;
+    for (int half = 0; half < 2; ++half) {
+        const int c = lane + 32 * half;
+        const unsigned row = sbase + (unsigned)c * 64u, sw = (unsigned)((c >> 1) & 3);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float d = st_lds32(ad[e] + L::off_go) - st_lds32(ad[e] + L::off_gs);
-            w |= (d != 0.f ? 1u : 0u) << (2 * e);
-            w |= (d > 0.f ? 2u : 0u) << (2 * e);
+        for (int ch = 0; ch < 4; ++ch) {
+            const unsigned a = row + (((unsigned)ch ^ sw) << 4);
+            const float4 o = st_lds128(a + L::off_go), m = st_lds128(a + L::off_gs);
+            const unsigned w0 = st_sign_bf16x2(o.x - m.x, o.y - m.y), w1 = st_sign_bf16x2(o.z - m.z, o.w - m.w);
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + L::off_sgn + (unsigned)c * L::sgn_pitch + (unsigned)ch * 8u), "r"(w0), "r"(w1) : "memory");
         }
-        sgn |= (unsigned long long)w << (16 * j);
     }
-    return sgn;
+}
+__device__ __forceinline__ float st_lds_bf16(unsigned a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return __uint_as_float((unsigned)v << 16);
 }
 
 // one 16x16 tile of the resident super tile: upstream values of the lane's 8 texels from shared memory, then the tile's candidates
 template <bool SUM, bool SOFTOR, bool SUM_T, bool MSK, int MODE>
 __device__ __forceinline__ void st_tile(unsigned sbase, int j, unsigned tm, unsigned nm, unsigned rec, StPend& pd, float& accr,
-                                        float& lacc, const StLane& ln, int lane, const WtConsts& fc, unsigned inv_bits, unsigned long long sgn) {
+                                        float& lacc, const StLane& ln, int lane, const WtConsts& fc) {
     typedef StSmem<SUM, SOFTOR, SUM_T, MODE> L;
     constexpr bool LOSS = MODE == ST_LOSS;
     constexpr bool SAVED = MODE == ST_SAVED && SOFTOR;
@@ -428,6 +441,7 @@ __device__ __forceinline__ void st_tile(unsigned sbase, int j, unsigned tm, unsi
     };
     const bool one = (tm & (tm - 1u)) == 0u;               // at most one candidate on this tile (warp-uniform)
     if (LOSS) {
+        // unit signs here; the 1 / numel of the mean is folded into the final scale of d/dP and of the loss
         float2 o[4], s[4];
         ld_nat(L::off_go, o);
         ld_nat(L::off_gs, s);
@@ -435,21 +449,20 @@ __device__ __forceinline__ void st_tile(unsigned sbase, int j, unsigned tm, unsi
         for (int v = 0; v < 4; ++v) {
             const float dx_ = o[v].x - s[v].x, dy_ = o[v].y - s[v].y;
             lacc += fabsf(dx_) + fabsf(dy_);
-            const float2 sg = make_float2(sign_times(dx_, inv_bits), sign_times(dy_, inv_bits));
+            const float2 sg = make_float2(sign_times(dx_, 0x3f800000u), sign_times(dy_, 0x3f800000u));
             gp[v] = __fmul2_rn(sg, make_float2(1.f - o[v].x, 1.f - o[v].y));
             gs[v] = neg2(sg);
         }
+        if (tm == 0u) return;
         if (SUM_T) {
-            // d loss / d sum at this texel = -sign(softor - sum) / numel at the mirrored texel: two bits per texel (st_loss_signs)
-            const unsigned w = (unsigned)(sgn >> (16 * j)) & 0xffffu;
+            // d loss / d sum at this texel = -sign(softor - sum) at the mirrored texel (st_loss_signs)
+            const unsigned t = sbase + L::off_sgn + (unsigned)(WT * j + 4 * (lane >> 3)) * L::sgn_pitch + 2u * (unsigned)(lane & 7);
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-                const unsigned bx_ = w >> (4 * v);
-                gs[v] = make_float2(__uint_as_float((bx_ & 1u) ? (inv_bits | ((bx_ & 2u) << 30)) : 0u),
-                                    __uint_as_float((bx_ & 4u) ? (inv_bits | ((bx_ & 8u) << 28)) : 0u));
+                const unsigned a = t + (unsigned)(2 * (v & 1)) * L::sgn_pitch + (v >> 1) * 16u;
+                gs[v] = make_float2(-st_lds_bf16(a), -st_lds_bf16(a + L::sgn_pitch));
             }
         }
-        if (tm == 0u) return;
     } else {
         if (SUM) { if (SUM_T) ld_tr(L::off_gs, gs); else ld_nat(L::off_gs, gs); }
         if (SOFTOR) {
@@ -611,19 +624,17 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_st(RasterParams q, 
     if (!eager) issue(false);
     const StLane ln = st_lane(lane, fc);
     const unsigned sbase = tma::smem_u32(st_smem);
-    unsigned long long sgn = 0ull;
     if (TWO) {
         tma::mbar_wait(bar, 0);
         tma::mbar_wait(bar + 1, 0);
-        sgn = st_loss_signs<L>(sbase, ln);
-        __syncwarp();                                       // every lane has its bits: the boxes may be overwritten
+        st_loss_signs<L>(sbase, lane);
+        __syncwarp();                                       // the signs are in shared memory: the boxes may be overwritten
         issue(false);
     }
     const WtMasks mk = st_stage(q, fc, grad, bin, beg, n, c0, r0, lane, rec, idx);
     StPend pd = {0.f, 0.f, 0};
     float accr = 0.f;                                       // lane (k, h): d/dp_h of candidate k, summed over the super tile
     float lacc = 0.f;                                       // LOSS: this lane's share of sum |softor - sum|
-    const unsigned inv_bits = __float_as_uint(q.loss_inv);
     __syncwarp();
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
@@ -631,9 +642,9 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_st(RasterParams q, 
         if (j == 2) tma::mbar_wait(bar + 1, TWO ? 1u : 0u);
         const unsigned tm = grad ? tile_mask(mk, j) : 0u;
         if (!LOSS && tm == 0u) continue;
-        st_tile<SUM, SOFTOR, SUM_T, MSK, MODE>(sbase, j, tm, near_mask(mk, j), sbase + L::off_rec, pd, accr, lacc, ln, lane, fc, inv_bits, sgn);
+        st_tile<SUM, SOFTOR, SUM_T, MSK, MODE>(sbase, j, tm, near_mask(mk, j), sbase + L::off_rec, pd, accr, lacc, ln, lane, fc);
     }
-    if (grad) st_flush(q, st_scale(q, fc, lane), pd, accr, lane, n, b, idx);
+    if (grad) st_flush(q, st_scale(q, fc, lane) * (LOSS ? q.loss_inv : 1.f), pd, accr, lane, n, b, idx);
     if (LOSS) {
         lacc = warp_sum(lacc);
         if (lane == 0) atomicAdd(q.loss + b, lacc * q.loss_inv);
@@ -709,9 +720,8 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_stp(RasterParams q,
         beg = __ldg(t); end = __ldg(t + 1);
     }
     const StLane ln = st_lane(lane, fc);
-    const unsigned inv_bits = __float_as_uint(q.loss_inv);
     const unsigned sbase = tma::smem_u32(st_smem);
-    const float kh = st_scale(q, fc, lane);
+    const float kh = st_scale(q, fc, lane) * (LOSS ? q.loss_inv : 1.f);
     unsigned phase = 0;
 #pragma unroll 1
     for (;;) {
@@ -726,14 +736,13 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_stp(RasterParams q,
         const unsigned asked = more ? claim_ask() : 0u;     // the item after the next
         const int n = end - beg, c0 = cur.bx * (4 * WT), r0 = cur.sty * WT;
         const bool grad = n > 0 && n <= WCH;               // empty: no gradient work; longer lists: overflow kernel
-        unsigned long long sgn = 0ull;
         if (TWO) {
             // round 1 (requested during the previous item): outputs at the mirrored index -> two sign bits per texel; then round 2, the
             // outputs at the item's own index, lands while the candidates are staged.  Each barrier completes twice per item, so
             // the mirrored round always waits on parity 0 and the own round on parity 1.
             tma::mbar_wait(bar, 0);
             tma::mbar_wait(bar + 1, 0);
-            sgn = st_loss_signs<L>(sbase, ln);
+            st_loss_signs<L>(sbase, lane);
             __syncwarp();
             st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar, 0, c0, r0, cur.b, &tm_gs, &tm_go, &tm_sv, &tm_ot);
             st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar + 1, 1, c0, r0, cur.b, &tm_gs, &tm_go, &tm_sv, &tm_ot);
@@ -759,7 +768,7 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_stp(RasterParams q,
             }
             const unsigned tm = tile_mask(mk, j);
             if (!LOSS && tm == 0u) continue;
-            st_tile<SUM, SOFTOR, SUM_T, MSK, MODE>(sbase, j, tm, near_mask(mk, j), sbase + L::off_rec, pd, accr, lacc, ln, lane, fc, inv_bits, sgn);
+            st_tile<SUM, SOFTOR, SUM_T, MSK, MODE>(sbase, j, tm, near_mask(mk, j), sbase + L::off_rec, pd, accr, lacc, ln, lane, fc);
         }
         __syncwarp();
         if (more) st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar + 1, 1, nx.bx * (4 * WT), nx.sty * WT, nx.b, &tm_gs, &tm_go, &tm_sv, &tm_ot, TWO);

@@ -50,11 +50,11 @@ for name, fn in [("nat sum+softor", lambda: plan.backward(ptsB, gSn, gO, False))
     env(FFB_SPLAT_BWD_ST="0"); to = t(fn); do = fn()
     env(FFB_SPLAT_BWD_ST=None)
     print(f"bwd {name:15s}: st {tn:.3f} ms, old {to:.3f} ms; rel diff {float((dn - do).norm() / do.norm()):.3e}")
-for nm_, st_ in (("st", "1"), ("old", None)):
+for nm_, st_ in (("st", None), ("old", "0")):
     env(FFB_SPLAT_L1_ST=st_)
     tl = t(lambda: plan.backward_l1(ptsB, S_, O_, True))
     ll, dl = plan.backward_l1(ptsB, S_, O_, True)
-    if st_ == "1": l_new, d_new = ll, dl
+    if st_ is None: l_new, d_new = ll, dl
     print(f"fused L1 backward ({nm_}): {tl:.3f} ms ({B*8*hw/tl/1e6:.0f} GB/s algorithmic)")
 env(FFB_SPLAT_L1_ST=None)
 print(f"  L1 st vs old: loss rel {float((l_new - ll).abs().max() / ll.abs().max()):.2e}, grad rel-to-norm {float((d_new - dl).norm() / dl.norm()):.3e}")
