@@ -769,6 +769,20 @@ static int launch_bwd_tma(K kernel, KO overflow, const RasterParams& q, const Wt
 
 __device__ unsigned st_counters[64];      // work counters of the persistent backward launches in flight (ffb_splat_st.cuh)
 
+// One zeroed counter per launch: a slot of the per-device pool, handed out round-robin across ALL instantiations and streams (64
+// launches may be in flight; a launch lasts milliseconds), zeroed on the launching stream.
+static int st_counter_slot(cudaStream_t st, unsigned** counter) {
+    static unsigned* pool[64] = {nullptr};
+    static unsigned turn = 0;
+    int dev = 0;
+    FFB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail_arg(FFB_E_LIMIT, "splat: device ordinal >= 64");
+    if (!pool[dev]) FFB_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&pool[dev]), st_counters));
+    *counter = pool[dev] + (__atomic_fetch_add(&turn, 1u, __ATOMIC_RELAXED) & 63u);
+    FFB_CUDA(cudaMemsetAsync(*counter, 0, sizeof(unsigned), st));
+    return 0;
+}
+
 // super-tile backward (ffb_splat_st.cuh): persistent one-warp CTAs walking the (super tile, sample) items for dense patterns,
 // one one-warp CTA per item otherwise
 template <typename KP, typename K, typename KO>
@@ -780,15 +794,8 @@ static int launch_bwd_st(KP persistent, K oneshot, KO overflow, const RasterPara
     const char* e = getenv("FFB_SPLAT_BWD_PERSIST");
     const bool persist = e ? e[0] == '1' : (q.eager != 0);
     if (persist && items < 0x7fffffffLL) {
-        // work counter of this launch: a slot of a small per-device pool, zeroed on the stream (64 launches may be in flight)
-        static unsigned* pool[64] = {nullptr};
-        static unsigned turn = 0;
-        int dev = 0;
-        FFB_CUDA(cudaGetDevice(&dev));
-        if (dev < 0 || dev >= 64) return fail_arg(FFB_E_LIMIT, "splat: device ordinal >= 64");
-        if (!pool[dev]) FFB_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&pool[dev]), st_counters));
-        unsigned* counter = pool[dev] + (__atomic_fetch_add(&turn, 1u, __ATOMIC_RELAXED) & 63u);
-        FFB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+        unsigned* counter = nullptr;
+        if (int rc = st_counter_slot(st, &counter)) return rc;
         static int occ = 0;                                 // per instantiation (the function is a template)
         if (occ == 0) {
             if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
