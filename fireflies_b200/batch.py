@@ -132,11 +132,14 @@ class SceneBatch:
             if isinstance(e, Mesh) or not e.randomizable():
                 continue
             for key, s in list(e._float_attributes.items()) + list(e._vec3_attributes.items()):
-                self._attr_rows[(e.name(), key)] = (len(samplers), 3 if s._KIND == nat.SAMPLER_SCALAR_TO_VEC3 else s._dim)
+                self._attr_rows[(e.name(), key)] = (len(samplers), 3 if getattr(s, "_KIND", None) == nat.SAMPLER_SCALAR_TO_VEC3 else s._dim)
                 samplers.append(s)
         for s in samplers:
             if not isinstance(s, Sampler):
                 raise TypeError("SceneBatch needs fireflies_b200.sampling.Sampler instances")
+            if getattr(s, "_KIND", None) is None:
+                raise NotImplementedError(f"SceneBatch: {type(s).__name__} has no device record (its samples are not 1-3 scalars); "
+                                          "sample it per scene through its own sample() instead")
         self.samplers = samplers
         self.S = len(samplers)
         self.sampler_table = torch.zeros((max(self.S, 1), _SMP_WORDS), dtype=torch.int32, device=self.device)

@@ -196,9 +196,11 @@ class Transformable:
         and is rebuilt only when the world matrix or the centroid changed (tensor identity + version), so a call is the
         sample stack and ONE launch instead of a table upload and a dozen slice writes."""
         dev = self._world.device
-        key = (id(self._world), self._world._version, id(self._centroid_mat), self._centroid_mat._version, self._KIND)
+        # the key holds the tensors themselves (compared by identity): an id() alone can be recycled by a later tensor
+        key = (self._world, self._world._version, self._centroid_mat, self._centroid_mat._version, self._KIND)
         cache = getattr(self, "_ent_cache", None)
-        if cache is None or cache[0] != key:
+        if cache is None or not (cache[0][0] is key[0] and cache[0][2] is key[2] and cache[0][1] == key[1] and cache[0][3] == key[3]
+                                 and cache[0][4] == key[4]):
             ints = np.full((1, _ENT_INTS), -1, dtype=np.int32)
             ints[0, 0], ints[0, 1], ints[0, 2] = self._KIND, -1, 1
             ints[0, 3], ints[0, 4], ints[0, 5] = 0, 1, 2

@@ -43,7 +43,7 @@ class Sampler:
         if dev.type != "cuda":
             raise RuntimeError("fireflies_b200 samplers live on a CUDA device; there is no CPU path")
         rec = np.zeros(_WORDS, dtype=np.int32)
-        rec[0], rec[1], rec[2] = self._KIND, dim, 0
+        rec[0], rec[1], rec[2] = (nat.SAMPLER_UNIFORM if self._KIND is None else self._KIND), dim, 0
         rec[3:4] = np.array([eval_step_size], dtype=np.float32).view(np.int32)
         self._buf = torch.from_numpy(rec).to(dev)
         fv = self._buf.view(torch.float32)

@@ -59,6 +59,7 @@ def rand_perlin_2d_octaves(shape, res, octaves=1, persistence=0.5, device=torch.
 
 
 class NoiseTextureLerpSampler(base.Sampler):
+    _KIND = None          # no device record: its samples are textures, not the 1-3 scalars the batched sampler table holds
     def __init__(self, color_a: torch.Tensor, color_b: torch.Tensor, texture_shape: List[int], eval_step_size: float = 0.01,
                  device: torch.device = torch.device("cuda")) -> None:
         super().__init__(torch.tensor([0.0], device=device), torch.tensor([1.0], device=device), eval_step_size, device)

@@ -127,6 +127,11 @@ def convert_points_to_nonhomogeneous(points: torch.Tensor) -> torch.Tensor:
 class _TransformFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, points, transform, as_directions):
+        if torch.is_tensor(transform) and transform.requires_grad:
+            # the reference is plain torch, so d/d(transform) flows there; this kernel has no such backward -- say so instead of
+            # returning a silent None
+            raise NotImplementedError("fireflies_b200.transform_points / transform_directions: gradient w.r.t. the transform is not "
+                                      "implemented (only w.r.t. the points); detach the transform or compose it in torch")
         pts = nat.require_cuda(points.detach().float().contiguous(), torch.float32, "points")
         T = nat.require_cuda(transform.detach().float().contiguous(), torch.float32, "transform")
         if pts.dim() != 2 or pts.shape[1] != 3 or T.shape != (4, 4):
