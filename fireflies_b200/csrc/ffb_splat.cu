@@ -787,12 +787,18 @@ static int st_counter_slot(cudaStream_t st, unsigned** counter) {
 // one one-warp CTA per item otherwise
 template <typename KP, typename K, typename KO>
 static int launch_bwd_st(KP persistent, K oneshot, KO overflow, const RasterParams& q, const WtConsts& fc, const OvfParams& o, int B,
-                         cudaStream_t st, const BwdMaps& m, size_t smem, size_t smem_ovf) {
+                         cudaStream_t st, const BwdMaps& m, size_t smem, size_t smem_ovf, bool prefer_persistent = false) {
     if (B > 65535 || q.tgy > 65535) return fail_arg(FFB_E_LIMIT, "splat: B or the tile rows exceed the grid limit (65535)");
     if (smem_ovf > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(overflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ovf));
     const long long items = (long long)q.T * B;
+    // The persistent form is ~5 % faster in isolation (0.524 against 0.554 ms per 64 samples) but its step times scatter: on a 4-GPU box
+    // some rank's backward takes ~0.6 ms longer in most steps, and a synchronous step waits for the slowest rank -- 4.36-4.49 ms per
+    // step against 3.88 ms with the one-shot form, which shows no scatter at all (profiles/r02t; one GPU, sustained: 4.11 against
+    // 4.15 ms, scripts/bench_ab.py).  One-shot is therefore the default; FFB_SPLAT_BWD_PERSIST=1 selects the persistent form.
     const char* e = getenv("FFB_SPLAT_BWD_PERSIST");
-    const bool persist = e ? e[0] == '1' : (q.eager != 0);
+    // The loss mode keeps the persistent form: its two request rounds per item need the cross-item prefetch, and its steps do not
+    // scatter (4 GPUs end to end: 4.45 ms per step against 4.41 ms on one, profiles/r02s).
+    const bool persist = (e ? e[0] == '1' : prefer_persistent) && q.eager != 0;
     if (persist && items < 0x7fffffffLL) {
         unsigned* counter = nullptr;
         if (int rc = st_counter_slot(st, &counter)) return rc;
@@ -1344,7 +1350,7 @@ extern "C" int ffb_splat_bwd_l1(const ffb_splat_desc* d, const float* pts, const
             const bool msk = e4 ? e4[0] == '1' : edge * edge < 15.25;
             q.eager = 1;                                    // the loss needs every texel: every item requests its blocks
 #define FFB_SL(T, K) launch_bwd_st(splat_bwd_stp<true, true, T, K, ST_LOSS>, splat_bwd_st<true, true, T, K, ST_LOSS>, \
-                                   splat_bwd_ovf<true, true, T, false, true, true>, q, fc, ov, B, st, n, (size_t)StSmem<true, true, T, ST_LOSS>::bytes, stage * WT_WARPS)
+                                   splat_bwd_ovf<true, true, T, false, true, true>, q, fc, ov, B, st, n, (size_t)StSmem<true, true, T, ST_LOSS>::bytes, stage * WT_WARPS, true)
             if (sum_transposed) return msk ? FFB_SL(true, true) : FFB_SL(true, false);
             return msk ? FFB_SL(false, true) : FFB_SL(false, false);
 #undef FFB_SL

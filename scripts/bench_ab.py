@@ -12,8 +12,8 @@ pattern = (torch.rand(4096, 2, generator=g0) * 0.96 + 0.02).to(dev)
 gS = torch.randn(B, 2048, 2048, device=dev); gO = torch.randn(B, 2048, 2048, device=dev)
 scene = bench.build_scene(ff, dev); sb = scene.batch(seed=1)
 step = ff.PatternStep(4096, (2048, 2048), 100.0, B, scene_batch=sb, device=dev)
-variants = {"persist": {}, "oneshot": {"FFB_SPLAT_BWD_PERSIST": "0"}, "persist_g20": {"FFB_SPLAT_BWD_GRID": str(148 * 20)},
-            "persist_g16": {"FFB_SPLAT_BWD_GRID": str(148 * 16)}, "old": {"FFB_SPLAT_BWD_ST": "0"},
+variants = {"persist": {"FFB_SPLAT_BWD_PERSIST": "1", "FFB_SPLAT_BWD_GRID": str(148 * 24)}, "oneshot": {}, "persist_g20": {"FFB_SPLAT_BWD_PERSIST": "1"},
+            "persist_g16": {"FFB_SPLAT_BWD_PERSIST": "1", "FFB_SPLAT_BWD_GRID": str(148 * 16)}, "old": {"FFB_SPLAT_BWD_ST": "0"},
             "l1_old": {"L1": "1", "FFB_SPLAT_L1_ST": "0"}, "l1_st": {"L1": "1"}, "l1_st_g24": {"L1": "1", "FFB_SPLAT_BWD_GRID": str(148 * 24)}}
 if len(sys.argv) > 1: variants = {k: v for k, v in variants.items() if k in sys.argv[1:]}
 res = {k: [] for k in variants}

@@ -28,8 +28,8 @@ tp = t(lambda: R._SplatPlan(ptsB, B, 100.0, ts[0], ts[1], 4, 5))
 tf = t(lambda: plan.forward(ptsB, True, True, True))
 S_, O_ = plan.forward(ptsB, True, True, True)
 res = {}
-for name, kw in [("st_rebuild", dict(FFB_SPLAT_BWD_ST=None, FFB_SPLAT_BWD_SAVED=None, FFB_SPLAT_BWD_PERSIST=None)),
-                 ("st_oneshot", dict(FFB_SPLAT_BWD_ST=None, FFB_SPLAT_BWD_SAVED=None, FFB_SPLAT_BWD_PERSIST="0")),
+for name, kw in [("st_rebuild", dict(FFB_SPLAT_BWD_ST=None, FFB_SPLAT_BWD_SAVED=None, FFB_SPLAT_BWD_PERSIST="1")),
+                 ("st_oneshot", dict(FFB_SPLAT_BWD_ST=None, FFB_SPLAT_BWD_SAVED=None, FFB_SPLAT_BWD_PERSIST=None)),
                  ("st_saved", dict(FFB_SPLAT_BWD_ST=None, FFB_SPLAT_BWD_SAVED="1", FFB_SPLAT_BWD_PERSIST=None)),
                  ("old_saved", dict(FFB_SPLAT_BWD_ST="0", FFB_SPLAT_BWD_SAVED=None)),
                  ("old_rebuild", dict(FFB_SPLAT_BWD_ST="0", FFB_SPLAT_BWD_SAVED=None))]:

@@ -14,8 +14,8 @@ plan = R._SplatPlan(ptsB, B, 100.0, ts[0], ts[1], 4, 5)
 gS = torch.randn(B, ts[0], ts[1], device="cuda"); gO = torch.randn(B, ts[1], ts[0], device="cuda")
 S_, O_ = plan.forward(ptsB, True, True, True)
 ev = lambda: torch.cuda.Event(enable_timing=True)
-variants = [("st_rebuild", dict()), ("st_oneshot", dict(FFB_SPLAT_BWD_PERSIST="0")), ("st_saved", dict(FFB_SPLAT_BWD_SAVED="1")),
-            ("old_saved", dict(FFB_SPLAT_BWD_ST="0")), ("st_rebuild", dict())]
+variants = [("st_rebuild", dict(FFB_SPLAT_BWD_PERSIST="1")), ("st_oneshot", dict()), ("st_saved", dict(FFB_SPLAT_BWD_SAVED="1")),
+            ("old_saved", dict(FFB_SPLAT_BWD_ST="0")), ("st_rebuild", dict(FFB_SPLAT_BWD_PERSIST="1"))]
 for name, kw in variants:
     for k in ("FFB_SPLAT_BWD_PERSIST", "FFB_SPLAT_BWD_SAVED", "FFB_SPLAT_BWD_ST"): os.environ.pop(k, None)
     os.environ.update(kw)
