@@ -815,7 +815,10 @@ static int launch_bwd_st(KP persistent, K oneshot, KO overflow, const RasterPara
         long long grid = (long long)kNumSMs * (occ < 20 ? occ : 20);
         if (const char* g = getenv("FFB_SPLAT_BWD_GRID")) grid = atoll(g) > 0 ? atoll(g) : grid;
         if (grid > items) grid = items;
-        persistent<<<(unsigned)grid, 32, smem, st>>>(q, fc, m.gs, m.go, m.sv, m.ot, (int)items, counter);
+        int chunk = 0;
+        if (const char* c = getenv("FFB_SPLAT_BWD_CHUNK")) chunk = atoi(c) > 0 ? atoi(c) : 0;   // static chunks of consecutive items per CTA
+        if (chunk > 0) grid = (items + chunk - 1) / chunk;
+        persistent<<<(unsigned)grid, 32, smem, st>>>(q, fc, m.gs, m.go, m.sv, m.ot, (int)items, counter, chunk);
     } else {
         if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(oneshot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         oneshot<<<dim3((unsigned)q.tgx, (unsigned)q.tgy, (unsigned)B), 32, smem, st>>>(q, fc, m.gs, m.go, m.sv, m.ot);

@@ -682,14 +682,16 @@ template <bool SUM, bool SOFTOR, bool SUM_T, bool MSK, int MODE>
 __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_stp(RasterParams q, WtConsts fc, const __grid_constant__ CUtensorMap tm_gs,
                                                                  const __grid_constant__ CUtensorMap tm_go,
                                                                  const __grid_constant__ CUtensorMap tm_sv,
-                                                                 const __grid_constant__ CUtensorMap tm_ot, int n_items, unsigned* counter) {
+                                                                 const __grid_constant__ CUtensorMap tm_ot, int n_items, unsigned* counter, int chunk) {
     typedef StSmem<SUM, SOFTOR, SUM_T, MODE> L;
     constexpr bool LOSS = MODE == ST_LOSS;
     extern __shared__ __align__(1024) unsigned char st_smem[];
     const int lane = threadIdx.x;
     const int G = (int)gridDim.x;
-    int it = blockIdx.x;
+    // chunk > 0: a CTA walks `chunk` consecutive items (no counter; the hardware scheduler balances the CTAs); chunk == 0: persistent
+    int it = chunk > 0 ? (int)blockIdx.x * chunk : (int)blockIdx.x;
     if (it >= n_items) return;
+    if (chunk > 0) n_items = min(n_items, it + chunk);
     uint64_t* bar = reinterpret_cast<uint64_t*>(st_smem + L::off_bar);
     float4* rec = reinterpret_cast<float4*>(st_smem + L::off_rec);
     int* idx = reinterpret_cast<int*>(st_smem + L::off_idx);
@@ -703,9 +705,10 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_stp(RasterParams q,
     auto toff_of = [&](const StItem& s) { return q.tile_off + (size_t)(q.shared_pattern ? 0 : s.b) * (q.T + 1) + (size_t)s.sty * q.tgx + s.bx; };
     // claims an item: the first G items are the CTAs' own indices, the counter hands out the rest.  One lane asks (claim_ask) at the start
     // of an item; the warp picks the answer up (claim_get) at its end, a whole item of work later.
+    const bool dyn = FFB_ST_DYN && chunk == 0;
     auto claim_ask = [&]() {
         unsigned v = 0;
-        if (FFB_ST_DYN && lane == 0) v = atomicAdd(counter, 1u);
+        if (dyn && lane == 0) v = atomicAdd(counter, 1u);
         return v;
     };
     auto claim_get = [&](unsigned v) { return (int)__shfl_sync(0xffffffffu, v, 0) + G; };
@@ -713,7 +716,8 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_stp(RasterParams q,
     StItem cur = st_decode(q, it, inv_T, inv_tgx);
     st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar, 0, cur.bx * (4 * WT), cur.sty * WT, cur.b, &tm_gs, &tm_go, &tm_sv, &tm_ot, TWO);
     st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar + 1, 1, cur.bx * (4 * WT), cur.sty * WT, cur.b, &tm_gs, &tm_go, &tm_sv, &tm_ot, TWO);
-    int nit = FFB_ST_DYN ? claim_get(claim_ask()) : it + G;   // the item after this one
+    const int step = chunk > 0 ? 1 : G;
+    int nit = dyn ? claim_get(claim_ask()) : it + step;      // the item after this one
     int beg, end;
     {
         const int* t = toff_of(cur);
@@ -778,7 +782,7 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_stp(RasterParams q,
             if (lane == 0) atomicAdd(q.loss + cur.b, lacc * q.loss_inv);
         }
         if (!more) break;
-        it = nit; nit = FFB_ST_DYN ? claim_get(asked) : nit + G; cur = nx; beg = nbeg; end = nend;
+        it = nit; nit = dyn ? claim_get(asked) : nit + step; cur = nx; beg = nbeg; end = nend;
         phase ^= 1u;
         __syncwarp();                                       // records and point indices of this item are dead
     }

@@ -14,13 +14,15 @@ scene = bench.build_scene(ff, dev); sb = scene.batch(seed=1)
 step = ff.PatternStep(4096, (2048, 2048), 100.0, B, scene_batch=sb, device=dev)
 variants = {"persist": {"FFB_SPLAT_BWD_PERSIST": "1", "FFB_SPLAT_BWD_GRID": str(148 * 24)}, "oneshot": {}, "persist_g20": {"FFB_SPLAT_BWD_PERSIST": "1"},
             "persist_g16": {"FFB_SPLAT_BWD_PERSIST": "1", "FFB_SPLAT_BWD_GRID": str(148 * 16)}, "old": {"FFB_SPLAT_BWD_ST": "0"},
+            "chunk2": {"FFB_SPLAT_BWD_PERSIST": "1", "FFB_SPLAT_BWD_CHUNK": "2"}, "chunk4": {"FFB_SPLAT_BWD_PERSIST": "1", "FFB_SPLAT_BWD_CHUNK": "4"},
+            "chunk8": {"FFB_SPLAT_BWD_PERSIST": "1", "FFB_SPLAT_BWD_CHUNK": "8"}, "chunk32": {"FFB_SPLAT_BWD_PERSIST": "1", "FFB_SPLAT_BWD_CHUNK": "32"},
             "l1_old": {"L1": "1", "FFB_SPLAT_L1_ST": "0"}, "l1_st": {"L1": "1"}, "l1_st_g24": {"L1": "1", "FFB_SPLAT_BWD_GRID": str(148 * 24)}}
 if len(sys.argv) > 1: variants = {k: v for k, v in variants.items() if k in sys.argv[1:]}
 res = {k: [] for k in variants}
 ev = lambda: torch.cuda.Event(enable_timing=True)
 for rnd in range(5):
     for name, env in variants.items():
-        for k in ("FFB_SPLAT_BWD_PERSIST", "FFB_SPLAT_BWD_GRID", "FFB_SPLAT_BWD_ST", "FFB_SPLAT_L1_ST"): os.environ.pop(k, None)
+        for k in ("FFB_SPLAT_BWD_PERSIST", "FFB_SPLAT_BWD_GRID", "FFB_SPLAT_BWD_ST", "FFB_SPLAT_L1_ST", "FFB_SPLAT_BWD_CHUNK"): os.environ.pop(k, None)
         os.environ.update({k: v for k, v in env.items() if k != "L1"})
         up = None if "L1" in env else (gS, gO)
         for i in range(3): step.forward_backward(pattern, upstream=up, sample0=i * B)

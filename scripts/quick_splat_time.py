@@ -30,7 +30,9 @@ S_, O_ = plan.forward(ptsB, True, True, True)
 res = {}
 for name, kw in [("st_rebuild", dict(FFB_SPLAT_BWD_ST=None, FFB_SPLAT_BWD_SAVED=None, FFB_SPLAT_BWD_PERSIST="1")),
                  ("st_oneshot", dict(FFB_SPLAT_BWD_ST=None, FFB_SPLAT_BWD_SAVED=None, FFB_SPLAT_BWD_PERSIST=None)),
-                 ("st_saved", dict(FFB_SPLAT_BWD_ST=None, FFB_SPLAT_BWD_SAVED="1", FFB_SPLAT_BWD_PERSIST=None)),
+                 ("st_chunk2", dict(FFB_SPLAT_BWD_PERSIST="1", FFB_SPLAT_BWD_CHUNK="2")), ("st_chunk4", dict(FFB_SPLAT_BWD_PERSIST="1", FFB_SPLAT_BWD_CHUNK="4")),
+                 ("st_chunk8", dict(FFB_SPLAT_BWD_PERSIST="1", FFB_SPLAT_BWD_CHUNK="8")),
+                 ("st_saved", dict(FFB_SPLAT_BWD_ST=None, FFB_SPLAT_BWD_SAVED="1", FFB_SPLAT_BWD_PERSIST=None, FFB_SPLAT_BWD_CHUNK=None)),
                  ("old_saved", dict(FFB_SPLAT_BWD_ST="0", FFB_SPLAT_BWD_SAVED=None)),
                  ("old_rebuild", dict(FFB_SPLAT_BWD_ST="0", FFB_SPLAT_BWD_SAVED=None))]:
     env(**kw)
