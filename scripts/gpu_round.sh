@@ -15,7 +15,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-side > "$OUT/ncu_launch_bench.log" 2>&1
 tail -2 "$OUT/ncu_launch_bench.log" | cut -c1-300
 echo "== ncu full (splat kernels)"
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:splat_(fwd_tma|bwd_stp)" -s 4 -c 2 -f -o "$OUT/prof_splat" \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:splat_(fwd_tma|bwd_st)" -s 4 -c 2 -f -o "$OUT/prof_splat" \
     python bench.py --batch 64 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-side > "$OUT/ncu_full_bench.log" 2>&1
 tail -2 "$OUT/ncu_full_bench.log" | cut -c1-300
 ls -la "$OUT"

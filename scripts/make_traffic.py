@@ -11,7 +11,8 @@ SC = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 per = {}
 for r in rows[2:]:
     name = r[ix["Kernel Name"]]
-    short = "splat_fwd_tma" if "splat_fwd_tma" in name else ("splat_bwd_stp" if "splat_bwd_stp" in name else ("splat_bwd_tma" if "splat_bwd_tma" in name else None))
+    short = ("splat_fwd_tma" if "splat_fwd_tma" in name else "splat_bwd_stp" if "splat_bwd_stp" in name else "splat_bwd_st" if "splat_bwd_st<" in name
+             else "splat_bwd_tma" if "splat_bwd_tma" in name else None)
     if not short:
         continue
     b = sum(float(r[ix[m]]) * SC[units[ix[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
