@@ -11,10 +11,10 @@ if [ -f "$REP" ]; then
   python scripts/ncu_summary.py "$REP" > "$DST/ncu_splat_summary.txt"
   python scripts/make_traffic.py "$REP" 64 "$TAG"
   python scripts/sass_summary.py > "$DST/sass_tma.txt"
-  for k in fwd_tma "bwd_st<" bwd_stp bwd_tma; do
-    ncu -i "$REP" --page source --csv --kernel-name regex:$k > "$SRC/src_${k//</}.csv" 2>/dev/null
-    if [ -s "$SRC/src_${k//</}.csv" ]; then
-      { echo "== $k: SASS lines bucketed by executions per super tile (warp-level), top stall lines"; python scripts/ncu_buckets.py "$SRC/src_${k//</}.csv" ${2:-262144} 12; } >> "$DST/ncu_splat_summary.txt"
+  for k in fwd_tma "bwd_st$" bwd_stp bwd_tma; do
+    ncu -i "$REP" --page source --csv --kernel-name regex:$k > "$SRC/src_${k//$/}.csv" 2>/dev/null
+    if [ -s "$SRC/src_${k//$/}.csv" ]; then
+      { echo "== $k: SASS lines bucketed by executions per super tile (warp-level), top stall lines"; python scripts/ncu_buckets.py "$SRC/src_${k//$/}.csv" ${2:-262144} 12; } >> "$DST/ncu_splat_summary.txt"
     fi
   done
 fi
