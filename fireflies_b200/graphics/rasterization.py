@@ -74,23 +74,27 @@ class _SplatPlan:
                                       nat.ptr(self.windows), nat.stream()), "ffb_splat_prepare")
         nat.count()
 
-    def forward(self, points, want_sum: bool, want_softor: bool, sum_transposed: bool):
+    def forward(self, points, want_sum: bool, want_softor: bool, sum_transposed: bool, out=None):
+        """``out``: optional ``(sum, softor)`` tensors to write into (contiguous, e.g. slices of a larger batch along dim 0)."""
         dev = points.device
         out_s = out_o = None
         if want_sum:
             shape = (self.B, self.ts0, self.ts1) if sum_transposed else (self.B, self.ts1, self.ts0)
-            out_s = torch.empty(shape, dtype=torch.float32, device=dev)
+            out_s = out[0] if out is not None else torch.empty(shape, dtype=torch.float32, device=dev)
+            assert tuple(out_s.shape) == shape and out_s.is_contiguous()
         if want_softor:
-            out_o = torch.empty((self.B, self.ts1, self.ts0), dtype=torch.float32, device=dev)
+            out_o = out[1] if out is not None else torch.empty((self.B, self.ts1, self.ts0), dtype=torch.float32, device=dev)
+            assert tuple(out_o.shape) == (self.B, self.ts1, self.ts0) and out_o.is_contiguous()
         nat.check(nat.lib().ffb_splat_fwd(C.byref(self.desc), points.data_ptr(), self.ws.data_ptr(), nat.ptr(out_s),
                                           int(sum_transposed), nat.ptr(out_o), nat.stream()), "ffb_splat_fwd")
         nat.count()
         return out_s, out_o
 
-    def backward(self, points, g_sum, g_softor, sum_transposed: bool, saved_softor=None) -> torch.Tensor:
-        """``saved_softor``: the forward's soft-OR output (what autograd saves for ``prod``'s backward); lets the
-        kernel read the per-texel product back instead of rebuilding it."""
-        d_pts = torch.empty((self.B, self.N, 2), dtype=torch.float32, device=points.device)
+    def backward(self, points, g_sum, g_softor, sum_transposed: bool, saved_softor=None, out=None) -> torch.Tensor:
+        """``saved_softor``: the forward's soft-OR output (what autograd saves for ``prod``'s backward); the production kernel
+        rebuilds the per-texel product instead (8 instead of 12 B/texel) unless ``FFB_SPLAT_BWD_SAVED=1``.  ``out``: optional
+        ``[B,N,2]`` tensor to write into."""
+        d_pts = out if out is not None else torch.empty((self.B, self.N, 2), dtype=torch.float32, device=points.device)
         nat.check(nat.lib().ffb_splat_bwd(C.byref(self.desc), points.data_ptr(), self.ws.data_ptr(), nat.ptr(g_sum),
                                           int(sum_transposed), nat.ptr(g_softor), nat.ptr(saved_softor), d_pts.data_ptr(),
                                           nat.stream()), "ffb_splat_bwd")
@@ -98,14 +102,14 @@ class _SplatPlan:
         return d_pts
 
 
-    def backward_l1(self, points, out_sum, out_softor, sum_transposed: bool):
+    def backward_l1(self, points, out_sum, out_softor, sum_transposed: bool, out=None):
         """Fused ``L1Loss(softor, sum).backward()`` (rasterization.py:589-599): returns ``(loss [B], d_pts [B,N,2])`` or
         ``None`` when the fused kernel does not cover the case (the caller then runs the loss and the backward
-        separately)."""
+        separately).  ``out``: optional ``(loss, d_pts)`` tensors to write into."""
         if sum_transposed and self.ts0 != self.ts1:
             return None
-        d_pts = torch.empty((self.B, self.N, 2), dtype=torch.float32, device=points.device)
-        loss = torch.empty(self.B, dtype=torch.float32, device=points.device)
+        d_pts = out[1] if out is not None else torch.empty((self.B, self.N, 2), dtype=torch.float32, device=points.device)
+        loss = out[0] if out is not None else torch.empty(self.B, dtype=torch.float32, device=points.device)
         rc = nat.lib().ffb_splat_bwd_l1(C.byref(self.desc), points.data_ptr(), self.ws.data_ptr(), out_sum.data_ptr(),
                                         int(sum_transposed), out_softor.data_ptr(), loss.data_ptr(), d_pts.data_ptr(), nat.stream())
         if rc == nat.E_UNSUPPORTED:
