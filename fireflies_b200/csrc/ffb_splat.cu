@@ -431,6 +431,169 @@ __global__ void __launch_bounds__(PREP_CTA, FFB_PREP_MINB) prepare_kernel(PrepPa
     if (tid == 0) tile_off[q.T] = band_base;
 }
 
+// One-pass binning for the warp-tile path (whole tile grid in one band, N <= 65535, everything below in shared memory).
+// prepare_kernel<true> counts, scans, fills a global index list and then lets every thread sort and emit whole super tiles: two
+// shared-memory atomics per (point, super tile) pair, and entry stores that scatter 32 x 16 bytes per instruction (profiles/r02x:
+// lg_throttle + long scoreboard are two thirds of its stall samples).  Here
+//   - a pair costs ONE atomic: the counter's old value is the point's slot in a fixed WCH-entry list per super tile (uint16 indices);
+//   - the lists are sorted in registers in place (point order = deterministic accumulation order);
+//   - the entries are written by whole warps, one super tile per step: lane (i, h) stores half h of entry i, so a store instruction
+//     covers one contiguous run of <= 512 bytes.
+// Super tiles with more than WCH candidates (clustered patterns; they go to the overflow kernels anyway) are completed by a second
+// pass into the global index list; the first word of their (unused) slot row is the fill cursor.
+struct Rec16 { float p0, p1; uint32_t ur, uc; };
+__global__ void __launch_bounds__(PREP_CTA, 1) prepare_onepass_kernel(PrepParams q) {
+    extern __shared__ __align__(16) int sm[];
+    int* cnt = sm;                                   // [T] candidates per super tile
+    int* off = sm + q.T;                             // [T] exclusive offsets
+    const int slot0 = (2 * q.T + 3) & ~3;            // 16-byte aligned rows
+    unsigned short* slot = reinterpret_cast<unsigned short*>(sm + slot0);                         // [T][WCH]
+    Rec16* recs = reinterpret_cast<Rec16*>(sm + slot0 + q.T * (WCH / 2));                          // [N]
+    __shared__ int warp_tot[32];
+    __shared__ int n_ovf;
+    const int bin = blockIdx.x, tid = threadIdx.x, T = q.T;
+    const float* pts = q.pts + (long long)bin * q.stride;
+    int* tile_off = q.tile_off + (size_t)bin * (T + 1);
+    int* list = q.list + (size_t)bin * q.cap;
+    Entry* entries = q.entries + (size_t)bin * q.cap;
+    const bool bs = q.baked_s != 0;
+    const int baked = (bs || !q.baked_o) ? (int)bs : 1, half = (bs || !q.baked_o) ? q.half_s : q.half_o;
+    for (int i = tid; i < T; i += PREP_CTA) cnt[i] = 0;
+    if (tid == 0) n_ovf = 0;
+    __syncthreads();
+    // 1. records + slots
+    for (int n = tid; n < q.N; n += PREP_CTA) {
+        const float2 xy = reinterpret_cast<const float2*>(pts)[n];
+        int win[12];
+        const PointRec rec = make_rec(q, xy.x, xy.y, q.windows ? win : nullptr);
+        const int c_lo = rec.uc & 0xffff, c_hi = rec.uc >> 16, r_lo = rec.ur & 0xffff, r_hi = rec.ur >> 16;
+        recs[n] = Rec16{rec.p0, rec.p1, rec.ur, rec.uc};
+        if (q.windows) {
+            int* w = q.windows + ((size_t)bin * q.N + n) * 12;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) w[k] = win[k];
+        }
+        if (c_hi > c_lo && r_hi > r_lo)
+            for (int ty = r_lo / q.th; ty <= (r_hi - 1) / q.th; ++ty)
+                for (int tx = c_lo / q.tw; tx <= (c_hi - 1) / q.tw; ++tx) {
+                    const int t = ty * q.tgx + tx;
+                    const int pos = atomicAdd(&cnt[t], 1);
+                    if (pos < WCH) slot[t * WCH + pos] = (unsigned short)n;
+                }
+    }
+    __syncthreads();
+    // 2. exclusive scan over the super tiles
+    const int per = (T + PREP_CTA - 1) / PREP_CTA;
+    const int beg = min(tid * per, T), end = min(beg + per, T);
+    int local = 0;
+    for (int i = beg; i < end; ++i) local += cnt[i];
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31) >= o) incl += v;
+    }
+    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        int v = warp_tot[tid], sc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, sc, o);
+            if (tid >= o) sc += t;
+        }
+        warp_tot[tid] = sc - v;
+    }
+    __syncthreads();
+    int run = warp_tot[tid >> 5] + incl - local;
+    for (int i = beg; i < end; ++i) {
+        const int c = cnt[i];
+        off[i] = run; tile_off[i] = run;
+        run += c;
+        if (c > WCH) {
+            q.ovf[1 + atomicAdd(q.ovf, 1)] = bin * T + i;
+            atomicAdd(&n_ovf, 1);
+            *reinterpret_cast<int*>(slot + i * WCH) = 0;       // becomes the fill cursor of pass 3
+        }
+    }
+    if (tid == PREP_CTA - 1) tile_off[T] = run;
+    __syncthreads();
+    // 3. overflow super tiles: the complete lists into the global list
+    if (n_ovf > 0) {
+        for (int n = tid; n < q.N; n += PREP_CTA) {
+            const Rec16 r = recs[n];
+            const int c_lo = r.uc & 0xffff, c_hi = r.uc >> 16, r_lo = r.ur & 0xffff, r_hi = r.ur >> 16;
+            if (c_hi > c_lo && r_hi > r_lo)
+                for (int ty = r_lo / q.th; ty <= (r_hi - 1) / q.th; ++ty)
+                    for (int tx = c_lo / q.tw; tx <= (c_hi - 1) / q.tw; ++tx) {
+                        const int t = ty * q.tgx + tx;
+                        if (cnt[t] > WCH) {
+                            const int pos = off[t] + atomicAdd(reinterpret_cast<int*>(slot + t * WCH), 1);
+                            if (pos < q.cap) list[pos] = n;
+                        }
+                    }
+        }
+        __syncthreads();
+    }
+    // 4. every super tile's list ordered by point index, in place; the overflow lists are ranked straight into their entries
+    for (int t = tid; t < T; t += PREP_CTA) {
+        const int c = cnt[t], b = off[t];
+        if (c > WCH) {
+            const int e = min(b + c, q.cap);
+            for (int i = b; i < e; ++i) {
+                const int v = list[i];
+                int rank = 0;
+                for (int j = b; j < e; ++j) rank += list[j] < v;
+                const Rec16 r = recs[v];
+                uint4* dst = reinterpret_cast<uint4*>(entries + b + rank);
+                dst[0] = make_uint4(__float_as_uint(r.p0), __float_as_uint(r.p1), __float_as_uint((float)origin_axis(r.p0, baked, half)),
+                                    __float_as_uint((float)origin_axis(r.p1, baked, half)));
+                dst[1] = make_uint4(r.ur, r.uc, (unsigned)v, 0u);
+            }
+        } else if (c > 1) {
+            uint4* row = reinterpret_cast<uint4*>(slot + t * WCH);
+            const uint4 w0 = row[0], w1 = row[1];
+            const unsigned w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            int l[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) l[i] = i < c ? (int)((w[i >> 1] >> (16 * (i & 1))) & 0xffffu) : 0x7fffffff;
+            // Batcher's odd-even merge sort on the 16 registers (63 compare-exchanges); empty slots (INT_MAX) sink to the end
+#define FFB_CE(a, c_) { const int lo_ = min(l[a], l[c_]), hi_ = max(l[a], l[c_]); l[a] = lo_; l[c_] = hi_; }
+            FFB_CE(0,1) FFB_CE(2,3) FFB_CE(0,2) FFB_CE(1,3) FFB_CE(1,2) FFB_CE(4,5) FFB_CE(6,7) FFB_CE(4,6) FFB_CE(5,7) FFB_CE(5,6)
+            FFB_CE(0,4) FFB_CE(2,6) FFB_CE(2,4) FFB_CE(1,5) FFB_CE(3,7) FFB_CE(3,5) FFB_CE(1,2) FFB_CE(3,4) FFB_CE(5,6)
+            FFB_CE(8,9) FFB_CE(10,11) FFB_CE(8,10) FFB_CE(9,11) FFB_CE(9,10) FFB_CE(12,13) FFB_CE(14,15) FFB_CE(12,14) FFB_CE(13,15) FFB_CE(13,14)
+            FFB_CE(8,12) FFB_CE(10,14) FFB_CE(10,12) FFB_CE(9,13) FFB_CE(11,15) FFB_CE(11,13) FFB_CE(9,10) FFB_CE(11,12) FFB_CE(13,14)
+            FFB_CE(0,8) FFB_CE(4,12) FFB_CE(4,8) FFB_CE(2,10) FFB_CE(6,14) FFB_CE(6,10) FFB_CE(2,4) FFB_CE(6,8) FFB_CE(10,12)
+            FFB_CE(1,9) FFB_CE(5,13) FFB_CE(5,9) FFB_CE(3,11) FFB_CE(7,15) FFB_CE(7,11) FFB_CE(3,5) FFB_CE(7,9) FFB_CE(11,13)
+            FFB_CE(1,2) FFB_CE(3,4) FFB_CE(5,6) FFB_CE(7,8) FFB_CE(9,10) FFB_CE(11,12) FFB_CE(13,14)
+#undef FFB_CE
+            unsigned o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = ((unsigned)l[2 * i] & 0xffffu) | ((unsigned)l[2 * i + 1] << 16);
+            row[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            row[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+    }
+    __syncthreads();
+    // 5. entries {p0, p1, f0, f1 | ur, uc, idx, 0}: one super tile per warp step, lane (i, h) writes half h of entry i
+    const int lane = tid & 31, wid = tid >> 5, i = lane >> 1, h = lane & 1;
+    const int tiles_per_warp = (T + 31) / 32;
+    const int tb = wid * tiles_per_warp, te = min(tb + tiles_per_warp, T);
+#pragma unroll 4
+    for (int t = tb; t < te; ++t) {
+        const int c = cnt[t], b = off[t];
+        if (c <= WCH && i < c && b + i < q.cap) {
+            const unsigned idx = slot[t * WCH + i];
+            const Rec16 r = recs[idx];
+            uint4 v;
+            if (h == 0) v = make_uint4(__float_as_uint(r.p0), __float_as_uint(r.p1), __float_as_uint((float)origin_axis(r.p0, baked, half)),
+                                       __float_as_uint((float)origin_axis(r.p1, baked, half)));
+            else v = make_uint4(r.ur, r.uc, idx, 0u);
+            reinterpret_cast<uint4*>(entries + b + i)[h] = v;
+        }
+    }
+}
+
 struct RasterParams {
     const PointRec* recs;
     const int* tile_off;
@@ -1122,6 +1285,17 @@ extern "C" int ffb_splat_prepare(const ffb_splat_desc* d, const float* pts, void
     const size_t smem = (size_t)p.band_rows * p.tgx * 2 * sizeof(int);
     if (p.fast) {
         FFB_CUDA(cudaMemsetAsync(q.ovf, 0, sizeof(int), as_stream(stream)));
+        {
+            // one-pass form: one shared-memory atomic per (point, super tile) pair instead of two
+            const size_t smem_one = (((size_t)p.T * 2 + 3) & ~(size_t)3) * sizeof(int) + (size_t)p.T * WCH * sizeof(unsigned short) + (size_t)d->N * sizeof(Rec16);
+            const char* e1 = getenv("FFB_PREP_ONEPASS");
+            if (p.band_rows == p.tgy && d->N <= 65535 && smem_one <= 226 * 1024 && !(e1 && e1[0] == '0')) {
+                FFB_CUDA(cudaFuncSetAttribute(prepare_onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_one));
+                prepare_onepass_kernel<<<p.Bp, PREP_CTA, smem_one, as_stream(stream)>>>(q);
+                FFB_CUDA(cudaGetLastError());
+                return 0;
+            }
+        }
         const size_t smem_rec = (((size_t)p.band_rows * p.tgx * 2 + 3) & ~(size_t)3) * sizeof(int) + (size_t)d->N * sizeof(PointRec);
         const char* e = getenv("FFB_PREP_SREC");
         if (smem_rec <= 200 * 1024 && !(e && e[0] == '0')) {        // records in shared memory

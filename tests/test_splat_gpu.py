@@ -195,6 +195,30 @@ def test_clustered_points_take_the_overflow_path(R, batched):
     close_grad(d[0], ana)
 
 
+@pytest.mark.parametrize("clustered", [False, True])
+def test_binning_forms_agree_bitwise(R, monkeypatch, clustered):
+    """The one-pass binning kernel (slot lists in shared memory, warp-wide entry stores) and the count/scan/fill kernel it replaces
+    order every candidate list by point index, so the outputs are identical to the bit -- also with overflowing lists and
+    with a tile count that is not a multiple of four (shared-memory rows stay 16-byte aligned)."""
+    gen = torch.Generator().manual_seed(5)
+    ts, sigma = ([200, 136] if clustered else [328, 200]), 25.0
+    pts = torch.rand(400, 2, generator=gen)
+    if clustered:
+        pts[:150] = 0.45 + 0.1 * pts[:150]
+    gS, gO = torch.randn(1, ts[1], ts[0], generator=gen).cuda(), torch.randn(1, ts[1], ts[0], generator=gen).cuda()
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("FFB_PREP_ONEPASS", flag)
+        plan = R._SplatPlan(pts.cuda(), 1, sigma, ts[0], ts[1], 4, 5)
+        s, o = plan.forward(pts.cuda(), True, True, False)
+        d = plan.backward(pts.cuda(), gS, gO, False)
+        res.append((s.clone(), o.clone(), d.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    # the per-point gradient is a sum of per-tile partials added with float atomics: same terms, arrival order not fixed
+    assert (res[0][2] - res[1][2]).norm() <= 1e-6 * res[1][2].norm()
+    close(res[0][0][0], O.baked_sum(pts, sigma, ts))
+
+
 def test_saturated_softor_backward(R, monkeypatch):
     """220 points inside a 20x20 texel patch at sigma = 100: the soft-OR saturates (prod(1 - g) runs from 1e-40 to 1e-2 across the
     patch), every super tile overflows.  The production backward rebuilds the product like torch.prod's backward; the earlier
