@@ -449,9 +449,8 @@ __device__ __forceinline__ void st_tile(unsigned sbase, int j, unsigned tm, unsi
         for (int v = 0; v < 4; ++v) {
             const float dx_ = o[v].x - s[v].x, dy_ = o[v].y - s[v].y;
             lacc += fabsf(dx_) + fabsf(dy_);
-            const float2 sg = make_float2(sign_times(dx_, 0x3f800000u), sign_times(dy_, 0x3f800000u));
-            gp[v] = __fmul2_rn(sg, make_float2(1.f - o[v].x, 1.f - o[v].y));
-            gs[v] = neg2(sg);
+            gp[v] = make_float2(sign_times(dx_, 0x3f800000u), sign_times(dy_, 0x3f800000u));      // d loss / d softor (unit)
+            gs[v] = neg2(gp[v]);
         }
         if (tm == 0u) return;
         if (SUM_T) {
@@ -482,23 +481,31 @@ __device__ __forceinline__ void st_tile(unsigned sbase, int j, unsigned tm, unsi
         tc.c01 = make_float2(cfs, cfs + sc);
         tc.c23 = make_float2(cfs + 2.f * sc, cfs + 3.f * sc);
     }
-    if (LOSS) {
-        // gp already holds gO * prod (from the forward's output): every candidate divides its own factor out
-        st_weigh<SUM, SOFTOR, MSK, 0>(rec, pd, accr, nm, tc, ln, lane, fc, gs, gp);
-        st_weigh<SUM, SOFTOR, MSK, 1>(rec, pd, accr, tm & ~nm, tc, ln, lane, fc, gs, gp);
-        return;
-    }
     if (one || !SOFTOR) {
         st_weigh<SUM, SOFTOR, MSK, 2>(rec, pd, accr, tm, tc, ln, lane, fc, gs, gp);
         return;
     }
     const int cands = __popc(tm);
-    if (FFB_ST_PAIR && MODE == ST_REBUILD && cands == 2) {
+    if (FFB_ST_PAIR && MODE != ST_SAVED && cands == 2) {
         st_weigh_pair<SUM, MSK>(rec, pd, accr, tm, tc, ln, lane, fc, gs, gp);
         return;
     }
-    if (FFB_ST_TRIPLE && MODE == ST_REBUILD && cands == 3) {
+    if (FFB_ST_TRIPLE && MODE != ST_SAVED && cands == 3) {
         st_weigh_triple<SUM, MSK>(rec, pd, accr, tm, tc, ln, lane, fc, gs, gp);
+        return;
+    }
+    if (LOSS) {
+        // longer lists: gO * prod from the forward's output (resident anyway), every candidate divides its own factor out
+        const unsigned nb_ = (ln.nat_e ^ ((unsigned)(j & 1) << 6)) + (unsigned)(j >> 1) * (ST_BOX / 2);
+        float2 o[4];
+        {
+            const float4 a = st_lds128(sbase + L::off_go + nb_), c = st_lds128(sbase + L::off_go + nb_ + 1024);
+            o[0] = make_float2(a.x, a.y); o[1] = make_float2(a.z, a.w); o[2] = make_float2(c.x, c.y); o[3] = make_float2(c.z, c.w);
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) gp[v] = __ffma2_rn(neg2(o[v]), gp[v], gp[v]);          // sign * (1 - softor), one rounding like fl(1 - o)
+        st_weigh<SUM, SOFTOR, MSK, 0>(rec, pd, accr, nm, tc, ln, lane, fc, gs, gp);
+        st_weigh<SUM, SOFTOR, MSK, 1>(rec, pd, accr, tm & ~nm, tc, ln, lane, fc, gs, gp);
         return;
     }
     unsigned rest = tm;
