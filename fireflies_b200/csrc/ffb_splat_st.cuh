@@ -389,12 +389,15 @@ __device__ __forceinline__ WtMasks st_stage(const RasterParams& q, const WtConst
 // conflict-free LDS.128 per array and column (the 64-byte swizzle spreads the eight lanes of a phase over all banks), packed
 // subtractions, and one 8-byte store per four rows.  The consumer mapping (rows q, q + 8; columns 4 cg ..) reads them back with
 // conflict-free 16-bit loads.  (A first version kept two bits per texel in registers: 64 scalar loads and ~350 instructions per item.)
-__device__ __forceinline__ unsigned st_sign_bf16x2(float a, float b) {
-    // (sign(b) as bf16) << 16 | (sign(a) as bf16): bf16(+-1) = 0x3f80 / 0xbf80, 0 for a zero difference
-    const unsigned ua = __float_as_uint(a), ub = __float_as_uint(b);
-    const unsigned sa = (a != 0.f) ? ((ua >> 16) & 0x8000u) | 0x3f80u : 0u;
-    const unsigned sb_ = (b != 0.f) ? ((ub >> 16) & 0x8000u) | 0x3f80u : 0u;
-    return sa | (sb_ << 16);
+__device__ __forceinline__ unsigned st_sign_bf16x2(const float2 d) {
+    // (sign(d.y) as bf16) << 16 | (sign(d.x) as bf16): the high halves of the two floats are d truncated to bf16 (zero only for a zero or
+    // flushed difference), and sign(x) = min(max(x * 2^127, -1), 1) in packed bf16 -- four instructions per texel pair where the
+    // select form took fourteen
+    unsigned h, w;
+    asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(h) : "r"(__float_as_uint(d.x)), "r"(__float_as_uint(d.y)));
+    asm("{\n\t.reg .b32 t;\n\tmul.rn.bf16x2 t, %1, %2;\n\tmax.bf16x2 t, t, %3;\n\tmin.bf16x2 %0, t, %4;\n\t}"
+        : "=r"(w) : "r"(h), "r"(0x7f007f00u), "r"(0xbf80bf80u), "r"(0x3f803f80u));
+    return w;
 }
 template <typename L>
 __device__ __forceinline__ void st_loss_signs(unsigned sbase, int lane) {
@@ -406,7 +409,8 @@ __device__ __forceinline__ void st_loss_signs(unsigned sbase, int lane) {
         for (int ch = 0; ch < 4; ++ch) {
             const unsigned a = row + (((unsigned)ch ^ sw) << 4);
             const float4 o = st_lds128(a + L::off_go), m = st_lds128(a + L::off_gs);
-            const unsigned w0 = st_sign_bf16x2(o.x - m.x, o.y - m.y), w1 = st_sign_bf16x2(o.z - m.z, o.w - m.w);
+            const unsigned w0 = st_sign_bf16x2(__fadd2_rn(make_float2(o.x, o.y), neg2(make_float2(m.x, m.y))));
+            const unsigned w1 = st_sign_bf16x2(__fadd2_rn(make_float2(o.z, o.w), neg2(make_float2(m.z, m.w))));
             asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + L::off_sgn + (unsigned)c * L::sgn_pitch + (unsigned)ch * 8u), "r"(w0), "r"(w1) : "memory");
         }
     }
@@ -445,13 +449,15 @@ __device__ __forceinline__ void st_tile(unsigned sbase, int j, unsigned tm, unsi
         float2 o[4], s[4];
         ld_nat(L::off_go, o);
         ld_nat(L::off_gs, s);
+        float2 lacc2 = bc(0.f);
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-            const float dx_ = o[v].x - s[v].x, dy_ = o[v].y - s[v].y;
-            lacc += fabsf(dx_) + fabsf(dy_);
-            gp[v] = make_float2(sign_times(dx_, 0x3f800000u), sign_times(dy_, 0x3f800000u));      // d loss / d softor (unit)
+            const float2 d = __fadd2_rn(o[v], neg2(s[v]));
+            gp[v] = make_float2(sign_times(d.x, 0x3f800000u), sign_times(d.y, 0x3f800000u));      // d loss / d softor (unit)
+            lacc2 = __ffma2_rn(d, gp[v], lacc2);                                                    // |d| = d * sign(d), exact
             gs[v] = neg2(gp[v]);
         }
+        lacc += lacc2.x + lacc2.y;
         if (tm == 0u) return;
         if (SUM_T) {
             // d loss / d sum at this texel = -sign(softor - sum) at the mirrored texel (st_loss_signs)
