@@ -865,7 +865,13 @@ static WtConsts wt_consts(const ffb_splat_desc* d, const Plan& p) {
     fc.hs = (float)p.H_s + 0.5f;
     fc.ho = (float)p.H_o + 0.5f;
     fc.c1 = 1.00000011920928955078125f;      // 1 + 2^-23
-    fc.disc2 = (float)((double)d->sigma * sqrt(20.723265836946414));      // (d2 / sigma)^2 = ln(1e9)
+    // backward tile culling: a tile whose nearest texel centre has g < 1e-7 is skipped.  Measured at config 3 against fp64
+    // (scripts/grad_precision.py, scripts/gpu_cull.sh): error relative to the gradient norm 5.2e-7 at 1e-7 and 5.3e-7 at 1e-9 (the
+    // round-1 threshold) -- below the kernels' own rounding -- and 8.2e-7 at 1e-6; 7 % fewer (candidate, tile) visits than at 1e-9.
+    // Worst case (upstream of one sign, dropped ring all on one side): 170 texels x 3.5e-7 against one-sided sums of ~20, 1e-5 of a
+    // non-cancelling gradient's norm = a tenth of the parity tolerance.
+    fc.disc2 = (float)((double)d->sigma * sqrt(16.11809565095832));       // (d2 / sigma)^2 = ln(1e7)
+    if (const char* e = getenv("FFB_BWD_CULL_LN")) fc.disc2 = (float)((double)d->sigma * sqrt(atof(e)));   // dev switch: ln(1 / threshold)
     fc.disc2_f = (float)((double)d->sigma * sqrt(17.5) * 1.02);           // same margin as the exact soft-OR no-op radius h_o (make_plan)
     fc.near2 = (float)((double)d->sigma * sqrt(5.545177444479562));       // (d2 / sigma)^2 = ln(2^8)
     fc.s2 = (float)(sqrt(1.4426950408889634) / (double)d->sigma);

@@ -365,7 +365,7 @@ __device__ __forceinline__ WtMasks st_stage(const RasterParams& q, const WtConst
         const float ry2 = ry * ry;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            // a tile whose nearest texel centre has g < 1e-9 contributes nothing measurable to d/dP (weights g * d2 * (c - P))
+            // a tile whose nearest texel centre has g < 1e-7 contributes nothing measurable to d/dP (weights g * d2 * (c - P); wt_consts)
             const float xl = (float)(WT * i);
             const float rx = fmaxf(fmaxf(xl - px, px - (xl + (float)(WT - 1))), 0.f);
             const float rr = fmaf(rx, rx, ry2);

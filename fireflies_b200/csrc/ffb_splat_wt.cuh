@@ -76,7 +76,7 @@ constexpr int WB_WARPS = WB_CTA / 32;
 #define FFB_BWD_SKIP 0                    // backward: skip 16x4 row groups outside a candidate's row span (measured slower: the branches cost more than the skipped MUFUs)
 #endif
 #ifndef FFB_BWD_DISC
-#define FFB_BWD_DISC 1                    // backward: drop (candidate, tile) pairs whose nearest texel is beyond the radius where g < 1e-9
+#define FFB_BWD_DISC 1                    // backward: drop (candidate, tile) pairs whose nearest texel is beyond the radius where g < 1e-7 (wt_consts)
 #endif
 #ifndef FFB_ACC_FOLD
 #define FFB_ACC_FOLD 0                    // backward: fold the parked partial sums once more (1 KB less shared memory per warp, one more shuffle per candidate tile)
@@ -104,7 +104,7 @@ struct WtConsts {
     float thr_s, thr_o;                   // 4*H + 2 for the sum / soft-OR row masks
     float hs, ho;                         // H + 0.5 for the column predicates
     float c1;                             // 1 + 2^-23: keeps 1 - g away from 0 in the backward quotient
-    float disc2;                          // squared radius beyond which g < 1e-9 (backward tile culling)
+    float disc2;                          // squared radius beyond which g < 1e-7 (backward tile culling; wt_consts)
     float disc2_f;                        // squared radius beyond which g <= 2^-25 (forward tile culling: 1 - g == 1 exactly)
     float near2;                          // squared radius beyond which g < 2^-8 (backward: far tiles need no reciprocal)
     float s2, rs2;                        // sqrt(-K2) and its reciprocal: the backward's tables hold d^2 * s2, so g = 2^-(d2s^2)
@@ -159,7 +159,7 @@ struct WarpStage {
 
 // Which staged candidates touch which 16x16 tile: warp-uniform ballots, 16 bits per tile.
 struct WtMasks {
-    unsigned tb01, tb23;                  // touched (and, in the backward, inside the 1e-9 disc)
+    unsigned tb01, tb23;                  // touched (and, in the backward, inside the culling disc)
     unsigned nb01, nb23;                  // backward: near tiles (some g >= 2^-8)
 };
 __device__ __forceinline__ unsigned tile_mask(const WtMasks& mk, int j) {
@@ -233,7 +233,7 @@ __device__ __forceinline__ WtMasks stage_regs(Stage& s, const EntryRegs& e, int 
             if (rlo < 4 * i + 4 && rhi > 4 * i) gm |= 1u << i;
         }
         if (ACC ? FFB_BWD_DISC : FFB_FWD_DISC) {
-            // backward: a tile whose nearest texel centre has g < 1e-9 contributes nothing measurable to d/dP (weights
+            // backward: a tile whose nearest texel centre has g < 1e-7 contributes nothing measurable to d/dP (weights
             // g * d2 * (c - P)); corner tiles of the square window go.  Forward: the radius is where g <= 2^-25, i.e. where
             // the soft-OR factor 1 - g is exactly 1 and a sum term is below 3e-8 (half an ulp of a texel value of 0.5; the
             // reference's own dense and baked sums differ by 2.4e-7).

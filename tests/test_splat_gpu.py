@@ -446,10 +446,8 @@ def test_every_kernel_variant(R, want, sum_t):
                 close(o[b], So.detach())
                 tot = tot + (So * wO[b]).sum()
             tot.backward()
-            # a soft-OR window cut where g is still 0.37 (no = 2): measured 1.08e-4 of the point's norm against the fp64 closed form on
-            # one point of this case (scripts/variant_precision.py; every other variant is below 0.17e-4) -- open, see DESIGN.md 7
             for g in grads:
-                close_grad(g[b], p.grad, rtol=2e-4 if (no == 2 and not ws) else 1e-4)
+                close_grad(g[b], p.grad)
 
 
 def test_l1_loss_single_pair_matches_torch(R):
