@@ -649,13 +649,18 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_st(RasterParams q, 
     float accr = 0.f;                                       // lane (k, h): d/dp_h of candidate k, summed over the super tile
     float lacc = 0.f;                                       // LOSS: this lane's share of sum |softor - sum|
     __syncwarp();
+    unsigned tbits = mk.tb01, nbits = mk.nb01;             // tile masks shifted out as the tiles go by (all zero without candidates)
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
         if (j == 0) tma::mbar_wait(bar, TWO ? 1u : 0u);
-        if (j == 2) tma::mbar_wait(bar + 1, TWO ? 1u : 0u);
-        const unsigned tm = grad ? tile_mask(mk, j) : 0u;
+        if (j == 2) {
+            tma::mbar_wait(bar + 1, TWO ? 1u : 0u);
+            tbits = mk.tb23; nbits = mk.nb23;
+        }
+        const unsigned tm = tbits & 0xffffu, nm = nbits & 0xffffu;
+        tbits >>= 16; nbits >>= 16;
         if (!LOSS && tm == 0u) continue;
-        st_tile<SUM, SOFTOR, SUM_T, MSK, MODE>(sbase, j, tm, near_mask(mk, j), sbase + L::off_rec, pd, accr, lacc, ln, lane, fc);
+        st_tile<SUM, SOFTOR, SUM_T, MSK, MODE>(sbase, j, tm, nm, sbase + L::off_rec, pd, accr, lacc, ln, lane, fc);
     }
     if (grad) st_flush(q, st_scale(q, fc, lane) * (LOSS ? q.loss_inv : 1.f), pd, accr, lane, n, b, idx);
     if (LOSS) {
@@ -770,6 +775,7 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_stp(RasterParams q,
         StPend pd = {0.f, 0.f, 0};
         float accr = 0.f, lacc = 0.f;
         __syncwarp();
+        unsigned tbits = mk.tb01, nbits = mk.nb01;
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
             if (j == 0) tma::mbar_wait(bar, TWO ? 1u : phase);
@@ -782,10 +788,12 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_stp(RasterParams q,
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(q.entries + (size_t)(q.shared_pattern ? 0 : nx.b) * q.cap + nbeg + lane));
                 }
                 tma::mbar_wait(bar + 1, TWO ? 1u : phase);
+                tbits = mk.tb23; nbits = mk.nb23;
             }
-            const unsigned tm = tile_mask(mk, j);
+            const unsigned tm = tbits & 0xffffu, nm = nbits & 0xffffu;
+            tbits >>= 16; nbits >>= 16;
             if (!LOSS && tm == 0u) continue;
-            st_tile<SUM, SOFTOR, SUM_T, MSK, MODE>(sbase, j, tm, near_mask(mk, j), sbase + L::off_rec, pd, accr, lacc, ln, lane, fc);
+            st_tile<SUM, SOFTOR, SUM_T, MSK, MODE>(sbase, j, tm, nm, sbase + L::off_rec, pd, accr, lacc, ln, lane, fc);
         }
         __syncwarp();
         if (more) st_issue_half<SUM, SOFTOR, SUM_T, MODE>(st_smem, bar + 1, 1, nx.bx * (4 * WT), nx.sty * WT, nx.b, &tm_gs, &tm_go, &tm_sv, &tm_ot, TWO);
