@@ -960,17 +960,24 @@ static int launch_bwd_st(KP persistent, K oneshot, KO overflow, const RasterPara
     if (B > 65535 || q.tgy > 65535) return fail_arg(FFB_E_LIMIT, "splat: B or the tile rows exceed the grid limit (65535)");
     if (smem_ovf > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(overflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ovf));
     const long long items = (long long)q.T * B;
-    // The persistent form is ~5 % faster in isolation (0.524 against 0.554 ms per 64 samples) but its step times scatter: on a 4-GPU box
-    // some rank's backward takes ~0.6 ms longer in most steps, and a synchronous step waits for the slowest rank -- 4.36-4.49 ms per
-    // step against 3.88 ms with the one-shot form, which shows no scatter at all (profiles/r02t; one GPU, sustained: 4.11 against
-    // 4.15 ms, scripts/bench_ab.py).  One-shot is therefore the default; FFB_SPLAT_BWD_PERSIST=1 selects the persistent form.
+    // Three launch forms of the same item loop (dense patterns; sparse ones -- !q.eager -- always take the one-shot kernel):
+    //   chunk   (default): a one-warp CTA walks FFB_SPLAT_BWD_CHUNK (8) consecutive items with the two-stage request pipeline of the
+    //           persistent kernel; the hardware block scheduler balances the 131 k CTAs of a config-3 launch.  1.91 ms per 256 samples
+    //           inside the bench step against 2.05 for the one-shot form (whose warp slots stay empty ~2 of every ~9 us) and 2.6-2.7 for
+    //           the counter form (scripts/gpu_forms.sh, profiles/r02x/forms.log);
+    //   counter (FFB_SPLAT_BWD_PERSIST=1): 148 x 20 resident warps claim items from a global counter.  Fastest of the three in
+    //           isolation until the chunks came (1.96 ms), but inside the step its times scatter (single steps 1.2 ms late, some rank
+    //           of a 4-GPU box late in most steps: profiles/r02t) -- kept for the fused-loss mode, which showed no scatter (r02s);
+    //   oneshot (FFB_SPLAT_BWD_PERSIST=0): one CTA per item.
     const char* e = getenv("FFB_SPLAT_BWD_PERSIST");
-    // The loss mode keeps the persistent form: its two request rounds per item need the cross-item prefetch, and its steps do not
-    // scatter (4 GPUs end to end: 4.45 ms per step against 4.41 ms on one, profiles/r02s).
-    const bool persist = (e ? e[0] == '1' : prefer_persistent) && q.eager != 0;
+    int chunk = prefer_persistent ? 0 : 8;
+    if (e && e[0] == '1') chunk = 0;
+    if (const char* c = getenv("FFB_SPLAT_BWD_CHUNK")) chunk = atoi(c) > 0 ? atoi(c) : 0;   // static chunks of consecutive items per CTA
+    const bool persist = !(e && e[0] == '0') && q.eager != 0;
     if (persist && items < 0x7fffffffLL) {
         unsigned* counter = nullptr;
-        if (int rc = st_counter_slot(st, &counter)) return rc;
+        if (chunk == 0)
+            if (int rc = st_counter_slot(st, &counter)) return rc;
         static int occ = 0;                                 // per instantiation (the function is a template)
         if (occ == 0) {
             if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -984,8 +991,6 @@ static int launch_bwd_st(KP persistent, K oneshot, KO overflow, const RasterPara
         long long grid = (long long)kNumSMs * (occ < 20 ? occ : 20);
         if (const char* g = getenv("FFB_SPLAT_BWD_GRID")) grid = atoll(g) > 0 ? atoll(g) : grid;
         if (grid > items) grid = items;
-        int chunk = 0;
-        if (const char* c = getenv("FFB_SPLAT_BWD_CHUNK")) chunk = atoi(c) > 0 ? atoi(c) : 0;   // static chunks of consecutive items per CTA
         if (chunk > 0) grid = (items + chunk - 1) / chunk;
         persistent<<<(unsigned)grid, 32, smem, st>>>(q, fc, m.gs, m.go, m.sv, m.ot, (int)items, counter, chunk);
     } else {
