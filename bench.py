@@ -396,7 +396,8 @@ def main_ours(args):
     alg = {"fwd": B * (8 * hw + 8 * N_POINTS), "bwd": B * (8 * hw + 16 * N_POINTS), "randomize": B * 24 * V_MESH}
     dom = max(("fwd", "bwd"), key=lambda p: ph_ms[p])
     traffic, traffic_src = None, None
-    kname = {"fwd": "splat_fwd_tma", "bwd": "splat_bwd_st"}[dom]
+    # dense patterns run the backward as splat_bwd_stp (chunks of consecutive items per CTA; FFB_SPLAT_BWD_PERSIST=0: splat_bwd_st)
+    kname = {"fwd": "splat_fwd_tma", "bwd": "splat_bwd_st" if os.environ.get("FFB_SPLAT_BWD_PERSIST") == "0" else "splat_bwd_stp"}[dom]
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath):                   # DRAM bytes per sample from the committed ncu --set full capture, scaled to this launch
         tj = json.load(open(tpath))

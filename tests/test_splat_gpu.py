@@ -415,6 +415,39 @@ def test_tma_and_plain_kernels_agree(R, monkeypatch):
     close_grad(p.grad, po.grad)
 
 
+def test_backward_launch_forms(R, monkeypatch):
+    """The dense-pattern backward has three launch forms of one item loop: chunks of consecutive items per CTA (default 8; 7 leaves a
+    ragged last chunk of the 128 items), resident warps with a work counter, one CTA per item.  Each against the fp64 closed form,
+    with given upstream gradients and through the fused L1 loss."""
+    gen = torch.Generator().manual_seed(77)
+    B, ts, sigma = 2, [256, 256], 49.0
+    pts = (torch.rand(B, 120, 2, generator=gen) * 0.96 + 0.02)
+    gS, gO = torch.randn(B, ts[0], ts[1], generator=gen), torch.randn(B, ts[1], ts[0], generator=gen)
+    monkeypatch.setenv("FFB_SPLAT_EAGER", "1")            # dense-pattern path whatever the density heuristic says
+    plan = R._SplatPlan(pts.cuda(), B, sigma, ts[0], ts[1], 4, 5)
+    s, o = plan.forward(pts.cuda(), True, True, True)
+    ana, ana_l1, loss_ref = [], [], []
+    for b in range(B):
+        ana.append(O.splat_grad_analytic(pts[b], sigma, ts, gS[b].T, gO[b], 4, 5))
+        diff = o[b].cpu() - s[b].cpu()                     # loss = mean |softor - sum (as stored)|, rasterization.py:589-599
+        sg = torch.sign(diff) / diff.numel()
+        ana_l1.append(O.splat_grad_analytic(pts[b], sigma, ts, (-sg).T, sg, 4, 5))
+        loss_ref.append(diff.abs().double().mean())
+    for form in ({}, {"FFB_SPLAT_BWD_CHUNK": "7"}, {"FFB_SPLAT_BWD_PERSIST": "1"}, {"FFB_SPLAT_BWD_PERSIST": "0"}):
+        for k in ("FFB_SPLAT_BWD_CHUNK", "FFB_SPLAT_BWD_PERSIST"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in form.items():
+            monkeypatch.setenv(k, v)
+        d = plan.backward(pts.cuda(), gS.cuda(), gO.cuda(), True).cpu()
+        fused = plan.backward_l1(pts.cuda(), s, o, True)
+        assert fused is not None
+        loss, dl = fused
+        for b in range(B):
+            close_grad(d[b], ana[b])
+            close(loss[b].cpu(), loss_ref[b].float(), rtol=1e-5, atol=1e-7)
+            close_grad(dl[b].cpu(), ana_l1[b])
+
+
 @pytest.mark.parametrize("want", [("sum",), ("softor",), ("sum", "softor")])
 @pytest.mark.parametrize("sum_t", [False, True])
 def test_every_kernel_variant(R, want, sum_t):
