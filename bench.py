@@ -21,6 +21,7 @@ gradient.  `cpu_baseline` / `--impl reference` time the CPU port of the referenc
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import sys
@@ -68,7 +69,7 @@ class ClockSampler:
                0x100: "display_clock_setting"}
 
     def __init__(self, index):
-        self.samples, self.reasons, self.max_mhz, self._stop, self._t = [], set(), None, threading.Event(), None
+        self.samples, self.reasons, self.max_mhz, self._stop, self._t, self._go = [], set(), None, threading.Event(), None, threading.Event()
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -79,6 +80,11 @@ class ClockSampler:
             self.nv = None
 
     def _run(self):
+        # Sampling starts when the main thread has enqueued the timed steps (go()): the device then still has all but the first
+        # fraction of a step in front of it, so every sample is taken under load, and no NVML call (a driver round trip of up to
+        # milliseconds) competes with the kernel launches of the first timed step, where the host is not yet ahead of the device
+        # -- about one run in six showed that step's first phases 4-20 ms late (profiles/r02x/forms.log).
+        self._go.wait()
         while not self._stop.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
@@ -95,8 +101,12 @@ class ClockSampler:
             self._t = threading.Thread(target=self._run, daemon=True)
             self._t.start()
 
+    def go(self):
+        self._go.set()
+
     def stop(self):
         if self._t is not None:
+            self._go.set()
             self._stop.set()
             self._t.join()
         s = sorted(self.samples)
@@ -371,11 +381,17 @@ def main_ours(args):
     clocks.start()
     l0 = nat.launch_count
     e0, e1 = ev(), ev()
+    # like timeit: no cyclic garbage collection inside a timed region.  The host enqueues the first timed step with an empty device
+    # queue behind it; a generation-2 collection there (milliseconds with torch's object graph loaded) starves the device once.
+    gc.collect()
+    gc.disable()
     barrier()
     e0.record()
     for i in range(K):
         one_step(Wm + i, marks[i])
     e1.record()
+    gc.enable()
+    clocks.go()                                            # the device is K steps behind the host here: samples are under load
     barrier()
     par.check_folders()                                    # the peer-memory allreduce reports a missing peer instead of hanging
     total_ms = max_over_ranks(e0.elapsed_time(e1), device)
@@ -449,12 +465,15 @@ def main_ours(args):
         torch.cuda.empty_cache()
         for i in range(2):
             step_obj.step_host(pts_host, out_host, loss_host, sample0=i * B * world + first)
+        gc.collect()
+        gc.disable()
         barrier()
         t0 = time.perf_counter()
         for i in range(K):
             step_obj.step_host(pts_host, out_host, loss_host, sample0=(2 + i) * B * world + first)
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0, device)
+        gc.enable()
         e2e = {"value": B * world * K / dt, "unit": UNIT, "h2d_bytes_per_step": pts_host.numel() * 4,
                "d2h_bytes_per_step": (out_host.numel() + loss_host.numel()) * 4, "ms_per_step": dt / K * 1e3,
                "path": "PatternStep.step_host: pinned pattern H2D -> randomise (side stream) | bin + splat fwd -> fused L1(softor,sum) "

@@ -243,24 +243,30 @@ class SceneBatch:
         mt.voff[mt.M] = self._voff[mt.M]
         return mt
 
-    def randomize(self, B: int, sample0: Optional[int] = None, variates: Optional[torch.Tensor] = None) -> BatchResult:
+    def randomize(self, B: int, sample0: Optional[int] = None, variates: Optional[torch.Tensor] = None,
+                  out: Optional[BatchResult] = None) -> BatchResult:
         """B scene samples.  Train mode: sample ``sample0 + b`` depends only on (seed, sample0 + b, sampler row)
         -- identical for any batch split or rank layout.  Eval mode: B successive ``sample_eval`` steps per
-        sampler.  ``variates`` ([B,S,3]) switches to injected mode (parity tests)."""
+        sampler.  ``variates`` ([B,S,3]) switches to injected mode (parity tests).  ``out``: a ``BatchResult`` of an earlier
+        call with the same ``B`` whose tensors are overwritten and returned (no allocation: a loop that runs ahead of the
+        device otherwise makes the caching allocator grow by one vertex buffer per step in flight, and a ``cudaMalloc`` of
+        B x V x 12 bytes blocks the host for 10-90 ms -- ``scripts/stall_probe2.py``)."""
         L = nat.lib()
+        if out is not None and (out.sampled.shape[0] != B or out.batch is not self):
+            raise ValueError("SceneBatch.randomize: `out` must be a BatchResult of this SceneBatch with the same B")
         train = bool(self.scene._train)
         mode = nat.MODE_INJECTED if variates is not None else (nat.MODE_TRAIN if train else nat.MODE_EVAL)
         if sample0 is None:
             sample0 = self._next_sample
             self._next_sample += B
         S, E = self.S, self.E
-        sampled = torch.empty((B, max(S, 1), 3), dtype=torch.float32, device=self.device)
+        sampled = out.sampled if out is not None else torch.empty((B, max(S, 1), 3), dtype=torch.float32, device=self.device)
         if S:
             v = None if variates is None else nat.require_cuda(variates.contiguous(), torch.float32, "variates")
             nat.check(L.ffb_sample(self.sampler_table.data_ptr(), S, B, mode, self.seed, int(sample0), nat.ptr(v),
                                    sampled.data_ptr(), nat.stream()), "ffb_sample")
             nat.count()
-        world = torch.empty((B, max(E, 1), 4, 4), dtype=torch.float32, device=self.device)
+        world = out.world if out is not None else torch.empty((B, max(E, 1), 4, 4), dtype=torch.float32, device=self.device)
         if E:
             nat.check(L.ffb_compose_world(self.entity_table.data_ptr(), E, B, sampled.data_ptr(), S, world.data_ptr(),
                                           nat.stream()), "ffb_compose_world")
@@ -286,10 +292,13 @@ class SceneBatch:
                                                   nat.MODE_TRAIN if train else nat.MODE_EVAL, self.seed, int(sample0),
                                                   idx.data_ptr(), nat.stream()), "ffb_sample_anim_index")
                 nat.count()
-            verts = torch.empty((B, self.Vtot, 3), dtype=torch.float32, device=self.device)
+            verts = out.vertices if out is not None and out.vertices is not None else torch.empty((B, self.Vtot, 3), dtype=torch.float32, device=self.device)
             nat.check(L.ffb_transform_vertices(C.byref(mt), self.verts.data_ptr(), E, B, nat.ptr(idx), world.data_ptr(),
                                                verts.data_ptr(), nat.stream()), "ffb_transform_vertices")
             nat.count()
+        if out is not None:
+            out._host = None                                # the cached host copy belongs to the overwritten samples
+            return out
         return BatchResult(world, sampled, verts, self)
 
 
@@ -301,11 +310,13 @@ class PatternStep:
     ``loss = L1(softored, summed)``, backward to ``points`` -- for B samples at once, preceded by the batched scene
     randomisation.  With ``upstream`` the loss stage is skipped and the given texture gradients (e.g. from the
     renderer's backward pass) are consumed instead.  The only collective is the allreduce of ``d loss/d points``.
+    The ``BatchResult`` a step returns stays valid through the next step and is reused by the one after
+    (``rotate_results=False``: a fresh one per step).
     """
 
     def __init__(self, n_points: int, texture_size, sigma: float, batch: int, scene_batch: Optional[SceneBatch] = None,
                  num_std_sum: int = 4, num_std_softor: int = 5, sum_transposed: bool = True, per_sample_points: bool = True,
-                 device="cuda", process_group=None, fuse_loss: bool = True):
+                 device="cuda", process_group=None, fuse_loss: bool = True, rotate_results: bool = True):
         self.N, self.B = int(n_points), int(batch)
         self.ts0, self.ts1 = R._ts(texture_size)
         self.sigma = float(sigma)
@@ -320,6 +331,10 @@ class PatternStep:
         self._pat_dev = torch.empty((self.N, 2), dtype=torch.float32, device=self.device)
         self.last = None
         self._side: Optional[torch.cuda.Stream] = None
+        # rotate_results: the randomised samples are written into two alternating BatchResults (the one returned by step i is
+        # overwritten by step i + 2); False: fresh tensors every step, like SceneBatch.randomize
+        self._res_ring = [None, None] if rotate_results else None
+        self._res_turn = 0
 
     def _allreduce(self, t: torch.Tensor) -> None:
         from .parallel import allreduce_sum_
@@ -351,7 +366,14 @@ class PatternStep:
             with torch.cuda.stream(self._side):
                 nvtx.range_push("ffb.randomize")
                 mark("randomize0", self._side)
-                res = self.scene_batch.randomize(self.B, sample0=sample0)
+                # two rotating result buffers: the samples of step i stay valid through step i + 1 (`self.last`), nothing is
+                # allocated per step.  Safe without further events: this stream has just waited for everything the calling
+                # stream has enqueued, which includes every consumer of the buffer written two steps ago.
+                ring = self._res_ring
+                slot = self._res_turn = (self._res_turn + 1) % len(ring) if ring is not None else 0
+                res = self.scene_batch.randomize(self.B, sample0=sample0, out=ring[slot] if ring is not None else None)
+                if ring is not None:
+                    ring[slot] = res
                 mark("randomize1", self._side)
                 nvtx.range_pop()
         if points.dim() == 2:

@@ -145,6 +145,40 @@ def test_config4_sharded_step_equals_whole_batch(ff):
     close(dp_parts[0] + dp_parts[1], dp_w, rtol=1e-4, atol=1e-4 * float(dp_w.abs().max()))
 
 
+def test_pattern_step_rotates_two_result_buffers(ff):
+    """PatternStep writes the randomised samples into two alternating BatchResults (no allocation per step): the result of step i is
+    intact after step i + 1, reused by step i + 2, and equal to what a fresh-tensor step (rotate_results=False) produces."""
+    N, ts, sigma, B = 200, [256, 192], 36.0, 6
+    gen = torch.Generator().manual_seed(9)
+    pattern = (torch.rand(N, 2, generator=gen) * 0.9 + 0.05).cuda()
+    verts = torch.rand(400, 3, generator=gen) * 2 - 1
+
+    def scene():
+        sc = ff.Scene(fm.FakeParams())
+        m = ff.entity.Mesh("mesh-R", verts.cuda())
+        m.rotate_y(-1.0, 1.0)
+        m.translate_z(-0.5, 0.5)
+        sc._meshes.append(m)
+        sc.train()
+        return sc
+
+    rot = ff.PatternStep(N, ts, sigma, B, scene_batch=scene().batch(seed=5))
+    fresh = ff.PatternStep(N, ts, sigma, B, scene_batch=scene().batch(seed=5), rotate_results=False)
+    res, copies = [], []
+    for i in range(4):
+        _, dp_r, r = rot.forward_backward(pattern, sample0=i * B)
+        _, dp_f, f = fresh.forward_backward(pattern, sample0=i * B)
+        assert torch.equal(r.vertices, f.vertices) and torch.equal(r.world, f.world) and torch.equal(r.sampled, f.sampled)
+        close(dp_r, dp_f, rtol=1e-5, atol=1e-6 * float(dp_f.abs().max()))
+        res.append(r); copies.append(r.vertices.clone())
+        if i >= 1:
+            assert torch.equal(res[i - 1].vertices, copies[i - 1])          # the previous step's samples are still there
+    assert res[2] is res[0] and res[3] is res[1] and res[1] is not res[0]
+    assert torch.equal(res[0].vertices, copies[2])                          # step 2 reused step 0's buffers
+    with pytest.raises(ValueError):
+        rot.scene_batch.randomize(B + 1, out=res[0])
+
+
 def test_shared_pattern_step_equals_per_sample_step(ff):
     """One pattern for all scenes of a step: the folded-gradient path (one forward, upstream gradients summed over the samples,
     one backward) gives the per-sample path's result."""
