@@ -966,8 +966,8 @@ static int launch_bwd_st(KP persistent, K oneshot, KO overflow, const RasterPara
     //           inside the bench step against 2.05 for the one-shot form (whose warp slots stay empty ~2 of every ~9 us) and 2.6-2.7 for
     //           the counter form (scripts/gpu_forms.sh, profiles/r02x/forms.log);
     //   counter (FFB_SPLAT_BWD_PERSIST=1): 148 x 20 resident warps claim items from a global counter.  Fastest of the three in
-    //           isolation until the chunks came (1.96 ms), but inside the step its times scatter (single steps 1.2 ms late, some rank
-    //           of a 4-GPU box late in most steps: profiles/r02t) -- kept for the fused-loss mode, which showed no scatter (r02s);
+    //           isolation until the chunks came (1.96 ms), but the slowest inside the step (2.07-2.24 ms next to 1.98 for the chunks,
+    //           profiles/r02x/forms.log) -- kept for the fused-loss mode, where it is the fastest;
     //   oneshot (FFB_SPLAT_BWD_PERSIST=0): one CTA per item.
     const char* e = getenv("FFB_SPLAT_BWD_PERSIST");
     int chunk = prefer_persistent ? 0 : 8;
