@@ -287,7 +287,9 @@ class SceneBatch:
                                         torch.tensor(hi, dtype=torch.int32, device=self.device))
                     self._anim_range_key = key
                 amin, amax = self._anim_range
-                idx = torch.empty((B, M), dtype=torch.int32, device=self.device)
+                idx = getattr(out, "_anim_idx", None) if out is not None else None
+                if idx is None or tuple(idx.shape) != (B, M):
+                    idx = torch.empty((B, M), dtype=torch.int32, device=self.device)
                 nat.check(L.ffb_sample_anim_index(amin.data_ptr(), amax.data_ptr(), self._anim_cur.data_ptr(), M, B,
                                                   nat.MODE_TRAIN if train else nat.MODE_EVAL, self.seed, int(sample0),
                                                   idx.data_ptr(), nat.stream()), "ffb_sample_anim_index")
@@ -298,8 +300,11 @@ class SceneBatch:
             nat.count()
         if out is not None:
             out._host = None                                # the cached host copy belongs to the overwritten samples
+            out._anim_idx = idx
             return out
-        return BatchResult(world, sampled, verts, self)
+        res = BatchResult(world, sampled, verts, self)
+        res._anim_idx = idx                                 # kept for reuse through `out=`
+        return res
 
 
 class PatternStep:
