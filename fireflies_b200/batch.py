@@ -272,9 +272,9 @@ class SceneBatch:
                                           nat.stream()), "ffb_compose_world")
             nat.count()
         verts = None
+        idx = None
         if self.meshes:
             mt = self._mesh_table(train)
-            idx = None
             if any(a is not None for a in self._anim_meshes):
                 M = len(self.meshes)
                 lo = [(a._animation_sampler._min_integer_train if train else a._animation_sampler._min_integer_eval) if a else 0
