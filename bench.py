@@ -83,9 +83,10 @@ class ClockSampler:
         # Sampling starts when the main thread has enqueued the timed steps (go()): the device then still has all but the first
         # fraction of a step in front of it, so every sample is taken under load, and no NVML call (a driver round trip of up to
         # milliseconds) competes with the kernel launches of the first timed step, where the host is not yet ahead of the device
-        # -- about one run in six showed that step's first phases 4-20 ms late (profiles/r02x/forms.log).
+        # (this was not the cause of the stalled steps of DESIGN.md 6 -- the caching allocator was -- but it keeps the driver out of
+        # the launch path of the step where a host delay reaches the device).
         self._go.wait()
-        while not self._stop.is_set():
+        while True:                                          # at least one sample, however short the timed region
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
                 mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
@@ -94,7 +95,8 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.005)
+            if self._stop.wait(0.005):
+                break
 
     def start(self):
         if self.nv is not None:
