@@ -450,122 +450,148 @@ __global__ void __launch_bounds__(PREP_CTA, FFB_PREP_MINB) prepare_kernel(PrepPa
 // Super tiles with more than WCH candidates (clustered patterns; they go to the overflow kernels anyway) are completed by a second
 // pass into the global index list; the first word of their (unused) slot row is the fill cursor.
 struct Rec16 { float p0, p1; uint32_t ur, uc; };
-__global__ void __launch_bounds__(PREP_CTA, 1) prepare_onepass_kernel(PrepParams q) {
+// BANDED: the tile grid does not fit the shared arrays at once (textures beyond ~2048^2): the records are computed once, then the
+// grid is binned in bands of q.band_rows tile rows, each with the same five phases.  !BANDED is the single-band kernel of config 3
+// with the record computation merged into the slot pass.
+// 48 registers: a resident CTA leaves a quarter of the register file to the CTAs of the scene randomisation, which runs next to it
+template <bool BANDED>
+__global__ void __maxnreg__(48) prepare_onepass_kernel(PrepParams q) {
     extern __shared__ __align__(16) int sm[];
-    int* cnt = sm;                                   // [T] candidates per super tile
-    int* off = sm + q.T;                             // [T] exclusive offsets
-    const int slot0 = (2 * q.T + 3) & ~3;            // 16-byte aligned rows
-    unsigned short* slot = reinterpret_cast<unsigned short*>(sm + slot0);                         // [T][WCH]
-    Rec16* recs = reinterpret_cast<Rec16*>(sm + slot0 + q.T * (WCH / 2));                          // [N]
+    const int T = q.T;
+    const int Tb = BANDED ? q.band_rows * q.tgx : T; // super tiles per band = capacity of the shared arrays
+    int* cnt = sm;                                   // [Tb] candidates per super tile
+    int* off = sm + Tb;                              // [Tb] exclusive offsets (into the sample's entry array)
+    const int slot0 = (2 * Tb + 3) & ~3;             // 16-byte aligned rows
+    unsigned short* slot = reinterpret_cast<unsigned short*>(sm + slot0);                         // [Tb][WCH]
+    Rec16* recs = reinterpret_cast<Rec16*>(sm + slot0 + Tb * (WCH / 2));                           // [N]
     __shared__ int warp_tot[32];
-    __shared__ int n_ovf;
-    const int bin = blockIdx.x, tid = threadIdx.x, T = q.T;
+    __shared__ int n_ovf, band_base;
+    const int bin = blockIdx.x, tid = threadIdx.x;
     const float* pts = q.pts + (long long)bin * q.stride;
     int* tile_off = q.tile_off + (size_t)bin * (T + 1);
     int* list = q.list + (size_t)bin * q.cap;
     Entry* entries = q.entries + (size_t)bin * q.cap;
     const bool bs = q.baked_s != 0;
     const int baked = (bs || !q.baked_o) ? (int)bs : 1, half = (bs || !q.baked_o) ? q.half_s : q.half_o;
-    for (int i = tid; i < T; i += PREP_CTA) cnt[i] = 0;
-    if (tid == 0) n_ovf = 0;
-    __syncthreads();
-    // 1. records + slots
-    for (int n = tid; n < q.N; n += PREP_CTA) {
+    auto record = [&](int n) {                       // the point's record (+ the reference's slice triples)
         const float2 xy = reinterpret_cast<const float2*>(pts)[n];
         int win[12];
         const PointRec rec = make_rec(q, xy.x, xy.y, q.windows ? win : nullptr);
-        const int c_lo = rec.uc & 0xffff, c_hi = rec.uc >> 16, r_lo = rec.ur & 0xffff, r_hi = rec.ur >> 16;
-        recs[n] = Rec16{rec.p0, rec.p1, rec.ur, rec.uc};
+        const Rec16 r = Rec16{rec.p0, rec.p1, rec.ur, rec.uc};
+        recs[n] = r;
         if (q.windows) {
             int* w = q.windows + ((size_t)bin * q.N + n) * 12;
 #pragma unroll
             for (int k = 0; k < 12; ++k) w[k] = win[k];
         }
-        if (c_hi > c_lo && r_hi > r_lo)
-            for (int ty = r_lo / WT; ty <= (r_hi - 1) / WT; ++ty)                 // super tiles are 4 WT x WT texels (make_plan, fast path)
-                for (int tx = c_lo / (4 * WT); tx <= (c_hi - 1) / (4 * WT); ++tx) {
-                    const int t = ty * q.tgx + tx;
-                    const int pos = atomicAdd(&cnt[t], 1);
-                    if (pos < WCH) slot[t * WCH + pos] = (unsigned short)n;
-                }
-    }
-    __syncthreads();
-    // 2. exclusive scan over the super tiles
-    const int per = (T + PREP_CTA - 1) / PREP_CTA;
-    const int beg = min(tid * per, T), end = min(beg + per, T);
-    int local = 0;
-    for (int i = beg; i < end; ++i) local += cnt[i];
-    int incl = local;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((tid & 31) >= o) incl += v;
-    }
-    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
-    __syncthreads();
-    if (tid < 32) {
-        int v = warp_tot[tid], sc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, sc, o);
-            if (tid >= o) sc += t;
-        }
-        warp_tot[tid] = sc - v;
-    }
-    __syncthreads();
-    int run = warp_tot[tid >> 5] + incl - local;
-    for (int i = beg; i < end; ++i) {
-        const int c = cnt[i];
-        off[i] = run; tile_off[i] = run;
-        run += c;
-        if (c > WCH) {
-            q.ovf[1 + atomicAdd(q.ovf, 1)] = bin * T + i;
-            atomicAdd(&n_ovf, 1);
-            *reinterpret_cast<int*>(slot + i * WCH) = 0;       // becomes the fill cursor of pass 3
-        }
-    }
-    if (tid == PREP_CTA - 1) tile_off[T] = run;
-    __syncthreads();
-    // 3. overflow super tiles: the complete lists into the global list
-    if (n_ovf > 0) {
+        return r;
+    };
+    if (BANDED)
+        for (int n = tid; n < q.N; n += PREP_CTA) record(n);
+    if (tid == 0) band_base = 0;
+    const int rows = BANDED ? q.band_rows : q.tgy;
+#pragma unroll 1
+    for (int ty0 = 0; ty0 < q.tgy; ty0 += rows) {
+        const int ty1 = BANDED ? min(ty0 + rows, q.tgy) : q.tgy;
+        const int nt = BANDED ? (ty1 - ty0) * q.tgx : T, t0 = ty0 * q.tgx;
+        for (int i = tid; i < nt; i += PREP_CTA) cnt[i] = 0;
+        if (tid == 0) n_ovf = 0;
+        __syncthreads();
+        // 1. (records +) slots
         for (int n = tid; n < q.N; n += PREP_CTA) {
-            const Rec16 r = recs[n];
+            const Rec16 r = BANDED ? recs[n] : record(n);
             const int c_lo = r.uc & 0xffff, c_hi = r.uc >> 16, r_lo = r.ur & 0xffff, r_hi = r.ur >> 16;
-            if (c_hi > c_lo && r_hi > r_lo)
-                for (int ty = r_lo / WT; ty <= (r_hi - 1) / WT; ++ty)                 // super tiles are 4 WT x WT texels (make_plan, fast path)
+            if (c_hi > c_lo && r_hi > r_lo) {
+                int ya = r_lo / WT, yb = (r_hi - 1) / WT;                             // super tiles are 4 WT x WT texels (make_plan, fast path)
+                if (BANDED) { ya = max(ya, ty0); yb = min(yb, ty1 - 1); }
+                for (int ty = ya; ty <= yb; ++ty)
                     for (int tx = c_lo / (4 * WT); tx <= (c_hi - 1) / (4 * WT); ++tx) {
-                        const int t = ty * q.tgx + tx;
-                        if (cnt[t] > WCH) {
-                            const int pos = off[t] + atomicAdd(reinterpret_cast<int*>(slot + t * WCH), 1);
-                            if (pos < q.cap) list[pos] = n;
-                        }
+                        const int t = (ty - ty0) * q.tgx + tx;
+                        const int pos = atomicAdd(&cnt[t], 1);
+                        if (pos < WCH) slot[t * WCH + pos] = (unsigned short)n;
                     }
+            }
         }
         __syncthreads();
-    }
-    // 4. every super tile's list ordered by point index, in place; the overflow lists are ranked straight into their entries
-    for (int t = tid; t < T; t += PREP_CTA) {
-        const int c = cnt[t], b = off[t];
-        if (c > WCH) {
-            const int e = min(b + c, q.cap);
-            for (int i = b; i < e; ++i) {
-                const int v = list[i];
-                int rank = 0;
-                for (int j = b; j < e; ++j) rank += list[j] < v;
-                const Rec16 r = recs[v];
-                uint4* dst = reinterpret_cast<uint4*>(entries + b + rank);
-                dst[0] = make_uint4(__float_as_uint(r.p0), __float_as_uint(r.p1), __float_as_uint(origin_axis_f(r.p0, baked, half)),
-                                    __float_as_uint(origin_axis_f(r.p1, baked, half)));
-                dst[1] = make_uint4(r.ur, r.uc, (unsigned)v, 0u);
-            }
-        } else if (c > 1) {
-            uint4* row = reinterpret_cast<uint4*>(slot + t * WCH);
-            const uint4 w0 = row[0], w1 = row[1];
-            const unsigned w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-            int l[16];
+        // 2. exclusive scan over the band's super tiles
+        const int per = (nt + PREP_CTA - 1) / PREP_CTA;
+        const int beg = min(tid * per, nt), end = min(beg + per, nt);
+        int local = 0;
+        for (int i = beg; i < end; ++i) local += cnt[i];
+        int incl = local;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) l[i] = i < c ? (int)((w[i >> 1] >> (16 * (i & 1))) & 0xffffu) : 0x7fffffff;
-            // Batcher's odd-even merge sort on the 16 registers (63 compare-exchanges); empty slots (INT_MAX) sink to the end
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((tid & 31) >= o) incl += v;
+        }
+        if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 32) {
+            int v = warp_tot[tid], sc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, sc, o);
+                if (tid >= o) sc += t;
+            }
+            warp_tot[tid] = sc - v;
+        }
+        __syncthreads();
+        int run = band_base + warp_tot[tid >> 5] + incl - local;
+        for (int i = beg; i < end; ++i) {
+            const int c = cnt[i];
+            off[i] = run; tile_off[t0 + i] = run;
+            run += c;
+            if (c > WCH) {
+                q.ovf[1 + atomicAdd(q.ovf, 1)] = bin * T + t0 + i;
+                atomicAdd(&n_ovf, 1);
+                *reinterpret_cast<int*>(slot + i * WCH) = 0;       // becomes the fill cursor of pass 3
+            }
+        }
+        __syncthreads();
+        if (tid == PREP_CTA - 1) band_base = run;                   // the last thread's running total covers the whole band
+        // 3. overflow super tiles: the complete lists into the global list
+        if (n_ovf > 0) {
+            for (int n = tid; n < q.N; n += PREP_CTA) {
+                const Rec16 r = recs[n];
+                const int c_lo = r.uc & 0xffff, c_hi = r.uc >> 16, r_lo = r.ur & 0xffff, r_hi = r.ur >> 16;
+                if (c_hi > c_lo && r_hi > r_lo) {
+                    int ya = r_lo / WT, yb = (r_hi - 1) / WT;
+                    if (BANDED) { ya = max(ya, ty0); yb = min(yb, ty1 - 1); }
+                    for (int ty = ya; ty <= yb; ++ty)
+                        for (int tx = c_lo / (4 * WT); tx <= (c_hi - 1) / (4 * WT); ++tx) {
+                            const int t = (ty - ty0) * q.tgx + tx;
+                            if (cnt[t] > WCH) {
+                                const int pos = off[t] + atomicAdd(reinterpret_cast<int*>(slot + t * WCH), 1);
+                                if (pos < q.cap) list[pos] = n;
+                            }
+                        }
+                }
+            }
+            __syncthreads();
+        }
+        // 4. every super tile's list ordered by point index, in place; the overflow lists are ranked straight into their entries
+        for (int t = tid; t < nt; t += PREP_CTA) {
+            const int c = cnt[t], b = off[t];
+            if (c > WCH) {
+                const int e = min(b + c, q.cap);
+                for (int i = b; i < e; ++i) {
+                    const int v = list[i];
+                    int rank = 0;
+                    for (int j = b; j < e; ++j) rank += list[j] < v;
+                    const Rec16 r = recs[v];
+                    uint4* dst = reinterpret_cast<uint4*>(entries + b + rank);
+                    dst[0] = make_uint4(__float_as_uint(r.p0), __float_as_uint(r.p1), __float_as_uint(origin_axis_f(r.p0, baked, half)),
+                                        __float_as_uint(origin_axis_f(r.p1, baked, half)));
+                    dst[1] = make_uint4(r.ur, r.uc, (unsigned)v, 0u);
+                }
+            } else if (c > 1) {
+                uint4* row = reinterpret_cast<uint4*>(slot + t * WCH);
+                const uint4 w0 = row[0], w1 = row[1];
+                const unsigned w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                int l[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) l[i] = i < c ? (int)((w[i >> 1] >> (16 * (i & 1))) & 0xffffu) : 0x7fffffff;
+                // Batcher's odd-even merge sort on the 16 registers (63 compare-exchanges); empty slots (INT_MAX) sink to the end
 #define FFB_CE(a, c_) { const int lo_ = min(l[a], l[c_]), hi_ = max(l[a], l[c_]); l[a] = lo_; l[c_] = hi_; }
             FFB_CE(0,1) FFB_CE(2,3) FFB_CE(0,2) FFB_CE(1,3) FFB_CE(1,2) FFB_CE(4,5) FFB_CE(6,7) FFB_CE(4,6) FFB_CE(5,7) FFB_CE(5,6)
             FFB_CE(0,4) FFB_CE(2,6) FFB_CE(2,4) FFB_CE(1,5) FFB_CE(3,7) FFB_CE(3,5) FFB_CE(1,2) FFB_CE(3,4) FFB_CE(5,6)
@@ -575,31 +601,35 @@ __global__ void __launch_bounds__(PREP_CTA, 1) prepare_onepass_kernel(PrepParams
             FFB_CE(1,9) FFB_CE(5,13) FFB_CE(5,9) FFB_CE(3,11) FFB_CE(7,15) FFB_CE(7,11) FFB_CE(3,5) FFB_CE(7,9) FFB_CE(11,13)
             FFB_CE(1,2) FFB_CE(3,4) FFB_CE(5,6) FFB_CE(7,8) FFB_CE(9,10) FFB_CE(11,12) FFB_CE(13,14)
 #undef FFB_CE
-            unsigned o[8];
+                unsigned o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = ((unsigned)l[2 * i] & 0xffffu) | ((unsigned)l[2 * i + 1] << 16);
-            row[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            row[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                for (int i = 0; i < 8; ++i) o[i] = ((unsigned)l[2 * i] & 0xffffu) | ((unsigned)l[2 * i + 1] << 16);
+                row[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                row[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            }
         }
+        __syncthreads();
+        // 5. entries {p0, p1, f0, f1 | ur, uc, idx, 0}: two super tiles per warp step, lane (hp, i) writes entry i of super tile t + hp --
+        // 32 contiguous bytes per lane, one contiguous run per warp (consecutive super tiles are consecutive in the entry array)
+        const int lane = tid & 31, wid = tid >> 5, i = lane & 15, hp = lane >> 4;
+        const int tiles_per_warp = (((nt + 31) / 32) + 1) & ~1;
+        const int tb = wid * tiles_per_warp, te = min(tb + tiles_per_warp, nt);
+#pragma unroll 2
+        for (int t = tb + hp; t < te; t += 2) {
+            const int c = cnt[t], b = off[t];
+            if (c <= WCH && i < c && b + i < q.cap) {
+                const unsigned idx = slot[t * WCH + i];
+                const Rec16 r = recs[idx];
+                uint4* dst = reinterpret_cast<uint4*>(entries + b + i);
+                dst[0] = make_uint4(__float_as_uint(r.p0), __float_as_uint(r.p1), __float_as_uint(origin_axis_f(r.p0, baked, half)),
+                                    __float_as_uint(origin_axis_f(r.p1, baked, half)));
+                dst[1] = make_uint4(r.ur, r.uc, idx, 0u);
+            }
+        }
+        if (BANDED) __syncthreads();                               // the next band reuses the shared arrays
     }
     __syncthreads();
-    // 5. entries {p0, p1, f0, f1 | ur, uc, idx, 0}: two super tiles per warp step, lane (hp, i) writes entry i of super tile t + hp --
-    // 32 contiguous bytes per lane, one contiguous run per warp (consecutive super tiles are consecutive in the entry array)
-    const int lane = tid & 31, wid = tid >> 5, i = lane & 15, hp = lane >> 4;
-    const int tiles_per_warp = (((T + 31) / 32) + 1) & ~1;
-    const int tb = wid * tiles_per_warp, te = min(tb + tiles_per_warp, T);
-#pragma unroll 2
-    for (int t = tb + hp; t < te; t += 2) {
-        const int c = cnt[t], b = off[t];
-        if (c <= WCH && i < c && b + i < q.cap) {
-            const unsigned idx = slot[t * WCH + i];
-            const Rec16 r = recs[idx];
-            uint4* dst = reinterpret_cast<uint4*>(entries + b + i);
-            dst[0] = make_uint4(__float_as_uint(r.p0), __float_as_uint(r.p1), __float_as_uint(origin_axis_f(r.p0, baked, half)),
-                                __float_as_uint(origin_axis_f(r.p1, baked, half)));
-            dst[1] = make_uint4(r.ur, r.uc, idx, 0u);
-        }
-    }
+    if (tid == 0) tile_off[T] = band_base;
 }
 
 struct RasterParams {
@@ -1305,14 +1335,35 @@ extern "C" int ffb_splat_prepare(const ffb_splat_desc* d, const float* pts, void
     if (p.fast) {
         FFB_CUDA(cudaMemsetAsync(q.ovf, 0, sizeof(int), as_stream(stream)));
         {
-            // one-pass form: one shared-memory atomic per (point, super tile) pair instead of two
-            const size_t smem_one = (((size_t)p.T * 2 + 3) & ~(size_t)3) * sizeof(int) + (size_t)p.T * WCH * sizeof(unsigned short) + (size_t)d->N * sizeof(Rec16);
+            // one-pass form: one shared-memory atomic per (point, super tile) pair instead of two.  Whole grid at once when it fits
+            // (config 3: 4096 super tiles + 4096 records = 224 KB), otherwise in bands of tile rows.
+            auto smem_for = [&](size_t tiles) {
+                return ((tiles * 2 + 3) & ~(size_t)3) * sizeof(int) + tiles * WCH * sizeof(unsigned short) + (size_t)d->N * sizeof(Rec16);
+            };
+            const size_t budget = 226 * 1024;
             const char* e1 = getenv("FFB_PREP_ONEPASS");
-            if (p.band_rows == p.tgy && d->N <= 65535 && smem_one <= 226 * 1024 && !(e1 && e1[0] == '0')) {
-                FFB_CUDA(cudaFuncSetAttribute(prepare_onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_one));
-                prepare_onepass_kernel<<<p.Bp, PREP_CTA, smem_one, as_stream(stream)>>>(q);
+            const bool on = !(e1 && e1[0] == '0') && d->N <= 65535;
+            const char* eb = getenv("FFB_PREP_BAND_ROWS");      // tests: force the banded kernel with this many tile rows per band
+            if (on && !eb && smem_for((size_t)p.T) <= budget) {
+                const size_t sm1 = smem_for((size_t)p.T);
+                FFB_CUDA(cudaFuncSetAttribute(prepare_onepass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+                prepare_onepass_kernel<false><<<p.Bp, PREP_CTA, sm1, as_stream(stream)>>>(q);
                 FFB_CUDA(cudaGetLastError());
                 return 0;
+            }
+            if (on && smem_for((size_t)p.tgx) <= budget) {
+                int rows = p.tgy;
+                while (rows > 1 && smem_for((size_t)rows * p.tgx) > budget) rows = (rows + 1) / 2;
+                if (eb && atoi(eb) > 0) rows = atoi(eb) < p.tgy ? atoi(eb) : p.tgy;
+                if (smem_for((size_t)rows * p.tgx) <= budget) {
+                    q.band_rows = rows;
+                    const size_t smb = smem_for((size_t)rows * p.tgx);
+                    FFB_CUDA(cudaFuncSetAttribute(prepare_onepass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+                    prepare_onepass_kernel<true><<<p.Bp, PREP_CTA, smb, as_stream(stream)>>>(q);
+                    FFB_CUDA(cudaGetLastError());
+                    return 0;
+                }
+                q.band_rows = p.band_rows;
             }
         }
         const size_t smem_rec = (((size_t)p.band_rows * p.tgx * 2 + 3) & ~(size_t)3) * sizeof(int) + (size_t)d->N * sizeof(PointRec);

@@ -197,7 +197,8 @@ def test_clustered_points_take_the_overflow_path(R, batched):
 
 @pytest.mark.parametrize("clustered", [False, True])
 def test_binning_forms_agree_bitwise(R, monkeypatch, clustered):
-    """The one-pass binning kernel (slot lists in shared memory, warp-wide entry stores) and the count/scan/fill kernel it replaces
+    """The one-pass binning kernel (slot lists in shared memory, warp-wide entry stores; whole grid at once, or in bands of tile rows
+    for grids that do not fit the shared arrays) and the count/scan/fill kernel it replaces
     order every candidate list by point index, so the outputs are identical to the bit -- also with overflowing lists and
     with a tile count that is not a multiple of four (shared-memory rows stay 16-byte aligned)."""
     gen = torch.Generator().manual_seed(5)
@@ -207,15 +208,18 @@ def test_binning_forms_agree_bitwise(R, monkeypatch, clustered):
         pts[:150] = 0.45 + 0.1 * pts[:150]
     gS, gO = torch.randn(1, ts[1], ts[0], generator=gen).cuda(), torch.randn(1, ts[1], ts[0], generator=gen).cuda()
     res = []
-    for flag in ("1", "0"):
+    for flag, band in (("1", None), ("0", None), ("1", "3")):      # one-pass; count / scan / fill; one-pass in bands of 3 tile rows
         monkeypatch.setenv("FFB_PREP_ONEPASS", flag)
+        if band:
+            monkeypatch.setenv("FFB_PREP_BAND_ROWS", band)
         plan = R._SplatPlan(pts.cuda(), 1, sigma, ts[0], ts[1], 4, 5)
         s, o = plan.forward(pts.cuda(), True, True, False)
         d = plan.backward(pts.cuda(), gS, gO, False)
         res.append((s.clone(), o.clone(), d.clone()))
-    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
-    # the per-point gradient is a sum of per-tile partials added with float atomics: same terms, arrival order not fixed
-    assert (res[0][2] - res[1][2]).norm() <= 1e-6 * res[1][2].norm()
+    for other in res[1:]:
+        assert torch.equal(res[0][0], other[0]) and torch.equal(res[0][1], other[1])
+        # the per-point gradient is a sum of per-tile partials added with float atomics: same terms, arrival order not fixed
+        assert (res[0][2] - other[2]).norm() <= 1e-6 * other[2].norm()
     close(res[0][0][0], O.baked_sum(pts, sigma, ts))
 
 
