@@ -223,6 +223,41 @@ def test_binning_forms_agree_bitwise(R, monkeypatch, clustered):
     close(res[0][0][0], O.baked_sum(pts, sigma, ts))
 
 
+def test_large_grid_takes_the_banded_binning(R, monkeypatch):
+    """4096 x 2048 texels = 8192 super tiles: more than the one-pass binning kernel holds in shared memory at once, so it bins in
+    bands of tile rows (chosen by the library).  Outputs identical to the count / scan / fill kernel's, which the smaller cases pin
+    against the oracle; column sums of the sum texture against the closed form for a few points."""
+    gen = torch.Generator().manual_seed(19)
+    ts, sigma = [4096, 2048], 100.0
+    pts = (torch.rand(1500, 2, generator=gen) * 0.98 + 0.01)
+    gS, gO = torch.randn(1, ts[1], ts[0], generator=gen).cuda(), torch.randn(1, ts[1], ts[0], generator=gen).cuda()
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("FFB_PREP_ONEPASS", flag)
+        plan = R._SplatPlan(pts.cuda(), 1, sigma, ts[0], ts[1], 4, 5)
+        s, o = plan.forward(pts.cuda(), True, True, False)
+        res.append((s.clone(), o.clone(), plan.backward(pts.cuda(), gS, gO, False).clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert (res[0][2] - res[1][2]).norm() <= 1e-6 * res[1][2].norm()
+    assert float(res[0][0].sum()) > 0 and torch.isfinite(res[0][2]).all()
+    # one check against the closed form (fp64) on a crop: the 64 x 64 texels around the first point, sum texture with its windows
+    P = pts[0] * torch.tensor([ts[0], ts[1]], dtype=torch.float32)
+    c0, r0 = int(P[0]) - 32, int(P[1]) - 32
+    c0, r0 = max(0, min(c0, ts[0] - 64)), max(0, min(r0, ts[1] - 64))
+    near = ((pts * torch.tensor([ts[0], ts[1]], dtype=torch.float32) - P).abs().max(dim=1).values < 120)
+    cols = torch.arange(c0, c0 + 64, dtype=torch.float64).view(1, 1, -1)
+    rows = torch.arange(r0, r0 + 64, dtype=torch.float64).view(1, -1, 1)
+    Pn = (pts[near].float() * torch.tensor([ts[0], ts[1]], dtype=torch.float32)).double()
+    u = ((cols - Pn[:, 0].view(-1, 1, 1)) ** 2 + (rows - Pn[:, 1].view(-1, 1, 1)) ** 2) / sigma
+    g = torch.exp(-u * u)
+    H = O.footprint_size(sigma, 4)[1]
+    f0 = torch.floor(Pn[:, 0].float() - H).double().view(-1, 1, 1) + H
+    f1 = torch.floor(Pn[:, 1].float() - H).double().view(-1, 1, 1) + H
+    inside = ((cols - f0).abs() <= H) & ((rows - f1).abs() <= H)
+    want = (g * inside).sum(0).float()
+    close(res[0][0][0, r0:r0 + 64, c0:c0 + 64].cpu(), want)
+
+
 def test_saturated_softor_backward(R, monkeypatch):
     """220 points inside a 20x20 texel patch at sigma = 100: the soft-OR saturates (prod(1 - g) runs from 1e-40 to 1e-2 across the
     patch), every super tile overflows.  The production backward rebuilds the product like torch.prod's backward; the earlier
