@@ -669,13 +669,15 @@ __global__ void __launch_bounds__(32, FFB_ST_MINB) splat_bwd_st(RasterParams q, 
     }
 }
 
-// Persistent form (dense patterns: nearly every super tile has candidates).  The one-shot kernel keeps only ~19 of its 24 warp slots per
-// SM filled (a one-warp CTA lives ~7 us and its slot stays empty ~2 us until the next CTA starts), and every warp begins with two
-// dependent global loads (list bounds, then records) before it can do anything.  Here 148 x 24 warps stay resident and claim
-// (super tile, sample) items from a global counter, two items ahead; the two halves of the upstream blocks sit behind one mbarrier each,
-// and the next item's left half is requested as soon as tiles 0 and 1 of the current one are done, its right half after tiles 2 and 3 --
-// the same 8 KB of shared memory hold a two-stage pipeline.  The next item's list bounds are loaded a whole item ahead, its records are
-// pulled into L1 half an item ahead.
+// Pipelined item loop (dense patterns: nearly every super tile has candidates).  The one-shot kernel keeps only ~19 of its 24 warp slots
+// per SM filled (a one-warp CTA lives ~7 us and its slot stays empty ~2 us until the next CTA starts), and every warp begins with two
+// dependent global loads (list bounds, then records) before it can do anything.  Here a warp walks several (super tile, sample) items:
+// the two halves of the upstream blocks sit behind one mbarrier each, and the next item's left half is requested as soon as tiles 0
+// and 1 of the current one are done, its right half after tiles 2 and 3 -- the same 8 KB of shared memory hold a two-stage pipeline.
+// The next item's list bounds are loaded a whole item ahead, its records are pulled into L1 half an item ahead.  Two ways to hand out
+// the items (launch_bwd_st): chunk > 0 -- the CTA walks `chunk` consecutive items and exits, the hardware block scheduler balances the
+// launch (the default, chunk = 8); chunk == 0 -- 148 x 20 resident warps claim items from a global counter, two items ahead (the
+// fused-loss mode).
 struct StItem {
     int b, sty, bx;
 };
