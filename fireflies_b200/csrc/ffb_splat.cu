@@ -1020,7 +1020,9 @@ static int launch_bwd_st(KP persistent, K oneshot, KO overflow, const RasterPara
         if (occ == 0) {
             if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             FFB_CUDA(cudaFuncSetAttribute(persistent, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            FFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, persistent, 32, smem));
+            // the dynamic shared memory of a CTA starts on a 1 KB boundary (extern __shared__ __align__(1024)): query with the rounded size,
+            // otherwise the loss mode's 10.8 KB report 20 CTAs per SM where 19 fit and 148 CTAs of the counter form start only at the end
+            FFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, persistent, 32, (smem + 1023) & ~(size_t)1023));
             if (occ < 1) occ = 1;
         }
         // 20 resident warps per SM, not the 24 that fit: inside the full step on a board at its power cap 148 x 20 measured
