@@ -1020,8 +1020,9 @@ static int launch_bwd_st(KP persistent, K oneshot, KO overflow, const RasterPara
         if (occ == 0) {
             if (smem > 48 * 1024) FFB_CUDA(cudaFuncSetAttribute(persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             FFB_CUDA(cudaFuncSetAttribute(persistent, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            // the dynamic shared memory of a CTA starts on a 1 KB boundary (extern __shared__ __align__(1024)): query with the rounded size,
-            // otherwise the loss mode's 10.8 KB report 20 CTAs per SM where 19 fit and 148 CTAs of the counter form start only at the end
+            // queried with the size rounded up to the next KB, which stands in for the 1 KB the system reserves per CTA: with the exact
+            // 10.8 KB of the loss mode the query reported 20 or more CTAs per SM where ncu shows 19 resident (profiles/r02z/ncu_loss_summary.txt),
+            // and 148 CTAs of the counter form started only when the others were done
             FFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, persistent, 32, (smem + 1023) & ~(size_t)1023));
             if (occ < 1) occ = 1;
         }
