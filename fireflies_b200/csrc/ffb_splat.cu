@@ -1029,7 +1029,9 @@ static int launch_bwd_st(KP persistent, K oneshot, KO overflow, const RasterPara
         // 20 resident warps per SM, not the 24 that fit: inside the full step on a board at its power cap 148 x 20 measured
         // 4.11 ms per step against 4.32 (x 24, with 4.9 ms outliers when the power controller overshoots), 4.32 (x 16), 4.15 for
         // the one-shot form and 4.41 for round 1's kernel (scripts/bench_ab.py, 5 alternating rounds of 10 steps on one box)
-        long long grid = (long long)kNumSMs * (occ < 20 ? occ : 20);
+        // the loss mode (int8 mirrored signs: 22 CTAs per SM fit): 2.31 / 2.26 / 2.22 ms per 256 samples with 19 / 20 / 22 resident warps per SM
+        const int cap_sm = prefer_persistent ? 22 : 20;
+        long long grid = (long long)kNumSMs * (occ < cap_sm ? occ : cap_sm);
         if (const char* g = getenv("FFB_SPLAT_BWD_GRID")) grid = atoll(g) > 0 ? atoll(g) : grid;
         if (grid > items) grid = items;
         if (chunk > 0) grid = (items + chunk - 1) / chunk;

@@ -41,6 +41,9 @@
 #ifndef FFB_ST_TRIPLE
 #define FFB_ST_TRIPLE 1                   // three-candidate tiles: all exponentials in registers, exclusive products are the other two factors
 #endif
+#ifndef FFB_ST_SIGN8
+#define FFB_ST_SIGN8 1                    // loss mode: mirrored signs as int8 (1 KB per warp, 22 resident warps) instead of bf16 (2.5 KB, 19)
+#endif
 #ifndef FFB_ST_DYN
 #define FFB_ST_DYN 1                      // persistent kernel: items claimed from a global counter (1) or walked with a fixed stride (0)
 #endif
@@ -60,9 +63,10 @@ struct StSmem {
     static constexpr int off_bar = n_box * ST_BOX;
     static constexpr int off_rec = off_bar + 16;
     static constexpr int off_idx = off_rec + WCH * 16;
-    // LOSS + SUM_T: signs of (softor - sum) at the mirrored index as bf16 (-1, 0, +1), [column 64][row 16] with a 40-byte pitch
+    // LOSS + SUM_T: -sign(softor - sum) at the mirrored index, [column 64][row 16]: int8 with a 16-byte pitch (FFB_ST_SIGN8), or the sign
+    // as bf16 (-1, 0, +1) with a 40-byte pitch
     static constexpr int off_sgn = off_idx + WCH * 4;
-    static constexpr int sgn_pitch = 40;
+    static constexpr int sgn_pitch = FFB_ST_SIGN8 ? 16 : 40;
     static constexpr int bytes = off_sgn + ((MODE == ST_LOSS && SUM_T) ? 4 * WT * sgn_pitch : 0);
 };
 
@@ -411,9 +415,23 @@ __device__ __forceinline__ void st_loss_signs(unsigned sbase, int lane) {
             const float4 o = st_lds128(a + L::off_go), m = st_lds128(a + L::off_gs);
             const unsigned w0 = st_sign_bf16x2(__fadd2_rn(make_float2(o.x, o.y), neg2(make_float2(m.x, m.y))));
             const unsigned w1 = st_sign_bf16x2(__fadd2_rn(make_float2(o.z, o.w), neg2(make_float2(m.z, m.w))));
-            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + L::off_sgn + (unsigned)c * L::sgn_pitch + (unsigned)ch * 8u), "r"(w0), "r"(w1) : "memory");
+            if (FFB_ST_SIGN8) {
+                // four bf16 signs -> four int8 of the NEGATED sign (what the consumer needs): top bytes 0x3f / 0xbf / 0x00 (0x80 for -0)
+                unsigned T;
+                asm("prmt.b32 %0, %1, %2, 0x7531;" : "=r"(T) : "r"(w0), "r"(w1));
+                const unsigned nz = T & 0x01010101u, sg = (T >> 7) & nz;
+                const unsigned out = (nz * 0xffu) ^ (sg * 0xfeu);                          // +1 -> 0xff, -1 -> 0x01, 0 -> 0x00
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + L::off_sgn + (unsigned)c * L::sgn_pitch + (unsigned)ch * 4u), "r"(out) : "memory");
+            } else {
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + L::off_sgn + (unsigned)c * L::sgn_pitch + (unsigned)ch * 8u), "r"(w0), "r"(w1) : "memory");
+            }
         }
     }
+}
+__device__ __forceinline__ float st_lds_s8(unsigned a) {
+    int v;
+    asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a));
+    return (float)v;
 }
 __device__ __forceinline__ float st_lds_bf16(unsigned a) {
     unsigned short v;
@@ -461,11 +479,12 @@ __device__ __forceinline__ void st_tile(unsigned sbase, int j, unsigned tm, unsi
         if (tm == 0u) return;
         if (SUM_T) {
             // d loss / d sum at this texel = -sign(softor - sum) at the mirrored texel (st_loss_signs)
-            const unsigned t = sbase + L::off_sgn + (unsigned)(WT * j + 4 * (lane >> 3)) * L::sgn_pitch + 2u * (unsigned)(lane & 7);
+            const unsigned t = sbase + L::off_sgn + (unsigned)(WT * j + 4 * (lane >> 3)) * L::sgn_pitch + (FFB_ST_SIGN8 ? 1u : 2u) * (unsigned)(lane & 7);
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-                const unsigned a = t + (unsigned)(2 * (v & 1)) * L::sgn_pitch + (v >> 1) * 16u;
-                gs[v] = make_float2(-st_lds_bf16(a), -st_lds_bf16(a + L::sgn_pitch));
+                const unsigned a = t + (unsigned)(2 * (v & 1)) * L::sgn_pitch + (v >> 1) * (FFB_ST_SIGN8 ? 8u : 16u);
+                if (FFB_ST_SIGN8) gs[v] = make_float2(st_lds_s8(a), st_lds_s8(a + L::sgn_pitch));
+                else gs[v] = make_float2(-st_lds_bf16(a), -st_lds_bf16(a + L::sgn_pitch));
             }
         }
     } else {
